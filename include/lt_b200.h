@@ -1,0 +1,173 @@
+/*
+ * lt_b200.h -- C ABI of liblt_b200.so: the B200 (sm_100a) kernels behind the volumetric
+ * triangulation hot path of karfly/learnable-triangulation-pytorch.
+ *
+ * The reference is 100% Python/PyTorch: it has no FFI for this path.  Each entry point
+ * below replaces the PyTorch library calls of one reference call site (cited per function);
+ * the Python host code in learnable-triangulation-pytorch_b200/ binds them with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ *   - the caller owns all memory (incl. workspaces); nothing here allocates device memory;
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - return value: 0 on success, negative lt_status on failure; lt_last_error_string()
+ *     returns a thread-local description of the last failure;
+ *   - activation tensors are channels-last: [N][D][H][W][C] (2-D maps have D = 1);
+ *   - LT_FMT_F32 is plain float; LT_FMT_S32 is "split-bf16": channels in blocks of 32, each
+ *     block stored as 32 bf16 high parts followed by 32 bf16 low parts (x = hi + lo, 128 bytes
+ *     per block, same footprint as fp32) -- the tensor-core operand format.
+ */
+#ifndef LT_B200_H
+#define LT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum lt_status {
+  LT_OK = 0,
+  LT_ERR_INVALID = -1,     /* bad argument */
+  LT_ERR_CUDA = -2,        /* CUDA runtime/driver error at launch */
+  LT_ERR_UNSUPPORTED = -3  /* shape/format combination not implemented */
+};
+
+enum lt_format { LT_FMT_F32 = 0, LT_FMT_S32 = 1 };
+
+/* view aggregation of the unprojection, reference mvn/utils/op.py:150-164 */
+enum lt_agg { LT_AGG_SUM = 0, LT_AGG_MAX = 1, LT_AGG_SOFTMAX = 2, LT_AGG_CONF = 3 };
+
+/* conv implementation selector */
+enum lt_conv_impl {
+  LT_CONV_SIMT = 0, /* fp32 FFMA implicit GEMM (exact, any shape) */
+  LT_CONV_TC = 1,   /* tcgen05, split-bf16 3-term products (fp32-grade) */
+  LT_CONV_TC1 = 2   /* tcgen05, high parts only (plain bf16 precision, fast mode) */
+};
+
+/* residual placement in the conv epilogue */
+enum lt_residual { LT_RES_NONE = 0, LT_RES_BEFORE_RELU = 1, LT_RES_AFTER_RELU = 2 };
+
+int lt_version(void);
+const char* lt_last_error_string(void);
+
+/* Number of SMs / compute capability of the current device (host-side query; -1 if no device). */
+int lt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Coordinate volume.  Replaces triangulation.py:306-341 (meshgrid, affine to mm, rotation
+ * about the base point, optional CMU->H36M axis transfer), all samples in one launch.
+ *   position[B*3], center[B*3] : float32 casts of (base - side/2) and base
+ *   step[3]                    : float32 cast of side / (n - 1)
+ *   rot[B*9]                   : float32 row-major rotation per sample (identity in eval)
+ *   out[B][n][n][n][3]
+ * ---------------------------------------------------------------------------------------- */
+int lt_coord_volume_fwd(const float* position, const float* center, const float* step, const float* rot,
+                        float* out, int B, int n, int transfer_cmu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused unprojection + view aggregation.  Replaces op.unproject_heatmaps (op.py:99-166):
+ * per voxel, per view: project with proj (3x4), depth mask, bilinear sample of the feature map
+ * (grid_sample align_corners=True, zero padding, incl. the reference's x/H, y/W normalisation
+ * quirk op.py:128-129), then aggregate across views in registers.
+ *   features [B][V][h][w][C] channels-last float32
+ *   proj     [B][V][3][4]
+ *   coord    [B][nvox][3]
+ *   conf     [B][V][C] (LT_AGG_CONF) or NULL
+ *   out      [B][nvox][C] in out_format (LT_FMT_S32 needs C % 32 == 0)
+ * ---------------------------------------------------------------------------------------- */
+int lt_unproject_aggregate_fwd(const float* features, const float* proj, const float* coord, const float* conf,
+                               void* out, int out_format, int B, int V, int C, int h, int w, long nvox,
+                               int agg, void* stream);
+
+/* View-sharded variant (multi-GPU): this rank holds V_local views.  Writes float32 partials
+ *   LT_AGG_SOFTMAX: partial[B][2][nvox][C] = (sum_v s*exp(s), sum_v exp(s))   (unshifted)
+ *   LT_AGG_SUM/CONF: partial[B][1][nvox][C] = sum_v s (*conf);  LT_AGG_MAX: max_v s
+ * which one all-reduce (sum / max) over ranks completes; lt_unproject_finalize_fwd then divides
+ * (softmax) and converts to out_format. */
+int lt_unproject_partial_fwd(const float* features, const float* proj, const float* coord, const float* conf,
+                             float* partial, int B, int V_local, int C, int h, int w, long nvox,
+                             int agg, void* stream);
+int lt_unproject_finalize_fwd(const float* partial, void* out, int out_format, int B, int C, long nvox,
+                              int agg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Volumetric soft-argmax.  Replaces op.integrate_tensor_3d_with_coordinates (op.py:84-96).
+ *   logits: element (b, j, vox) at logits[b*batch_stride + vox*voxel_stride + j*chan_stride]
+ *           (channels-last: voxel_stride = Cpad, chan_stride = 1; NCDHW: voxel_stride = 1,
+ *           chan_stride = nvox)
+ *   coord [B][nvox][3]; multiplier is applied to the logits first (triangulation.py:353)
+ *   volumes_out [B][J][nvox] (may be NULL to skip the normalised-volume write)
+ *   keypoints_out [B][J][3]
+ *   workspace: lt_softargmax3d_workspace_bytes(B, J, nvox) bytes
+ *   softmax = 0 selects the ReLU variant (op.py:90-91).
+ * ---------------------------------------------------------------------------------------- */
+size_t lt_softargmax3d_workspace_bytes(int B, int J, long nvox);
+int lt_softargmax3d_fwd(const float* logits, long batch_stride, long voxel_stride, long chan_stride,
+                        const float* coord, float* volumes_out, float* keypoints_out,
+                        void* workspace, size_t workspace_bytes,
+                        int B, int J, long nvox, float multiplier, int softmax, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * N-d convolution as implicit GEMM with fused epilogue.  Replaces nn.Conv2d/Conv3d (+ folded
+ * BatchNorm, + residual add, + ReLU) call sites of pose_resnet.py:75-95,293-318 and
+ * v2v.py:7-42,146-160; transposed convs (pose_resnet.py:266-291 k4s2p1, v2v.py:54-66 k2s2)
+ * are issued as stride-phase sub-convolutions through the output mapping fields.
+ *   out[n, od*osd+ood, oh*osh+ooh, ow*osw+oow, co] =
+ *       act( scale[co] * sum_{kd,kh,kw,ci} in[n, od*sd-pd+kd, oh*sh-ph+kh, ow*sw-pw+kw, ci]
+ *                                          * W[kd,kh,kw,ci,co]  + shift[co]  (+ residual) )
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lt_conv_desc {
+  int N, ID, IH, IW, Cin;    /* input tensor dims (channels-last) */
+  int OD, OH, OW, Cout;      /* output positions computed by this call, output channels */
+  int KD, KH, KW;            /* filter taps */
+  int sd, sh, sw;            /* input stride */
+  int pd, ph, pw;            /* front zero padding */
+  int FD, FH, FW, FC;        /* full output tensor dims ([N][FD][FH][FW][FC]) */
+  int osd, osh, osw;         /* output coordinate scale (1 for plain conv, 2 for deconv phases) */
+  int ood, ooh, oow;         /* output coordinate offset */
+  int relu;                  /* apply max(x,0) */
+  int residual;              /* lt_residual; residual tensor has the output tensor's shape/format */
+  int in_format, out_format; /* lt_format */
+} lt_conv_desc;
+
+/* SIMT weights: float32 [KD*KH*KW][Cin][CoutW], CoutW = round_up(Cout, 4), zero padded.
+ * TC weights: see lt_conv_tc_pack_weights. */
+int lt_conv_nd_fwd(const lt_conv_desc* desc, const void* in, const void* weight, const float* scale,
+                   const float* shift, const void* residual, void* out, int impl, void* stream);
+
+/* Tensor-core (tcgen05) weight packing: float32 [taps][Cin][Cout] (host or device? -> DEVICE)
+ * to split-bf16 [taps][Cin/32][CoutP][64], CoutP = round_up(Cout, 16); Cin % 32 == 0. */
+size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout);
+int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Max pooling, channels-last (pose_resnet.py:208 3x3 s2 p1; v2v.py:51 2x2x2 s2).
+ * ---------------------------------------------------------------------------------------- */
+int lt_maxpool_fwd(const void* in, void* out, int format, int N, int ID, int IH, int IW, int C,
+                   int kd, int kh, int kw, int sd, int sh, int sw, int pd, int ph, int pw,
+                   int OD, int OH, int OW, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / format helpers.
+ * ---------------------------------------------------------------------------------------- */
+/* images [N][C][H][W] float32 -> [N][H][W][Cp] float32, channels >= C zero filled */
+int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, int Cp, void* stream);
+/* channels-last [P][C] float32 <-> split-bf16 (C % 32 == 0) */
+int lt_f32_to_s32(const float* in, void* out, long pixels, int C, void* stream);
+int lt_s32_to_f32(const void* in, float* out, long pixels, int C, void* stream);
+/* channels-last [N][P][Cs] (first C channels) -> channels-first [N][C][P] float32 */
+int lt_cl_to_cf_f32(const float* in, float* out, int N, long P, int Cs, int C, void* stream);
+
+/* Self test of the tcgen05/TMA GEMM core: D[M][N] = A[M][K] * B[N][K]^T with bf16 inputs
+ * (row-major, K contiguous), float32 output.  variant selects descriptor conventions
+ * (bring-up aid; 0 is the shipped one). */
+int lt_tc_gemm_selftest(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K,
+                        int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LT_B200_H */

@@ -1,0 +1,180 @@
+"""ctypes binding of liblt_b200.so (the C ABI declared in include/lt_b200.h).
+
+This is the stub a maintainer of the (pure-Python) reference would add to call the native
+kernels: raw device pointers + sizes in, status code out.  torch tensors are only used as
+device-memory owners (`data_ptr()`), never passed through the ABI.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
+
+FMT_F32, FMT_S32 = 0, 1
+AGG = {"sum": 0, "max": 1, "softmax": 2, "conf": 3, "conf_norm": 3}
+CONV_SIMT, CONV_TC, CONV_TC1 = 0, 1, 2
+RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU = 0, 1, 2
+
+c_int, c_long, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of `struct lt_conv_desc` (include/lt_b200.h) -- field order matters."""
+    _fields_ = [(n, c_int) for n in (
+        "N", "ID", "IH", "IW", "Cin",
+        "OD", "OH", "OW", "Cout",
+        "KD", "KH", "KW",
+        "sd", "sh", "sw",
+        "pd", "ph", "pw",
+        "FD", "FH", "FW", "FC",
+        "osd", "osh", "osw",
+        "ood", "ooh", "oow",
+        "relu", "residual", "in_format", "out_format")]
+
+
+# every symbol include/lt_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "lt_version": (c_int, []),
+    "lt_last_error_string": (ctypes.c_char_p, []),
+    "lt_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "lt_coord_volume_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_void_p]),
+    "lt_unproject_aggregate_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_long, c_int, c_void_p]),
+    "lt_unproject_partial_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_long, c_int, c_void_p]),
+    "lt_unproject_finalize_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
+    "lt_softargmax3d_workspace_bytes": (c_size_t, [c_int, c_int, c_long]),
+    "lt_softargmax3d_fwd": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    c_int, c_int, c_long, c_float, c_int, c_void_p]),
+    "lt_conv_nd_fwd": (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6 + [c_int, c_void_p]),
+    "lt_conv_tc_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
+    "lt_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "lt_f32_to_s32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    "lt_s32_to_f32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    "lt_cl_to_cf_f32": (c_int, [c_void_p, c_void_p, c_int, c_long, c_int, c_int, c_void_p]),
+    "lt_tc_gemm_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (building first if the .so is missing or stale and nvcc is present) the native library.
+
+    Fails loudly: there is no Python/CPU substitute for these kernels.
+    """
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH) or (os.path.exists("/usr/local/cuda/bin/nvcc") and not _build.is_current()):
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("liblt_b200.so is missing and could not be built -- the native CUDA extension is required")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().lt_last_error_string().decode()))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "native kernels need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+# ---- thin wrappers -------------------------------------------------------------------------------
+
+def device_info():
+    sm, major, minor = c_int(), c_int(), c_int()
+    _check(lib().lt_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "lt_device_info")
+    return sm.value, major.value, minor.value
+
+
+def coord_volume(position, center, step, rot, out, transfer_cmu=False):
+    B, n = out.shape[0], out.shape[1]
+    _check(lib().lt_coord_volume_fwd(_ptr(position), _ptr(center), _ptr(step), _ptr(rot), _ptr(out), B, n,
+                                     int(transfer_cmu), _stream()), "lt_coord_volume_fwd")
+
+
+def unproject_aggregate(features_cl, proj, coord, conf, out, out_format, agg):
+    B, V, h, w, C = features_cl.shape
+    nvox = coord.shape[1]
+    _check(lib().lt_unproject_aggregate_fwd(_ptr(features_cl), _ptr(proj), _ptr(coord), _ptr(conf), _ptr(out), out_format,
+                                            B, V, C, h, w, nvox, agg, _stream()), "lt_unproject_aggregate_fwd")
+
+
+def unproject_partial(features_cl, proj, coord, conf, partial, agg):
+    B, V, h, w, C = features_cl.shape
+    nvox = coord.shape[1]
+    _check(lib().lt_unproject_partial_fwd(_ptr(features_cl), _ptr(proj), _ptr(coord), _ptr(conf), _ptr(partial),
+                                          B, V, C, h, w, nvox, agg, _stream()), "lt_unproject_partial_fwd")
+
+
+def unproject_finalize(partial, out, out_format, B, C, nvox, agg):
+    _check(lib().lt_unproject_finalize_fwd(_ptr(partial), _ptr(out), out_format, B, C, nvox, agg, _stream()),
+           "lt_unproject_finalize_fwd")
+
+
+def softargmax3d(logits, batch_stride, voxel_stride, chan_stride, coord, volumes_out, keypoints_out, workspace,
+                 B, J, nvox, multiplier, softmax):
+    _check(lib().lt_softargmax3d_fwd(_ptr(logits), batch_stride, voxel_stride, chan_stride, _ptr(coord), _ptr(volumes_out),
+                                     _ptr(keypoints_out), _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                     B, J, nvox, float(multiplier), int(softmax), _stream()), "lt_softargmax3d_fwd")
+
+
+def softargmax3d_workspace_bytes(B, J, nvox):
+    return lib().lt_softargmax3d_workspace_bytes(B, J, nvox)
+
+
+def conv_nd(desc, inp, weight, scale, shift, residual, out, impl):
+    _check(lib().lt_conv_nd_fwd(ctypes.byref(desc), _ptr(inp), _ptr(weight), _ptr(scale), _ptr(shift), _ptr(residual),
+                                _ptr(out), impl, _stream()), "lt_conv_nd_fwd")
+
+
+def conv_tc_weight_bytes(taps, cin, cout):
+    return lib().lt_conv_tc_weight_bytes(taps, cin, cout)
+
+
+def conv_tc_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
+    _check(lib().lt_conv_tc_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), taps, cin, cout, _stream()), "lt_conv_tc_pack_weights")
+
+
+def maxpool(inp, out, fmt, N, ID, IH, IW, C, k, s, p, OD, OH, OW):
+    _check(lib().lt_maxpool_fwd(_ptr(inp), _ptr(out), fmt, N, ID, IH, IW, C, k[0], k[1], k[2], s[0], s[1], s[2],
+                                p[0], p[1], p[2], OD, OH, OW, _stream()), "lt_maxpool_fwd")
+
+
+def nchw_to_nhwc(inp, out, N, C, H, W, Cp):
+    _check(lib().lt_nchw_to_nhwc_f32(_ptr(inp), _ptr(out), N, C, H, W, Cp, _stream()), "lt_nchw_to_nhwc_f32")
+
+
+def f32_to_s32(inp, out, pixels, C):
+    _check(lib().lt_f32_to_s32(_ptr(inp), _ptr(out), pixels, C, _stream()), "lt_f32_to_s32")
+
+
+def s32_to_f32(inp, out, pixels, C):
+    _check(lib().lt_s32_to_f32(_ptr(inp), _ptr(out), pixels, C, _stream()), "lt_s32_to_f32")
+
+
+def cl_to_cf(inp, out, N, P, Cs, C):
+    _check(lib().lt_cl_to_cf_f32(_ptr(inp), _ptr(out), N, P, Cs, C, _stream()), "lt_cl_to_cf_f32")
+
+
+def tc_gemm_selftest(a_bf16, b_bf16, d, M, N, K, variant=0):
+    _check(lib().lt_tc_gemm_selftest(_ptr(a_bf16), _ptr(b_bf16), _ptr(d), M, N, K, variant, _stream()), "lt_tc_gemm_selftest")

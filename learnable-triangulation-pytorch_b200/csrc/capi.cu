@@ -1,0 +1,72 @@
+// C-ABI glue: error state, device queries and the conv dispatcher (include/lt_b200.h).
+#include "common.cuh"
+#include <string.h>
+
+namespace lt {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+int conv_simt_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                  const void* residual, void* out, void* stream);
+int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                      const void* residual, void* out, int terms, void* stream);
+
+}  // namespace lt
+
+extern "C" int lt_version(void) { return 100; }
+
+extern "C" const char* lt_last_error_string(void) { return lt::err_buf(); }
+
+extern "C" int lt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return lt::fail(LT_ERR_CUDA, "no CUDA device");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return lt::fail(LT_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return LT_OK;
+}
+
+extern "C" int lt_conv_nd_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale,
+                              const float* shift, const void* residual, void* out, int impl, void* stream) {
+  using namespace lt;
+  LT_REQUIRE(d && in && weight && scale && shift && out, "conv_nd: null pointer");
+  LT_REQUIRE(d->N > 0 && d->ID > 0 && d->IH > 0 && d->IW > 0 && d->Cin > 0, "conv_nd: bad input dims");
+  LT_REQUIRE(d->OD > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0, "conv_nd: bad output dims");
+  LT_REQUIRE(d->KD > 0 && d->KH > 0 && d->KW > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0, "conv_nd: bad filter/stride");
+  LT_REQUIRE(d->osd > 0 && d->osh > 0 && d->osw > 0, "conv_nd: bad output scale");
+  LT_REQUIRE((d->OD - 1) * d->osd + d->ood < d->FD && (d->OH - 1) * d->osh + d->ooh < d->FH &&
+                 (d->OW - 1) * d->osw + d->oow < d->FW && d->ood >= 0 && d->ooh >= 0 && d->oow >= 0,
+             "conv_nd: output mapping exceeds the output tensor");
+  LT_REQUIRE(d->residual == LT_RES_NONE || residual, "conv_nd: residual requested but pointer is null");
+  LT_REQUIRE(d->residual >= LT_RES_NONE && d->residual <= LT_RES_AFTER_RELU, "conv_nd: bad residual mode");
+  if (impl == LT_CONV_SIMT) return conv_simt_fwd(d, in, weight, scale, shift, residual, out, stream);
+  if (impl == LT_CONV_TC) return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 3, stream);
+  if (impl == LT_CONV_TC1) return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 1, stream);
+  return fail(LT_ERR_INVALID, "conv_nd: unknown impl %d", impl);
+}

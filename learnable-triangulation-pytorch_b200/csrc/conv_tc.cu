@@ -1,0 +1,482 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: TMA-staged channels-last tiles ->
+// shared memory (128B swizzle) -> tcgen05.mma (UMMA 128 x Nt x 16, bf16 in, fp32 accumulate in
+// TMEM) -> tcgen05.ld epilogue with folded-BN scale/shift, residual, ReLU and strided
+// channels-last store (plain conv, stride-phase transposed conv).
+//
+// GEMM view:  M = output positions (tile = a bw x bh x bd x bn box of 128 positions),
+//             N = output channels (tile Nt <= 256), K = taps x Cin.
+// For every filter tap the A tile is ONE TMA box load of the input tensor shifted by the tap
+// offset; out-of-range coordinates are zero-filled by TMA, which implements the padding.
+//
+// Precision: activations and weights travel as split-bf16 (x = hi + lo, see common.cuh).  Per
+// 16-wide K slice the kernel issues hi*hi + hi*lo + lo*hi (3 MMAs, relative error ~2^-17 per
+// product, i.e. fp32-grade results from the bf16 pipe) or hi*hi only (LT_CONV_TC1, fast mode).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (one TMEM lane quadrant each).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace lt {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms
+// 1024 bytes apart): start address >> 4 | LBO=1 | SBO=1024>>4 | version=1 | layout=SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+  int OW, OH, OD, N;       // output grid computed by this launch
+  int bw, bh, bd, bn;      // M-tile box, product 128
+  int tw, th, td, tn;      // tiles per dim
+  int KW, KH, KD, pw, ph, pd;
+  int CB;                  // 64-element K chunks per tap
+  int b_step0, b_step1;    // B-map coordinates of chunk q: (q*b_step0, q*b_step1 + n0)
+  int Nt, stages, terms;   // N tile, pipeline depth, 1 or 3 product terms
+  int tmem_cols;
+  // epilogue
+  int FC, FD, FH, FW, osd, osh, osw, ood, ooh, oow, relu, residual, out_format;
+  const float* scale;
+  const float* shift;
+  const void* res;
+  void* out;
+};
+
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.Nt * 128;
+  const int stage_bytes = kATileBytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int twi = t % p.tw; t /= p.tw;
+  const int thi = t % p.th; t /= p.th;
+  const int tdi = t % p.td; t /= p.td;
+  const int tni = t;
+  const int ow0 = twi * p.bw, oh0 = thi * p.bh, od0 = tdi * p.bd, nb0 = tni * p.bn;
+  const int n0 = blockIdx.y * p.Nt;
+  const int nchunks = p.KD * p.KH * p.KW * p.CB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int q = 0; q < nchunks; ++q) {
+        const int s = q % p.stages;
+        const uint32_t ph = (uint32_t)((q / p.stages) & 1);
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int tap = q / p.CB, cb = q % p.CB;
+        const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        uint8_t* b_dst = a_dst + kATileBytes;
+        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+        tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 - p.pw + kw, oh0 - p.ph + kh, od0 - p.pd + kd, nb0);
+        tma_load_2d(b_dst, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(p.Nt);
+      uint32_t accumulate = 0;
+      for (int q = 0; q < nchunks; ++q) {
+        const int s = q % p.stages;
+        const uint32_t ph = (uint32_t)((q / p.stages) & 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + kATileBytes;
+        const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw128_desc(b_addr);
+        if (p.terms == 3) {
+          // row = [32 hi | 32 lo] bf16: hi slices at +0,+32 B, lo slices at +64,+96 B (>>4 units: 2 per 32 B)
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const uint64_t ah = ad + (uint64_t)(sl * 2), al = ad + (uint64_t)(4 + sl * 2);
+            const uint64_t bh = bd + (uint64_t)(sl * 2), bl = bd + (uint64_t)(4 + sl * 2);
+            umma_bf16(tmem_base, ah, bh, idesc, accumulate);
+            accumulate = 1;
+            umma_bf16(tmem_base, ah, bl, idesc, 1);
+            umma_bf16(tmem_base, al, bh, idesc, 1);
+          }
+        } else if (p.terms == 1) {
+          // split storage, high parts only
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            umma_bf16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
+            accumulate = 1;
+          }
+        } else {
+          // plain bf16 rows (self test): 4 slices of 16
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            umma_bf16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int r = row;
+    const int dw = r % p.bw; r /= p.bw;
+    const int dh = r % p.bh; r /= p.bh;
+    const int dd = r % p.bd; r /= p.bd;
+    const int dn = r;
+    const int ow = ow0 + dw, oh = oh0 + dh, od = od0 + dd, nb = nb0 + dn;
+    const bool valid = ow < p.OW && oh < p.OH && od < p.OD && nb < p.N;
+    const long opix = (((long)nb * p.FD + (od * p.osd + p.ood)) * p.FH + (oh * p.osh + p.ooh)) * p.FW + (ow * p.osw + p.oow);
+
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.Nt; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);   // whole warp (sync.aligned)
+      if (!valid) continue;
+      const int co0 = n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const int co = co0 + j;
+        if (co >= p.FC) break;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + co));
+        float4 o = make_float4(fmaf(__uint_as_float(v[j]), sc.x, sh.x), fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y),
+                               fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z), fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w));
+        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.residual != LT_RES_NONE) {
+          if (p.out_format == LT_FMT_F32) rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + opix * p.FC + co);
+          else rr = load_s32x4(reinterpret_cast<const __nv_bfloat16*>(p.res) + opix * 2 * p.FC, co);
+        }
+        if (p.residual == LT_RES_BEFORE_RELU) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (p.residual == LT_RES_AFTER_RELU) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+        if (p.out_format == LT_FMT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.FC + co) = o;
+        else store_s32x4(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * 2 * p.FC, co, o);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* estrides, int swizzle128) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estrides ? estrides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return LT_OK;
+}
+
+static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// pick the (bw, bh, bd, bn) power-of-two box with product 128 that wastes the fewest positions
+static void pick_box(int OW, int OH, int OD, int N, int* box) {
+  double best = 1e300;
+  for (int bw = 1; bw <= 128; bw <<= 1)
+    for (int bh = 1; bw * bh <= 128; bh <<= 1)
+      for (int bd = 1; bw * bh * bd <= 128; bd <<= 1) {
+        const int bn = 128 / (bw * bh * bd);
+        if (bw > pow2_ceil(OW) || bh > pow2_ceil(OH) || bd > pow2_ceil(OD) || bn > pow2_ceil(N)) continue;
+        const double padded = (double)ceil_div(OW, bw) * bw * ceil_div(OH, bh) * bh * (double)ceil_div(OD, bd) * bd * ceil_div(N, bn) * bn;
+        const double score = padded * (1.0 + 1e-3 / bw);  // tie-break: wider rows
+        if (score < best) { best = score; box[0] = bw; box[1] = bh; box[2] = bd; box[3] = bn; }
+      }
+  if (best == 1e300) { box[0] = pow2_ceil(OW) > 128 ? 128 : pow2_ceil(OW); box[1] = box[2] = 1; box[3] = 128 / box[0]; }
+}
+
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, int n_tiles, cudaStream_t st) {
+  const int stage_bytes = kATileBytes + p.Nt * 128;
+  int stages = (96 * 1024) / stage_bytes;   // aim at two resident CTAs per SM
+  if (stages < 2) stages = 2;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.tmem_cols = pow2_ceil(p.Nt) < 32 ? 32 : pow2_ceil(p.Nt);
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = 227 * 1024;
+  }
+  const long m_tiles = (long)p.tw * p.th * p.td * p.tn;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
+  conv_tc_kernel<<<grid, 192, smem, st>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_kernel: %s", cudaGetErrorString(e));
+  return LT_OK;
+}
+
+int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                      const void* residual, void* out, int terms, void* stream) {
+  LT_REQUIRE(d->in_format == LT_FMT_S32, "conv_tc: input must be split-bf16");
+  LT_REQUIRE(d->Cin % 32 == 0, "conv_tc: Cin=%d must be a multiple of 32", d->Cin);
+  LT_REQUIRE(d->sd == 1 && d->sh == 1 && d->sw == 1, "conv_tc: strided input not supported (use LT_CONV_SIMT)");
+  LT_REQUIRE(d->FC % 4 == 0 && (d->out_format == LT_FMT_F32 || d->FC % 32 == 0), "conv_tc: bad output channel stride %d", d->FC);
+  const int CoutP = (d->Cout + 15) & ~15;
+  const int Nt = CoutP <= 128 ? CoutP : 128;
+  LT_REQUIRE(CoutP % Nt == 0, "conv_tc: Cout=%d (padded %d) not tileable by %d", d->Cout, CoutP, Nt);
+  const int CB = d->Cin / 32;
+  const int taps = d->KD * d->KH * d->KW;
+
+  TcParams p;
+  p.OW = d->OW; p.OH = d->OH; p.OD = d->OD; p.N = d->N;
+  int box[4];
+  pick_box(d->OW, d->OH, d->OD, d->N, box);
+  p.bw = box[0]; p.bh = box[1]; p.bd = box[2]; p.bn = box[3];
+  p.tw = ceil_div(d->OW, p.bw); p.th = ceil_div(d->OH, p.bh); p.td = ceil_div(d->OD, p.bd); p.tn = ceil_div(d->N, p.bn);
+  p.KW = d->KW; p.KH = d->KH; p.KD = d->KD; p.pw = d->pw; p.ph = d->ph; p.pd = d->pd;
+  p.CB = CB; p.b_step0 = 0; p.b_step1 = CoutP; p.Nt = Nt; p.terms = terms;
+  p.FC = d->FC; p.FD = d->FD; p.FH = d->FH; p.FW = d->FW;
+  p.osd = d->osd; p.osh = d->osh; p.osw = d->osw; p.ood = d->ood; p.ooh = d->ooh; p.oow = d->oow;
+  p.relu = d->relu; p.residual = d->residual; p.out_format = d->out_format;
+  p.scale = scale; p.shift = shift; p.res = residual; p.out = out;
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t rowb = (uint64_t)d->Cin * 2 * 2;  // 2*Cin bf16 per position
+    const uint64_t dims[5] = {(uint64_t)d->Cin * 2, (uint64_t)d->IW, (uint64_t)d->IH, (uint64_t)d->ID, (uint64_t)d->N};
+    const uint64_t str[4] = {rowb, rowb * d->IW, rowb * d->IW * d->IH, rowb * d->IW * d->IH * d->ID};
+    const uint32_t bx[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+    int rc = make_map(&tmA, in, 5, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {64, (uint64_t)taps * CB * CoutP};
+    const uint64_t str[1] = {128};
+    const uint32_t bx[2] = {64, (uint32_t)Nt};
+    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  return launch_tc(tmA, tmB, p, CoutP / Nt, (cudaStream_t)stream);
+}
+
+int conv_tc_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                const void* residual, void* out, void* stream) {
+  return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 3, stream);
+}
+
+// ---- weight packing: fp32 [taps][Cin][Cout] -> split-bf16 [taps][Cin/32][CoutP][64] ----------------
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                           int taps, int Cin, int Cout, int CoutP) {
+  const int CB = Cin / 32;
+  const long total = (long)taps * CB * CoutP * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % 32);
+    long r = i / 32;
+    const int n = (int)(r % CoutP); r /= CoutP;
+    const int cb = (int)(r % CB);
+    const int tap = (int)(r / CB);
+    const float v = (n < Cout) ? w[((long)tap * Cin + cb * 32 + j) * Cout + n] : 0.0f;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    __nv_bfloat16* row = out + (((long)tap * CB + cb) * CoutP + n) * 64;
+    row[j] = hi;
+    row[32 + j] = lo;
+  }
+}
+
+__global__ void ones_zeros_kernel(float* ones, float* zeros, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { ones[i] = 1.0f; zeros[i] = 0.0f; }
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout) {
+  const int CoutP = (Cout + 15) & ~15;
+  return (size_t)taps * (Cin / 32) * CoutP * 64 * 2;
+}
+
+extern "C" int lt_conv_tc_pack_weights(const float* w, void* packed, int taps, int Cin, int Cout, void* stream) {
+  LT_REQUIRE(w && packed, "conv_tc_pack_weights: null pointer");
+  LT_REQUIRE(Cin % 32 == 0 && taps > 0 && Cout > 0, "conv_tc_pack_weights: bad sizes");
+  const int CoutP = (Cout + 15) & ~15;
+  const long total = (long)taps * (Cin / 32) * CoutP * 32;
+  long blocks = (total + 255) / 256;
+  if (blocks > 65535) blocks = 65535;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), taps, Cin, Cout, CoutP);
+  LT_CHECK_LAUNCH("pack_weights_kernel");
+  return LT_OK;
+}
+
+// D[M][N] (fp32) = A[M][K] * B[N][K]^T, plain bf16 row-major operands; exercises the exact TMA /
+// descriptor / tcgen05 / epilogue code of the conv kernel (terms = 0 selects plain rows).
+// `d` must hold M*N floats followed by 2*N floats of scratch (scale/shift).
+extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M, int N, int K, int variant, void* stream) {
+  LT_REQUIRE(a && b && d, "tc_gemm_selftest: null pointer");
+  LT_REQUIRE(M > 0 && N % 16 == 0 && N >= 16 && K % 64 == 0, "tc_gemm_selftest: need N %% 16 == 0, K %% 64 == 0");
+  (void)variant;
+  const int Nt = N <= 128 ? N : 128;
+  LT_REQUIRE(N % Nt == 0, "tc_gemm_selftest: N must be <= 128 or a multiple of 128");
+  float* ones = d + (size_t)M * N;
+  float* zeros = ones + N;
+  ones_zeros_kernel<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(ones, zeros, N);
+  TcParams p;
+  p.OW = M; p.OH = 1; p.OD = 1; p.N = 1;
+  p.bw = 128; p.bh = 1; p.bd = 1; p.bn = 1;
+  p.tw = ceil_div(M, 128); p.th = 1; p.td = 1; p.tn = 1;
+  p.KW = p.KH = p.KD = 1; p.pw = p.ph = p.pd = 0;
+  p.CB = K / 64; p.b_step0 = 64; p.b_step1 = 0; p.Nt = Nt; p.terms = 0;
+  p.FC = N; p.FD = 1; p.FH = 1; p.FW = M; p.osd = p.osh = p.osw = 1; p.ood = p.ooh = p.oow = 0;
+  p.relu = 0; p.residual = LT_RES_NONE; p.out_format = LT_FMT_F32;
+  p.scale = ones; p.shift = zeros; p.res = nullptr; p.out = d;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[5] = {(uint64_t)K, (uint64_t)M, 1, 1, 1};
+    const uint64_t str[4] = {(uint64_t)K * 2, (uint64_t)K * 2 * M, (uint64_t)K * 2 * M, (uint64_t)K * 2 * M};
+    const uint32_t bx[5] = {64, 128, 1, 1, 1};
+    int rc = make_map(&tmA, a, 5, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint32_t bx[2] = {64, (uint32_t)Nt};
+    int rc = make_map(&tmB, b, 2, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  return launch_tc(tmA, tmB, p, N / Nt, (cudaStream_t)stream);
+}

@@ -1,0 +1,189 @@
+// Small bandwidth-bound helpers: coordinate volume, max pooling, layout / format conversion.
+#include "common.cuh"
+
+namespace lt {
+
+// ---- coordinate volume -------------------------------------------------------------------------
+// triangulation.py:306-333: grid index -> mm (position + step * index, float32), minus centre,
+// rotation (volumetric.py:102-114, R @ v), plus centre; optional CMU->H36M transfer (:336-339):
+// out[a][b][c] = base[a][c][n-1-b].  __fmul_rn/__fadd_rn keep the reference's unfused op order.
+__global__ void __launch_bounds__(256) coord_volume_kernel(const float* __restrict__ position, const float* __restrict__ center,
+                                                           const float* __restrict__ step, const float* __restrict__ rot,
+                                                           float* __restrict__ out, int B, int n, int transfer_cmu) {
+  const long nvox = (long)n * n * n;
+  const long total = (long)B * nvox;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / nvox);
+    const long r = i % nvox;
+    int a = (int)(r / ((long)n * n)), bb = (int)((r / n) % n), c = (int)(r % n);
+    int gi = a, gj = bb, gk = c;
+    if (transfer_cmu) { gj = c; gk = n - 1 - bb; }
+    const float* pos = position + b * 3;
+    const float* cen = center + b * 3;
+    const float* R = rot + b * 9;
+    float x = __fadd_rn(pos[0], __fmul_rn(step[0], (float)gi));
+    float y = __fadd_rn(pos[1], __fmul_rn(step[1], (float)gj));
+    float z = __fadd_rn(pos[2], __fmul_rn(step[2], (float)gk));
+    x = __fadd_rn(x, -cen[0]); y = __fadd_rn(y, -cen[1]); z = __fadd_rn(z, -cen[2]);
+    const float rx = fmaf(R[2], z, fmaf(R[1], y, __fmul_rn(R[0], x)));
+    const float ry = fmaf(R[5], z, fmaf(R[4], y, __fmul_rn(R[3], x)));
+    const float rz = fmaf(R[8], z, fmaf(R[7], y, __fmul_rn(R[6], x)));
+    float* o = out + i * 3;
+    o[0] = __fadd_rn(rx, cen[0]);
+    o[1] = __fadd_rn(ry, cen[1]);
+    o[2] = __fadd_rn(rz, cen[2]);
+  }
+}
+
+// ---- max pooling, channels-last, 4 channels per thread ----------------------------------------------
+struct PoolParams {
+  const void* in; void* out; int format;
+  int N, ID, IH, IW, C, kd, kh, kw, sd, sh, sw, pd, ph, pw, OD, OH, OW;
+};
+
+__global__ void __launch_bounds__(256) maxpool_kernel(const PoolParams p) {
+  const int c4n = p.C / 4;
+  const long total = (long)p.N * p.OD * p.OH * p.OW * c4n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long r = i / c4n;
+    const int ow = (int)(r % p.OW); r /= p.OW;
+    const int oh = (int)(r % p.OH); r /= p.OH;
+    const int od = (int)(r % p.OD);
+    const int n = (int)(r / p.OD);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int a = 0; a < p.kd; ++a) {
+      const int id = od * p.sd - p.pd + a;
+      if (id < 0 || id >= p.ID) continue;
+      for (int b = 0; b < p.kh; ++b) {
+        const int ih = oh * p.sh - p.ph + b;
+        if (ih < 0 || ih >= p.IH) continue;
+        for (int e = 0; e < p.kw; ++e) {
+          const int iw = ow * p.sw - p.pw + e;
+          if (iw < 0 || iw >= p.IW) continue;
+          const long pix = (((long)n * p.ID + id) * p.IH + ih) * p.IW + iw;
+          float4 v;
+          if (p.format == LT_FMT_F32) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + pix * p.C + c));
+          else v = load_s32x4(reinterpret_cast<const __nv_bfloat16*>(p.in) + pix * 2 * p.C, c);
+          m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+      }
+    }
+    const long opix = (((long)n * p.OD + od) * p.OH + oh) * p.OW + ow;
+    if (p.format == LT_FMT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.C + c) = m;
+    else store_s32x4(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * 2 * p.C, c, m);
+  }
+}
+
+// ---- layout / format conversion -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           int N, int C, int H, int W, int Cp) {
+  const long hw = (long)H * W;
+  const long total = (long)N * hw;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / hw, r = i % hw;
+    float* o = out + i * Cp;
+    for (int c = 0; c < Cp; ++c) o[c] = (c < C) ? __ldg(in + (n * C + c) * hw + r) : 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_s32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long pixels, int C) {
+  const int c4n = C / 4;
+  const long total = pixels * c4n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / c4n;
+    const int c = (int)(i % c4n) * 4;
+    store_s32x4(out + pix * 2 * C, c, __ldg(reinterpret_cast<const float4*>(in + pix * C + c)));
+  }
+}
+
+__global__ void __launch_bounds__(256) s32_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long pixels, int C) {
+  const int c4n = C / 4;
+  const long total = pixels * c4n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / c4n;
+    const int c = (int)(i % c4n) * 4;
+    *reinterpret_cast<float4*>(out + pix * C + c) = load_s32x4(in + pix * 2 * C, c);
+  }
+}
+
+// [N][P][Cs] -> [N][C][P], 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) cl_to_cf_kernel(const float* __restrict__ in, float* __restrict__ out, long P, int Cs, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long p0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const long pp = p0 + r;
+    const int c = c0 + tx;
+    tile[r][tx] = (pp < P && c < C) ? __ldg(in + ((long)n * P + pp) * Cs + c) : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long pp = p0 + tx;
+    if (c < C && pp < P) out[((long)n * C + c) * P + pp] = tile[tx][r];
+  }
+}
+
+static inline unsigned grid_for(long total, int per_block = 256) {
+  long b = (total + per_block - 1) / per_block;
+  const long cap = (long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" int lt_coord_volume_fwd(const float* position, const float* center, const float* step, const float* rot,
+                                   float* out, int B, int n, int transfer_cmu, void* stream) {
+  LT_REQUIRE(position && center && step && rot && out, "coord_volume: null pointer");
+  LT_REQUIRE(B > 0 && n > 1, "coord_volume: bad size B=%d n=%d", B, n);
+  coord_volume_kernel<<<grid_for((long)B * n * n * n), 256, 0, (cudaStream_t)stream>>>(position, center, step, rot, out, B, n, transfer_cmu);
+  LT_CHECK_LAUNCH("coord_volume_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_maxpool_fwd(const void* in, void* out, int format, int N, int ID, int IH, int IW, int C, int kd, int kh,
+                              int kw, int sd, int sh, int sw, int pd, int ph, int pw, int OD, int OH, int OW, void* stream) {
+  LT_REQUIRE(in && out, "maxpool: null pointer");
+  LT_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
+  LT_REQUIRE(format == LT_FMT_F32 || C % 32 == 0, "maxpool: split-bf16 needs C %% 32 == 0");
+  PoolParams p{in, out, format, N, ID, IH, IW, C, kd, kh, kw, sd, sh, sw, pd, ph, pw, OD, OH, OW};
+  maxpool_kernel<<<grid_for((long)N * OD * OH * OW * (C / 4)), 256, 0, (cudaStream_t)stream>>>(p);
+  LT_CHECK_LAUNCH("maxpool_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, int Cp, void* stream) {
+  LT_REQUIRE(in && out && Cp >= C, "nchw_to_nhwc: bad arguments");
+  nchw_to_nhwc_kernel<<<grid_for((long)N * H * W), 256, 0, (cudaStream_t)stream>>>(in, out, N, C, H, W, Cp);
+  LT_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_f32_to_s32(const float* in, void* out, long pixels, int C, void* stream) {
+  LT_REQUIRE(in && out && C % 32 == 0, "f32_to_s32: C %% 32 != 0");
+  f32_to_s32_kernel<<<grid_for(pixels * (C / 4)), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), pixels, C);
+  LT_CHECK_LAUNCH("f32_to_s32_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_s32_to_f32(const void* in, float* out, long pixels, int C, void* stream) {
+  LT_REQUIRE(in && out && C % 32 == 0, "s32_to_f32: C %% 32 != 0");
+  s32_to_f32_kernel<<<grid_for(pixels * (C / 4)), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, pixels, C);
+  LT_CHECK_LAUNCH("s32_to_f32_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_cl_to_cf_f32(const float* in, float* out, int N, long P, int Cs, int C, void* stream) {
+  LT_REQUIRE(in && out && C <= Cs && N <= 65535, "cl_to_cf: bad arguments");
+  dim3 grid((unsigned)((P + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+  cl_to_cf_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, P, Cs, C);
+  LT_CHECK_LAUNCH("cl_to_cf_kernel");
+  return LT_OK;
+}

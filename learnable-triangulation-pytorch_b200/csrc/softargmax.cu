@@ -1,0 +1,259 @@
+// Volumetric soft-argmax (HBM-bound).
+//
+// Replaces mvn/utils/op.py:84-96 (integrate_tensor_3d_with_coordinates): softmax over the N^3
+// voxels of every (sample, joint) followed by the expectation of the voxel coordinates
+// (einsum "bnxyz,bxyzc->bnc"), returning the keypoints and the normalised volumes.
+//
+// Pass 1 streams the logits once with an online (running max) softmax that carries the three
+// coordinate-weighted sums along, warp-reduced per chunk; pass 2 merges the per-chunk partials of
+// each (b, j) in one warp; pass 3 (only when the normalised volumes are requested -- the API
+// default) re-reads the logits (L2-resident per sample) and writes exp(l - max)/sum in NCDHW,
+// transposing channels-last tiles through shared memory so both sides stay coalesced.
+//
+// Algorithmic bytes per sample (J=17, 64^3): 17.83 MB logits + 3.15 MB coords (+17.83 MB volume
+// write) = 20.97 MB keypoints-only / 38.80 MB with volumes.
+#include "common.cuh"
+
+namespace lt {
+
+constexpr int kChunk = 2048;  // voxels per pass-1 CTA
+
+struct SoftState {
+  float m, d, sx, sy, sz;
+};
+
+__device__ __forceinline__ void st_init(SoftState& s, bool softmax) {
+  s.m = softmax ? -INFINITY : 0.0f;
+  s.d = s.sx = s.sy = s.sz = 0.0f;
+}
+// add one element with logit l and coordinate (x, y, z)
+__device__ __forceinline__ void st_push(SoftState& s, float l, float x, float y, float z, bool softmax) {
+  if (softmax) {
+    const float mn = fmaxf(s.m, l);
+    const float r = __expf(s.m - mn);   // rescale of the running sums (exp(-inf) = 0 on first element)
+    const float e = __expf(l - mn);
+    s.d = fmaf(s.d, r, e);
+    s.sx = fmaf(s.sx, r, e * x);
+    s.sy = fmaf(s.sy, r, e * y);
+    s.sz = fmaf(s.sz, r, e * z);
+    s.m = mn;
+  } else {
+    const float e = fmaxf(l, 0.0f);     // op.py:90-91: ReLU, no normalisation
+    s.sx = fmaf(e, x, s.sx);
+    s.sy = fmaf(e, y, s.sy);
+    s.sz = fmaf(e, z, s.sz);
+  }
+}
+__device__ __forceinline__ void st_merge(SoftState& a, const SoftState& b, bool softmax) {
+  if (softmax) {
+    const float mn = fmaxf(a.m, b.m);
+    const float ra = (a.m == -INFINITY) ? 0.0f : __expf(a.m - mn);
+    const float rb = (b.m == -INFINITY) ? 0.0f : __expf(b.m - mn);
+    a.d = a.d * ra + b.d * rb;
+    a.sx = a.sx * ra + b.sx * rb;
+    a.sy = a.sy * ra + b.sy * rb;
+    a.sz = a.sz * ra + b.sz * rb;
+    a.m = mn;
+  } else {
+    a.sx += b.sx; a.sy += b.sy; a.sz += b.sz;
+  }
+}
+__device__ __forceinline__ SoftState st_shfl_xor(const SoftState& s, int o) {
+  SoftState r;
+  r.m = __shfl_xor_sync(0xffffffffu, s.m, o);
+  r.d = __shfl_xor_sync(0xffffffffu, s.d, o);
+  r.sx = __shfl_xor_sync(0xffffffffu, s.sx, o);
+  r.sy = __shfl_xor_sync(0xffffffffu, s.sy, o);
+  r.sz = __shfl_xor_sync(0xffffffffu, s.sz, o);
+  return r;
+}
+
+struct SoftParams {
+  const float* logits;
+  long bs, vs, cs;        // batch / voxel / channel strides (floats)
+  const float* coord;     // [B][nvox][3]
+  float* volumes;         // [B][J][nvox] or null
+  float* keypoints;       // [B][J][3]
+  float* partial;         // [B][J][nch][5]
+  float* stats;           // [B][J][2] = (max, sum)
+  int B, J, nch;
+  long nvox;
+  float mult;
+  int softmax;
+};
+
+// Pass 1, channels-last logits (cs == 1, J <= 32): lane = joint, warps stride over voxels.
+__global__ void __launch_bounds__(256) softargmax_partial_cl(const SoftParams p) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long v0 = (long)chunk * kChunk;
+  const long v1 = min(v0 + kChunk, p.nvox);
+  const bool sm = p.softmax != 0;
+  const bool active = lane < p.J;
+  const float* lg = p.logits + (long)b * p.bs + lane;
+  const float* cd = p.coord + (long)b * p.nvox * 3;
+  SoftState s;
+  st_init(s, sm);
+  // 4 voxels in flight per warp iteration
+  for (long v = v0 + warp * 4; v < v1; v += 32) {
+    float l[4], x[4], y[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long vv = v + u;
+      const bool ok = vv < v1;
+      l[u] = (ok && active) ? __ldg(lg + vv * p.vs) : 0.0f;
+      x[u] = ok ? __ldg(cd + vv * 3) : 0.0f;
+      y[u] = ok ? __ldg(cd + vv * 3 + 1) : 0.0f;
+      z[u] = ok ? __ldg(cd + vv * 3 + 2) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u < v1) st_push(s, l[u] * p.mult, x[u], y[u], z[u], sm);
+  }
+  __shared__ SoftState sh[8][32];
+  sh[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && active) {
+    SoftState a = sh[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) st_merge(a, sh[w][lane], sm);
+    float* o = p.partial + (((long)b * p.J + lane) * p.nch + chunk) * 5;
+    o[0] = a.m; o[1] = a.d; o[2] = a.sx; o[3] = a.sy; o[4] = a.sz;
+  }
+}
+
+// Pass 1, generic strides: one CTA per (chunk, joint, sample), threads stride over voxels.
+__global__ void __launch_bounds__(256) softargmax_partial_generic(const SoftParams p) {
+  const int chunk = blockIdx.x, j = blockIdx.y, b = blockIdx.z;
+  const long v0 = (long)chunk * kChunk;
+  const long v1 = min(v0 + kChunk, p.nvox);
+  const bool sm = p.softmax != 0;
+  const float* lg = p.logits + (long)b * p.bs + (long)j * p.cs;
+  const float* cd = p.coord + (long)b * p.nvox * 3;
+  SoftState s;
+  st_init(s, sm);
+  for (long v = v0 + threadIdx.x; v < v1; v += blockDim.x)
+    st_push(s, __ldg(lg + v * p.vs) * p.mult, __ldg(cd + v * 3), __ldg(cd + v * 3 + 1), __ldg(cd + v * 3 + 2), sm);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(s, o); st_merge(s, t, sm); }
+  __shared__ SoftState sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SoftState a = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) st_merge(a, sh[w], sm);
+    float* o = p.partial + (((long)b * p.J + j) * p.nch + chunk) * 5;
+    o[0] = a.m; o[1] = a.d; o[2] = a.sx; o[3] = a.sy; o[4] = a.sz;
+  }
+}
+
+// Pass 2: one warp per (b, j) merges the chunk partials.
+__global__ void __launch_bounds__(128) softargmax_finalize(const SoftParams p) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= p.B * p.J) return;
+  const bool sm = p.softmax != 0;
+  SoftState s;
+  st_init(s, sm);
+  const float* src = p.partial + (long)gw * p.nch * 5;
+  for (int c = lane; c < p.nch; c += 32) {
+    SoftState t{src[c * 5], src[c * 5 + 1], src[c * 5 + 2], src[c * 5 + 3], src[c * 5 + 4]};
+    st_merge(s, t, sm);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(s, o); st_merge(s, t, sm); }
+  if (lane == 0) {
+    float* k = p.keypoints + (long)gw * 3;
+    if (sm) { k[0] = s.sx / s.d; k[1] = s.sy / s.d; k[2] = s.sz / s.d; }
+    else { k[0] = s.sx; k[1] = s.sy; k[2] = s.sz; }
+    p.stats[gw * 2] = s.m;
+    p.stats[gw * 2 + 1] = s.d;
+  }
+}
+
+// Pass 3, channels-last logits: each warp transposes a 32-voxel x 32-channel tile.
+__global__ void __launch_bounds__(256) softargmax_normalize_cl(const SoftParams p) {
+  __shared__ float tile[8][32][33];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool sm = p.softmax != 0;
+  const float* st = p.stats + (long)b * p.J * 2;
+  for (long v0 = ((long)blockIdx.x * 8 + warp) * 32; v0 < p.nvox; v0 += (long)gridDim.x * 256) {
+    const float* lg = p.logits + (long)b * p.bs + lane;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const long v = v0 + r;
+      tile[warp][r][lane] = (v < p.nvox && lane < p.J) ? __ldg(lg + v * p.vs) : 0.0f;
+    }
+    __syncwarp();
+    const long v = v0 + lane;
+    if (v < p.nvox) {
+      for (int j = 0; j < p.J; ++j) {
+        const float l = tile[warp][lane][j] * p.mult;
+        const float o = sm ? __expf(l - st[j * 2]) / st[j * 2 + 1] : fmaxf(l, 0.0f);
+        p.volumes[((long)b * p.J + j) * p.nvox + v] = o;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) softargmax_normalize_generic(const SoftParams p) {
+  const int j = blockIdx.y, b = blockIdx.z;
+  const bool sm = p.softmax != 0;
+  const float mx = p.stats[((long)b * p.J + j) * 2], dn = p.stats[((long)b * p.J + j) * 2 + 1];
+  const float* lg = p.logits + (long)b * p.bs + (long)j * p.cs;
+  float* o = p.volumes + ((long)b * p.J + j) * p.nvox;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < p.nvox; v += (long)gridDim.x * blockDim.x) {
+    const float l = __ldg(lg + v * p.vs) * p.mult;
+    o[v] = sm ? __expf(l - mx) / dn : fmaxf(l, 0.0f);
+  }
+}
+
+static inline int n_chunks(long nvox) { return (int)((nvox + kChunk - 1) / kChunk); }
+
+}  // namespace lt
+
+extern "C" size_t lt_softargmax3d_workspace_bytes(int B, int J, long nvox) {
+  return (size_t)B * J * ((size_t)lt::n_chunks(nvox) * 5 + 2) * sizeof(float);
+}
+
+extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long voxel_stride, long chan_stride,
+                                   const float* coord, float* volumes_out, float* keypoints_out, void* workspace,
+                                   size_t workspace_bytes, int B, int J, long nvox, float multiplier, int softmax,
+                                   void* stream) {
+  using namespace lt;
+  LT_REQUIRE(logits && coord && keypoints_out && workspace, "softargmax3d: null pointer");
+  LT_REQUIRE(B > 0 && J > 0 && nvox > 0, "softargmax3d: non-positive size");
+  LT_REQUIRE(B <= 65535 && J <= 65535, "softargmax3d: B/J too large");
+  LT_REQUIRE(workspace_bytes >= lt_softargmax3d_workspace_bytes(B, J, nvox), "softargmax3d: workspace too small");
+  SoftParams p;
+  p.logits = logits; p.bs = batch_stride; p.vs = voxel_stride; p.cs = chan_stride;
+  p.coord = coord; p.volumes = volumes_out; p.keypoints = keypoints_out;
+  p.nch = n_chunks(nvox);
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.stats = p.partial + (size_t)B * J * p.nch * 5;
+  p.B = B; p.J = J; p.nvox = nvox; p.mult = multiplier; p.softmax = softmax;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool cl = (chan_stride == 1 && J <= 32 && voxel_stride >= J);
+  if (cl) softargmax_partial_cl<<<dim3(p.nch, B), 256, 0, st>>>(p);
+  else softargmax_partial_generic<<<dim3(p.nch, J, B), 256, 0, st>>>(p);
+  LT_CHECK_LAUNCH("softargmax_partial");
+  softargmax_finalize<<<ceil_div((long)B * J * 32, 128), 128, 0, st>>>(p);
+  LT_CHECK_LAUNCH("softargmax_finalize");
+  if (volumes_out) {
+    if (cl) {
+      long blocks = (nvox + 255) / 256;
+      const long cap = (long)sm_count() * 8;
+      if (blocks > cap) blocks = cap;
+      softargmax_normalize_cl<<<dim3((unsigned)blocks, B), 256, 0, st>>>(p);
+    } else {
+      long blocks = (nvox + 255) / 256;
+      if (blocks > 1024) blocks = 1024;
+      softargmax_normalize_generic<<<dim3((unsigned)blocks, J, B), 256, 0, st>>>(p);
+    }
+    LT_CHECK_LAUNCH("softargmax_normalize");
+  }
+  return LT_OK;
+}

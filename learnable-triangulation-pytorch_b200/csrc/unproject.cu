@@ -1,0 +1,341 @@
+// Fused unprojection + cross-view aggregation (HBM-bound).
+//
+// Replaces mvn/utils/op.py:99-166 (unproject_heatmaps): the reference loops over B*V pairs,
+// launches ~15 ATen kernels per pair, materialises a (V, C, N^3) staging tensor per sample and
+// makes >= 5 more passes over it for the softmax aggregation.  Here one launch does everything:
+// a group of G = C/4 lanes owns one voxel; per view the group builds the projection ray
+// (3x4 matvec, depth test, perspective divide), derives the four bilinear taps with
+// grid_sample(align_corners=True, padding zeros) semantics -- including the reference's
+// normalisation quirk (x divided by the map HEIGHT, y by the WIDTH, op.py:128-129) -- fetches
+// each tap as one coalesced 16-byte load per lane (C=32 -> one 128-byte line per tap per voxel
+// from the channels-last feature map), keeps the V per-view samples in registers, aggregates
+// (softmax / sum / max / conf) and writes the voxel's C channels once, channels-last, either as
+// float32 or directly in the split-bf16 operand format of the V2V tensor-core convs.
+//
+// Algorithmic bytes per sample (V=4, C=32, 96x96 maps, 64^3 voxels, fp32 out):
+//   33.55 MB volume write + 4.72 MB feature read (compulsory) + 3.15 MB coordinate read = 41.42 MB.
+#include "common.cuh"
+
+namespace lt {
+
+constexpr int kMaxStoredViews = 8;
+constexpr int kMaxSmemViews = 64;
+
+struct UnprojParams {
+  const float* features;  // [B][V][h][w][C]
+  const float* proj;      // [B][V][12]
+  const float* coord;     // [B][nvox][3]
+  const float* conf;      // [B][V][C] or null
+  void* out;              // full: [B][nvox][C] (fmt); partial: float [B][P][nvox][C]
+  int B, V, C, h, w;
+  long nvox;
+  int agg, out_format, G, partial;
+};
+
+struct Taps {
+  int o00, o01, o10, o11;  // pixel offsets (y*w + x), valid only when the matching weight flag is set
+  float w00, w01, w10, w11;
+  unsigned mask;           // bit i set -> tap i inside the map; 0 when depth <= 0
+};
+
+__device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float X, float Y, float Z, int h, int w) {
+  Taps t;
+  // [X Y Z 1] . P^T (multiview.py:104), k-sequential accumulation like sgemm
+  float px = fmaf(Z, P[2], fmaf(Y, P[1], X * P[0])) + P[3];
+  float py = fmaf(Z, P[6], fmaf(Y, P[5], X * P[4])) + P[7];
+  float pz = fmaf(Z, P[10], fmaf(Y, P[9], X * P[8])) + P[11];
+  const bool depth_ok = !(pz <= 0.0f);      // op.py:121
+  if (pz == 0.0f) pz = 1.0f;                // op.py:123
+  const float x = px / pz, y = py / pz;     // multiview.py:84
+  // op.py:128-129: x normalised by heatmap_shape[0] (= h), y by heatmap_shape[1] (= w)
+  const float gx = 2.0f * (x / (float)h - 0.5f);
+  const float gy = 2.0f * (y / (float)w - 0.5f);
+  // grid_sample unnormalise, align_corners=True
+  const float ix = ((gx + 1.0f) / 2.0f) * (float)(w - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * (float)(h - 1);
+  const float x0 = floorf(ix), y0 = floorf(iy);
+  const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+  t.w00 = (x1 - ix) * (y1 - iy);  // nw
+  t.w01 = (ix - x0) * (y1 - iy);  // ne
+  t.w10 = (x1 - ix) * (iy - y0);  // sw
+  t.w11 = (ix - x0) * (iy - y0);  // se
+  const float wm = (float)(w - 1), hm = (float)(h - 1);
+  const bool vx0 = (x0 >= 0.0f) && (x0 <= wm), vx1 = (x1 >= 0.0f) && (x1 <= wm);
+  const bool vy0 = (y0 >= 0.0f) && (y0 <= hm), vy1 = (y1 >= 0.0f) && (y1 <= hm);
+  // NaN/inf-safe integer conversion (comparisons above are false for NaN)
+  const int xi = (int)fminf(fmaxf(x0, -2.0f), wm + 1.0f);
+  const int yi = (int)fminf(fmaxf(y0, -2.0f), hm + 1.0f);
+  t.o00 = yi * w + xi;
+  t.o01 = t.o00 + 1;
+  t.o10 = t.o00 + w;
+  t.o11 = t.o10 + 1;
+  t.mask = depth_ok ? ((vx0 && vy0 ? 1u : 0u) | (vx1 && vy0 ? 2u : 0u) | (vx0 && vy1 ? 4u : 0u) | (vx1 && vy1 ? 8u : 0u)) : 0u;
+  return t;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void sample(const float* __restrict__ fmap, int C, int c0, const Taps& t, float (&s)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s[i] = 0.0f;
+  float v[VEC];
+  if (t.mask & 1u) { load_vec<VEC>(fmap + (long)t.o00 * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = fmaf(v[i], t.w00, s[i]); }
+  if (t.mask & 2u) { load_vec<VEC>(fmap + (long)t.o01 * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = fmaf(v[i], t.w01, s[i]); }
+  if (t.mask & 4u) { load_vec<VEC>(fmap + (long)t.o10 * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = fmaf(v[i], t.w10, s[i]); }
+  if (t.mask & 8u) { load_vec<VEC>(fmap + (long)t.o11 * C + c0, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = fmaf(v[i], t.w11, s[i]); }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_out(const UnprojParams& p, long b, long vox, int c0, const float (&o)[VEC]) {
+  if (p.out_format == LT_FMT_F32) {
+    float* dst = reinterpret_cast<float*>(p.out) + ((long)b * p.nvox + vox) * p.C + c0;
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    else dst[0] = o[0];
+  } else {
+    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long)b * p.nvox + vox) * 2 * p.C;
+    if constexpr (VEC == 4) store_s32x4(row, c0, make_float4(o[0], o[1], o[2], o[3]));
+    else {
+      __nv_bfloat16 hi, lo;
+      split_bf16(o[0], hi, lo);
+      row[s32_off(c0)] = hi;
+      row[s32_off(c0) + 32] = lo;
+    }
+  }
+}
+
+// STORED: V <= kMaxStoredViews, per-view samples kept in registers (two-pass softmax with the
+// max subtracted, like torch.softmax); otherwise a streaming (online) softmax is used.
+template <int VEC, bool STORED>
+__global__ void __launch_bounds__(256) unproject_kernel(const UnprojParams p) {
+  __shared__ float sP[kMaxSmemViews * 12];
+  const int b = blockIdx.y;
+  const int nP = min(p.V, kMaxSmemViews) * 12;
+  for (int i = threadIdx.x; i < nP; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
+  __syncthreads();
+
+  const int G = p.G;
+  const int slot = threadIdx.x / G, sub = threadIdx.x % G;
+  const int vpb = blockDim.x / G;
+  const long map_elems = (long)p.h * p.w * p.C;
+
+  for (long vox = (long)blockIdx.x * vpb + slot; vox < p.nvox; vox += (long)gridDim.x * vpb) {
+    const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
+    const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
+
+    for (int c0 = sub * VEC; c0 < p.C; c0 += G * VEC) {
+      float acc[VEC], aux[VEC], run_max[VEC];
+      float st[STORED ? kMaxStoredViews : 1][VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc[i] = 0.0f; aux[i] = 0.0f; run_max[i] = -INFINITY; }
+
+      const int vend = STORED ? kMaxStoredViews : p.V;
+#pragma unroll
+      for (int v = 0; v < vend; ++v) {
+        if (STORED && v >= p.V) break;
+        const float* Pm = (v < kMaxSmemViews) ? (sP + v * 12) : (p.proj + ((long)b * p.V + v) * 12);
+        const Taps t = make_taps(Pm, X, Y, Z, p.h, p.w);
+        float s[VEC];
+        sample<VEC>(p.features + ((long)b * p.V + v) * map_elems, p.C, c0, t, s);
+
+        if (p.partial) {
+          if (p.agg == LT_AGG_SOFTMAX) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { const float e = expf(s[i]); acc[i] = fmaf(s[i], e, acc[i]); aux[i] += e; }
+          } else if (p.agg == LT_AGG_MAX) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) run_max[i] = fmaxf(run_max[i], s[i]);
+          } else if (p.agg == LT_AGG_CONF) {
+            float cf[VEC];
+            load_vec<VEC>(p.conf + ((long)b * p.V + v) * p.C + c0, cf);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s[i], cf[i], acc[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += s[i];
+          }
+        } else if (p.agg == LT_AGG_SOFTMAX) {
+          if constexpr (STORED) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { st[v][i] = s[i]; run_max[i] = fmaxf(run_max[i], s[i]); }
+          } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              const float m = fmaxf(run_max[i], s[i]);
+              const float r = expf(run_max[i] - m), e = expf(s[i] - m);
+              acc[i] = fmaf(acc[i], r, s[i] * e);
+              aux[i] = fmaf(aux[i], r, e);
+              run_max[i] = m;
+            }
+          }
+        } else if (p.agg == LT_AGG_MAX) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) run_max[i] = fmaxf(run_max[i], s[i]);
+        } else if (p.agg == LT_AGG_CONF) {
+          float cf[VEC];
+          load_vec<VEC>(p.conf + ((long)b * p.V + v) * p.C + c0, cf);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s[i], cf[i], acc[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] += s[i];
+        }
+      }
+
+      if (p.partial) {
+        float* base = reinterpret_cast<float*>(p.out);
+        const int planes = (p.agg == LT_AGG_SOFTMAX) ? 2 : 1;
+        float* d0 = base + (((long)b * planes + 0) * p.nvox + vox) * p.C + c0;
+        const float* src = (p.agg == LT_AGG_MAX) ? run_max : acc;
+        if constexpr (VEC == 4) *reinterpret_cast<float4*>(d0) = make_float4(src[0], src[1], src[2], src[3]);
+        else d0[0] = src[0];
+        if (planes == 2) {
+          float* d1 = d0 + p.nvox * p.C;
+          if constexpr (VEC == 4) *reinterpret_cast<float4*>(d1) = make_float4(aux[0], aux[1], aux[2], aux[3]);
+          else d1[0] = aux[0];
+        }
+        continue;
+      }
+
+      float o[VEC];
+      if (p.agg == LT_AGG_SOFTMAX) {
+        if constexpr (STORED) {
+          float den[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) den[i] = 0.0f;
+#pragma unroll
+          for (int v = 0; v < kMaxStoredViews; ++v) {
+            if (v >= p.V) break;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) den[i] += expf(st[v][i] - run_max[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = 0.0f;
+#pragma unroll
+          for (int v = 0; v < kMaxStoredViews; ++v) {
+            if (v >= p.V) break;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              const float pr = expf(st[v][i] - run_max[i]) / den[i];   // softmax over views (op.py:158)
+              o[i] = fmaf(st[v][i], pr, o[i]);                          // (vol * softmax).sum(0) (op.py:162)
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = acc[i] / aux[i];
+        }
+      } else if (p.agg == LT_AGG_MAX) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = run_max[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = acc[i];
+      }
+      store_out<VEC>(p, b, vox, c0, o);
+    }
+  }
+}
+
+// partial[B][P][nvox][C] -> out[B][nvox][C] (divide numerator by denominator for softmax)
+__global__ void __launch_bounds__(256) unproject_finalize_kernel(const float* __restrict__ partial, void* out, int out_format,
+                                                                 int B, int C, long nvox, int agg) {
+  const long per_b = nvox * C;
+  const long total4 = (long)B * per_b / 4;
+  const int planes = (agg == LT_AGG_SOFTMAX) ? 2 : 1;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const long e = i * 4;
+    const long b = e / per_b, r = e % per_b;
+    const float4 n = *reinterpret_cast<const float4*>(partial + (b * planes) * per_b + r);
+    float4 o = n;
+    if (planes == 2) {
+      const float4 d = *reinterpret_cast<const float4*>(partial + (b * planes + 1) * per_b + r);
+      o = make_float4(n.x / d.x, n.y / d.y, n.z / d.z, n.w / d.w);
+    }
+    if (out_format == LT_FMT_F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e) = o;
+    } else {
+      const long pix = e / C;
+      const int c = (int)(e % C);
+      store_s32x4(reinterpret_cast<__nv_bfloat16*>(out) + pix * 2 * C, c, o);
+    }
+  }
+}
+
+static int launch_unproject(const float* features, const float* proj, const float* coord, const float* conf, void* out,
+                            int out_format, int B, int V, int C, int h, int w, long nvox, int agg, int partial,
+                            void* stream) {
+  LT_REQUIRE(features && proj && coord && out, "unproject: null pointer");
+  LT_REQUIRE(B > 0 && V > 0 && C > 0 && h > 0 && w > 0 && nvox > 0, "unproject: non-positive size");
+  LT_REQUIRE(agg >= LT_AGG_SUM && agg <= LT_AGG_CONF, "unproject: unknown aggregation %d", agg);
+  LT_REQUIRE(agg != LT_AGG_CONF || conf, "unproject: LT_AGG_CONF needs confidences");
+  LT_REQUIRE(out_format == LT_FMT_F32 || (out_format == LT_FMT_S32 && C % 32 == 0),
+             "unproject: split-bf16 output needs C %% 32 == 0 (C=%d)", C);
+  LT_REQUIRE(B <= 65535, "unproject: batch too large");
+  UnprojParams p{features, proj, coord, conf, out, B, V, C, h, w, nvox, agg, out_format, 1, partial};
+  const bool vec4 = (C % 4 == 0);
+  const int units = vec4 ? C / 4 : C;   // lanes wanted per voxel
+  int G = 1;
+  while (G < units && G < 32) G <<= 1;
+  p.G = G;
+  const int vpb = 256 / G;
+  long blocks = (nvox + vpb - 1) / vpb;
+  const long cap = (long)sm_count() * 8;    // 8 resident 256-thread CTAs per SM, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool stored = V <= kMaxStoredViews;
+  if (vec4) {
+    if (stored) unproject_kernel<4, true><<<grid, 256, 0, st>>>(p);
+    else unproject_kernel<4, false><<<grid, 256, 0, st>>>(p);
+  } else {
+    if (stored) unproject_kernel<1, true><<<grid, 256, 0, st>>>(p);
+    else unproject_kernel<1, false><<<grid, 256, 0, st>>>(p);
+  }
+  LT_CHECK_LAUNCH("unproject_kernel");
+  return LT_OK;
+}
+
+}  // namespace lt
+
+extern "C" int lt_unproject_aggregate_fwd(const float* features, const float* proj, const float* coord, const float* conf,
+                                          void* out, int out_format, int B, int V, int C, int h, int w, long nvox,
+                                          int agg, void* stream) {
+  return lt::launch_unproject(features, proj, coord, conf, out, out_format, B, V, C, h, w, nvox, agg, 0, stream);
+}
+
+extern "C" int lt_unproject_partial_fwd(const float* features, const float* proj, const float* coord, const float* conf,
+                                        float* partial, int B, int V_local, int C, int h, int w, long nvox, int agg,
+                                        void* stream) {
+  return lt::launch_unproject(features, proj, coord, conf, partial, LT_FMT_F32, B, V_local, C, h, w, nvox, agg, 1, stream);
+}
+
+extern "C" int lt_unproject_finalize_fwd(const float* partial, void* out, int out_format, int B, int C, long nvox, int agg,
+                                         void* stream) {
+  using namespace lt;
+  LT_REQUIRE(partial && out, "unproject_finalize: null pointer");
+  LT_REQUIRE(C % 4 == 0, "unproject_finalize: C %% 4 != 0");
+  LT_REQUIRE(out_format == LT_FMT_F32 || C % 32 == 0, "unproject_finalize: split-bf16 output needs C %% 32 == 0");
+  const long total4 = (long)B * nvox * C / 4;
+  long blocks = (total4 + 255) / 256;
+  const long cap = (long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  unproject_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partial, out, out_format, B, C, nvox, agg);
+  LT_CHECK_LAUNCH("unproject_finalize_kernel");
+  return LT_OK;
+}

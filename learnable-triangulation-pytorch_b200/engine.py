@@ -1,0 +1,387 @@
+"""Native inference executor for the volumetric path.
+
+Walks the parameter-holding module tree (pose_resnet.PoseResNet, v2v.V2VModel, the 1x1
+`process_features` conv) once, folds BatchNorm into per-channel scale/shift, packs the filters
+into the layouts the kernels want, and then runs the whole device side of
+`VolumetricTriangulationNet.forward` (reference triangulation.py:250-353) as a sequence of
+C-ABI launches on the current CUDA stream -- optionally captured into one CUDA graph.
+
+Data layout in HBM: every activation is channels-last ([N][D][H][W][C]); 2-D maps use D = 1.
+  mode "simt": float32 activations, exact-fp32 FFMA convs (parity mode / checker)
+  mode "tc"  : split-bf16 activations, tcgen05 convs with 3-term products (fp32-grade)
+  mode "tc1" : split-bf16 activations, tcgen05 convs with high parts only (bf16-grade, fast)
+Layers the tensor-core kernel does not cover (the 3-channel stem and the six stride-2 convs of
+the trunk) run on the FFMA kernel in every mode.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import capi
+from .capi import FMT_F32, FMT_S32, CONV_SIMT, CONV_TC, CONV_TC1, RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Act:
+    """Channels-last activation: `data` is float32 [N,D,H,W,C] or bfloat16 [N,D,H,W,2C] (split-bf16)."""
+    __slots__ = ("data", "N", "D", "H", "W", "C", "fmt")
+
+    def __init__(self, N, D, H, W, C, fmt, device, zero=False):
+        self.N, self.D, self.H, self.W, self.C, self.fmt = N, D, H, W, C, fmt
+        alloc = torch.zeros if zero else torch.empty
+        if fmt == FMT_F32:
+            self.data = alloc((N, D, H, W, C), dtype=torch.float32, device=device)
+        else:
+            assert C % 32 == 0
+            self.data = alloc((N, D, H, W, 2 * C), dtype=torch.bfloat16, device=device)
+
+    @property
+    def pixels(self):
+        return self.N * self.D * self.H * self.W
+
+
+class ConvPack:
+    """One (phase of a) convolution, ready to launch: packed filter + folded scale/shift + geometry."""
+    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt")
+
+
+def _fold_bn(conv_bias, bn, cout, device):
+    """BatchNorm (eval) + conv bias -> y = acc * scale + shift."""
+    if bn is not None:
+        inv = (bn.running_var.detach().double() + bn.eps).rsqrt()
+        g = bn.weight.detach().double() if bn.weight is not None else torch.ones(cout, dtype=torch.double, device=device)
+        b = bn.bias.detach().double() if bn.bias is not None else torch.zeros(cout, dtype=torch.double, device=device)
+        scale = g * inv
+        shift = b - bn.running_mean.detach().double() * scale
+        if conv_bias is not None:
+            shift = shift + conv_bias.detach().double() * scale
+    else:
+        scale = torch.ones(cout, dtype=torch.double, device=device)
+        shift = conv_bias.detach().double() if conv_bias is not None else torch.zeros(cout, dtype=torch.double, device=device)
+    return scale.float(), shift.float()
+
+
+class NativeEngine:
+    def __init__(self, model, mode="tc", use_graph=True):
+        assert mode in ("simt", "tc", "tc1")
+        self.model = model
+        self.mode = mode
+        self.use_graph = use_graph
+        self.act_fmt = FMT_F32 if mode == "simt" else FMT_S32
+        self.tc_impl = {"simt": CONV_SIMT, "tc": CONV_TC, "tc1": CONV_TC1}[mode]
+        self._packs = None
+        self._packs_version = None
+        self._graphs = {}
+        self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
+        capi.lib()                 # fail loudly if the extension is missing
+
+    # ------------------------------------------------------------------ weight packing
+    def _param_version(self):
+        return tuple(p._version for p in self.model.parameters()) + tuple(b._version for b in self.model.buffers())
+
+    def _pack(self, w_taps, bias, bn, k, stride, pad, force_simt=False, out_fmt=None):
+        """w_taps: float32 [taps][Cin][Cout] (device)."""
+        dev = w_taps.device
+        taps, cin, cout = w_taps.shape
+        out_fmt = self.act_fmt if out_fmt is None else out_fmt
+        pk = ConvPack()
+        pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
+        use_tc = (self.mode != "simt") and not force_simt and max(stride) == 1
+        scale, shift = _fold_bn(bias, bn, cout, dev)
+        if use_tc:
+            cin_p = _round_up(cin, 32)
+            cout_p = _round_up(cout, 32 if out_fmt == FMT_S32 else 16)
+            wp = torch.zeros((taps, cin_p, cout_p), dtype=torch.float32, device=dev)
+            wp[:, :cin, :cout] = w_taps
+            packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.bfloat16, device=dev)
+            capi.conv_tc_pack_weights(wp.contiguous(), packed, taps, cin_p, cout_p)
+            pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = packed, cin_p, cout_p, self.tc_impl, FMT_S32
+        else:
+            cout_p = _round_up(cout, 4)
+            wp = torch.zeros((taps, cin, cout_p), dtype=torch.float32, device=dev)
+            wp[:, :, :cout] = w_taps
+            pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = wp.contiguous(), cin, cout_p, CONV_SIMT, FMT_F32
+        pk.scale = torch.zeros(cout_p, dtype=torch.float32, device=dev)
+        pk.shift = torch.zeros(cout_p, dtype=torch.float32, device=dev)
+        pk.scale[:cout] = scale
+        pk.shift[:cout] = shift
+        return pk
+
+    def _pack_conv(self, conv, bn, cin_pad=None, **kw):
+        w = conv.weight.detach().float()
+        if w.dim() == 4:   # (Cout, Cin, KH, KW)
+            k = (1,) + tuple(conv.kernel_size)
+            stride = (1,) + tuple(conv.stride)
+            pad = (0,) + tuple(conv.padding)
+            wt = w.permute(2, 3, 1, 0).reshape(k[1] * k[2], w.shape[1], w.shape[0])
+        else:              # (Cout, Cin, KD, KH, KW)
+            k, stride, pad = tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
+            wt = w.permute(2, 3, 4, 1, 0).reshape(k[0] * k[1] * k[2], w.shape[1], w.shape[0])
+        if cin_pad is not None and cin_pad > wt.shape[1]:
+            wz = torch.zeros((wt.shape[0], cin_pad, wt.shape[2]), dtype=wt.dtype, device=wt.device)
+            wz[:, :wt.shape[1]] = wt
+            wt = wz
+        return self._pack(wt.contiguous(), conv.bias, bn, k, stride, pad, **kw)
+
+    def _pack_deconv2d_k4s2(self, deconv, bn):
+        """ConvTranspose2d(k=4, s=2, p=1) as four 2x2 stride-1 convs, one per output parity.
+
+        out[2m+py] takes ky in {3,1} (input rows m-1, m) for py=0 and {2,0} (rows m, m+1) for py=1.
+        """
+        w = deconv.weight.detach().float()  # (Cin, Cout, 4, 4)
+        assert tuple(deconv.kernel_size) == (4, 4) and tuple(deconv.stride) == (2, 2) and tuple(deconv.padding) == (1, 1)
+        phases = {}
+        sel = {0: [3, 1], 1: [2, 0]}
+        for py in (0, 1):
+            for px in (0, 1):
+                wt = w[:, :, sel[py], :][:, :, :, sel[px]]           # (Cin, Cout, 2, 2)
+                wt = wt.permute(2, 3, 0, 1).reshape(4, w.shape[0], w.shape[1]).contiguous()
+                phases[(py, px)] = self._pack(wt, deconv.bias, bn, (1, 2, 2), (1, 1, 1), (0, 1 - py, 1 - px))
+        return phases
+
+    def _pack_deconv3d_k2s2(self, deconv, bn):
+        """ConvTranspose3d(k=2, s=2): eight independent 1x1x1 convs scattered to the output parities."""
+        w = deconv.weight.detach().float()  # (Cin, Cout, 2, 2, 2)
+        phases = {}
+        for a in (0, 1):
+            for b in (0, 1):
+                for c in (0, 1):
+                    wt = w[:, :, a, b, c].reshape(1, w.shape[0], w.shape[1]).contiguous()
+                    phases[(a, b, c)] = self._pack(wt, deconv.bias, bn, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+        return phases
+
+    def prepare(self):
+        ver = self._param_version()
+        if self._packs is not None and ver == self._packs_version:
+            return
+        m = self.model
+        bb, P = m.backbone, {}
+        with torch.no_grad():
+            # stem: 3 input channels padded to 4 (float4 per pixel), always on the FFMA kernel
+            P["stem"] = self._pack_conv(bb.conv1, bb.bn1, cin_pad=4, force_simt=True)
+            for li in range(1, 5):
+                for ui, unit in enumerate(getattr(bb, "layer%d" % li)):
+                    key = "layer%d.%d" % (li, ui)
+                    for si, (conv, bn) in enumerate(unit.stages()):
+                        P["%s.c%d" % (key, si)] = self._pack_conv(conv, bn)
+                    if unit.downsample is not None:
+                        P[key + ".ds"] = self._pack_conv(unit.downsample[0], unit.downsample[1])
+            for i in (0, 3, 6):
+                P["deconv%d" % i] = self._pack_deconv2d_k4s2(bb.deconv_layers[i], bb.deconv_layers[i + 1])
+            P["process_features"] = self._pack_conv(m.process_features[0], None, out_fmt=FMT_F32)
+            v = m.volume_net
+            pad16 = 32 if self.mode != "simt" else None   # the 16-channel tensor is stored 32 wide in split-bf16
+
+            def pack_res(name, blk):
+                cin_pad = pad16 if blk.res_branch[0].in_channels == 16 else None
+                P[name + ".a"] = self._pack_conv(blk.res_branch[0], blk.res_branch[1], cin_pad=cin_pad)
+                P[name + ".b"] = self._pack_conv(blk.res_branch[3], blk.res_branch[4])
+                if len(blk.skip_con) > 0:
+                    P[name + ".s"] = self._pack_conv(blk.skip_con[0], blk.skip_con[1], cin_pad=cin_pad)
+
+            P["front0"] = self._pack_conv(v.front_layers[0].block[0], v.front_layers[0].block[1])
+            for i in (1, 2, 3):
+                pack_res("front%d" % i, v.front_layers[i])
+            ed = v.encoder_decoder
+            for lvl in range(1, 6):
+                pack_res("skip%d" % lvl, getattr(ed, "skip_res%d" % lvl))
+                pack_res("enc%d" % lvl, getattr(ed, "encoder_res%d" % lvl))
+                pack_res("dec%d" % lvl, getattr(ed, "decoder_res%d" % lvl))
+                up = getattr(ed, "decoder_upsample%d" % lvl)
+                P["up%d" % lvl] = self._pack_deconv3d_k2s2(up.block[0], up.block[1])
+            pack_res("mid", ed.mid_res)
+            pack_res("back0", v.back_layers[0])
+            P["back1"] = self._pack_conv(v.back_layers[1].block[0], v.back_layers[1].block[1])
+            P["back2"] = self._pack_conv(v.back_layers[2].block[0], v.back_layers[2].block[1])
+            P["output"] = self._pack_conv(v.output_layer, None, out_fmt=FMT_F32)
+        self._packs, self._packs_version = P, ver
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ op helpers
+    def _as_f32(self, x):
+        if x.fmt == FMT_F32:
+            return x
+        y = Act(x.N, x.D, x.H, x.W, x.C, FMT_F32, x.data.device)
+        capi.s32_to_f32(x.data, y.data, x.pixels, x.C)
+        self.launches += 1
+        return y
+
+    def _conv(self, x, pk, relu, residual=None, res_mode=RES_NONE, out=None, out_scale=(1, 1, 1), out_off=(0, 0, 0),
+              out_dims=None, out_fmt=None):
+        """Launch one conv. `out` (with out_scale/out_off) lets transposed-conv phases share an output tensor."""
+        if pk.impl == CONV_SIMT:
+            x = self._as_f32(x)
+        assert x.fmt == pk.in_fmt and x.C == pk.cin, (x.fmt, pk.in_fmt, x.C, pk.cin)
+        kd, kh, kw = pk.k
+        sd, sh, sw = pk.stride
+        pd, ph, pw = pk.pad
+        if out_dims is None:
+            od = (x.D + 2 * pd - kd) // sd + 1
+            oh = (x.H + 2 * ph - kh) // sh + 1
+            ow = (x.W + 2 * pw - kw) // sw + 1
+        else:
+            od, oh, ow = out_dims
+        if out is None:
+            fmt = self.act_fmt if out_fmt is None else out_fmt
+            c = _round_up(pk.cout, 32) if fmt == FMT_S32 else pk.cout_p
+            out = Act(x.N, od, oh, ow, c, fmt, x.data.device)
+        d = capi.ConvDesc(N=x.N, ID=x.D, IH=x.H, IW=x.W, Cin=x.C, OD=od, OH=oh, OW=ow, Cout=pk.cout_p,
+                          KD=kd, KH=kh, KW=kw, sd=sd, sh=sh, sw=sw, pd=pd, ph=ph, pw=pw,
+                          FD=out.D, FH=out.H, FW=out.W, FC=out.C,
+                          osd=out_scale[0], osh=out_scale[1], osw=out_scale[2], ood=out_off[0], ooh=out_off[1], oow=out_off[2],
+                          relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt)
+        if residual is not None:
+            assert residual.fmt == out.fmt and residual.C == out.C
+        capi.conv_nd(d, x.data, pk.w, pk.scale, pk.shift, None if residual is None else residual.data, out.data, pk.impl)
+        self.launches += 1
+        return out
+
+    def _maxpool(self, x, k, s, p):
+        od = (x.D + 2 * p[0] - k[0]) // s[0] + 1
+        oh = (x.H + 2 * p[1] - k[1]) // s[1] + 1
+        ow = (x.W + 2 * p[2] - k[2]) // s[2] + 1
+        y = Act(x.N, od, oh, ow, x.C, x.fmt, x.data.device)
+        capi.maxpool(x.data, y.data, x.fmt, x.N, x.D, x.H, x.W, x.C, k, s, p, od, oh, ow)
+        self.launches += 1
+        return y
+
+    def _deconv2d(self, x, phases):
+        c = next(iter(phases.values())).cout
+        out = Act(x.N, 1, 2 * x.H, 2 * x.W, c, self.act_fmt, x.data.device)
+        for (py, px), pk in phases.items():
+            self._conv(x, pk, relu=True, out=out, out_scale=(1, 2, 2), out_off=(0, py, px), out_dims=(1, x.H, x.W))
+        return out
+
+    def _deconv3d(self, x, phases, skip):
+        c = next(iter(phases.values())).cout
+        out = Act(x.N, 2 * x.D, 2 * x.H, 2 * x.W, c, self.act_fmt, x.data.device)
+        for (a, b, cc), pk in phases.items():
+            self._conv(x, pk, relu=True, residual=skip, res_mode=RES_AFTER_RELU, out=out, out_scale=(2, 2, 2),
+                       out_off=(a, b, cc), out_dims=(x.D, x.H, x.W))
+        return out
+
+    def _res3d(self, x, name):
+        P = self._packs
+        skip = self._conv(x, P[name + ".s"], relu=False) if (name + ".s") in P else x
+        y = self._conv(x, P[name + ".a"], relu=True)
+        return self._conv(y, P[name + ".b"], relu=True, residual=skip, res_mode=RES_BEFORE_RELU)
+
+    # ------------------------------------------------------------------ network stages
+    def backbone_features(self, images_nchw):
+        """(BV, 3, H, W) float32 -> processed features, channels-last float32 Act (BV, 1, h, w, 32).
+
+        = backbone trunk + deconvs (pose_resnet.py:293-313) + process_features (triangulation.py:344-346).
+        The 17-channel heatmap head (final_layer) is not evaluated: the volumetric forward uses it
+        only for its shape (triangulation.py:257,264-265).
+        """
+        P = self._packs
+        bv, c, H, W = images_nchw.shape
+        dev = images_nchw.device
+        x = Act(bv, 1, H, W, 4, FMT_F32, dev)
+        capi.nchw_to_nhwc(images_nchw, x.data, bv, c, H, W, 4)
+        self.launches += 1
+        x = self._conv(x, P["stem"], relu=True)
+        x = self._maxpool(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        bb = self.model.backbone
+        for li in range(1, 5):
+            for ui, unit in enumerate(getattr(bb, "layer%d" % li)):
+                key = "layer%d.%d" % (li, ui)
+                n_st = len(unit.stages())
+                identity = self._conv(x, P[key + ".ds"], relu=False) if unit.downsample is not None else x
+                y = x
+                for si in range(n_st - 1):
+                    y = self._conv(y, P["%s.c%d" % (key, si)], relu=True)
+                x = self._conv(y, P["%s.c%d" % (key, n_st - 1)], relu=True, residual=identity, res_mode=RES_BEFORE_RELU)
+        for i in (0, 3, 6):
+            x = self._deconv2d(x, P["deconv%d" % i])
+        return self._conv(x, P["process_features"], relu=False, out_fmt=FMT_F32)
+
+    def unproject(self, feats, B, V, proj, coord, agg, conf=None):
+        """feats: Act (B*V, 1, h, w, C) float32 -> volume Act (B, n, n, n, C) in the conv operand format."""
+        n = coord.shape[1]
+        vol = Act(B, n, n, n, feats.C, self.act_fmt, feats.data.device)
+        capi.unproject_aggregate(feats.data.view(B, V, feats.H, feats.W, feats.C), proj, coord.view(B, n * n * n, 3), conf,
+                                 vol.data, vol.fmt, agg)
+        self.launches += 1
+        return vol
+
+    def v2v(self, x):
+        """volume Act (B, n, n, n, 32) -> logits Act float32 channels-last (v2v.py:164-169)."""
+        P = self._packs
+        x = self._conv(x, P["front0"], relu=True)
+        for i in (1, 2, 3):
+            x = self._res3d(x, "front%d" % i)
+        skips = {}
+        for lvl in range(1, 6):
+            skips[lvl] = self._res3d(x, "skip%d" % lvl)
+            x = self._maxpool(x, (2, 2, 2), (2, 2, 2), (0, 0, 0))
+            x = self._res3d(x, "enc%d" % lvl)
+        x = self._res3d(x, "mid")
+        for lvl in range(5, 0, -1):
+            x = self._res3d(x, "dec%d" % lvl)
+            x = self._deconv3d(x, P["up%d" % lvl], skips.pop(lvl))
+        x = self._res3d(x, "back0")
+        x = self._conv(x, P["back1"], relu=True)
+        x = self._conv(x, P["back2"], relu=True)
+        return self._conv(x, P["output"], relu=False, out_fmt=FMT_F32)
+
+    def softargmax(self, logits, coord, J, multiplier, softmax):
+        B, n = logits.N, logits.D
+        nvox = n * n * n
+        dev = logits.data.device
+        volumes = torch.empty((B, J, n, n, n), dtype=torch.float32, device=dev)
+        keypoints = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+        ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=dev)
+        capi.softargmax3d(logits.data, nvox * logits.C, logits.C, 1, coord, volumes, keypoints, ws, B, J, nvox, multiplier, softmax)
+        self.launches += 3
+        return keypoints, volumes
+
+    # ------------------------------------------------------------------ whole device-side forward
+    def _device_forward(self, images, proj, position, center, step, rot, conf=None):
+        m = self.model
+        B, V = images.shape[:2]
+        n = m.volume_size
+        dev = images.device
+        self.launches = 0
+        coord = torch.empty((B, n, n, n, 3), dtype=torch.float32, device=dev)
+        capi.coord_volume(position, center, step, rot, coord, m.transfer_cmu_to_human36m)
+        self.launches += 1
+        feats = self.backbone_features(images.reshape(B * V, *images.shape[2:]))
+        agg = capi.AGG[m.volume_aggregation_method]
+        vol = self.unproject(feats, B, V, proj, coord, agg, conf)
+        logits = self.v2v(vol)
+        keypoints, volumes = self.softargmax(logits, coord, m.num_joints, m.volume_multiplier, m.volume_softmax)
+        # (B, V, 32, h, w) view of the channels-last features (values identical, strides permuted)
+        features = feats.data.view(B, V, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
+        return keypoints, features, volumes, coord
+
+    def forward(self, images, proj, position, center, step, rot):
+        """All inputs are CUDA float32 tensors. Returns (keypoints, features, volumes, coord_volumes)."""
+        self.prepare()
+        if not self.use_graph:
+            return self._device_forward(images, proj, position, center, step, rot)
+        key = (tuple(images.shape), images.device.index)
+        g = self._graphs.get(key)
+        if g is None:
+            static_in = [t.clone() for t in (images, proj, position, center, step, rot)]
+            s = torch.cuda.Stream(device=images.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._device_forward(*static_in)      # warm-up (module load, func attributes)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._device_forward(*static_in)
+            g = (graph, static_in, static_out, self.launches)
+            self._graphs[key] = g
+        graph, static_in, static_out, launches = g
+        for dst, src in zip(static_in, (images, proj, position, center, step, rot)):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        self.launches = launches
+        return static_out

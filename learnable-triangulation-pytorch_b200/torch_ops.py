@@ -1,0 +1,49 @@
+"""Autograd-capable torch formulations of the two custom ops (backend="torch").
+
+Used when gradients are needed (training is a "next" row) and for host-logic
+tests on machines without a GPU.  They are vectorised over batch and views (no Python loops over
+B*V like the reference) and are NOT the product inference path: the native backend never routes
+through this file.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregation_method="sum", vol_confidences=None):
+    """Same contract as reference op.py:99-166, batched."""
+    B, V, C, h, w = heatmaps.shape
+    vol_shape = coord_volumes.shape[1:4]
+    pts = coord_volumes.reshape(B, 1, -1, 3)
+    ones = torch.ones_like(pts[..., :1])
+    proj = torch.cat([pts, ones], dim=-1) @ proj_matricies.transpose(-1, -2)       # (B, V, N, 3)
+    z = proj[..., 2]
+    invalid = z <= 0.0
+    z = torch.where(z == 0.0, torch.ones_like(z), z)
+    xy = proj[..., :2] / z.unsqueeze(-1)
+    # reference quirk (op.py:128-129): x is normalised by the map height, y by the width
+    gx = 2 * (xy[..., 0] / h - 0.5)
+    gy = 2 * (xy[..., 1] / w - 0.5)
+    grid = torch.stack([gx, gy], dim=-1).reshape(B * V, -1, 1, 2)
+    sampled = F.grid_sample(heatmaps.reshape(B * V, C, h, w), grid, align_corners=True)   # (BV, C, N, 1)
+    sampled = sampled.reshape(B, V, C, -1)
+    sampled = sampled.masked_fill(invalid.unsqueeze(2), 0.0)
+    if volume_aggregation_method.startswith("conf"):
+        out = (sampled * vol_confidences.reshape(B, V, C, 1)).sum(1)
+    elif volume_aggregation_method == "sum":
+        out = sampled.sum(1)
+    elif volume_aggregation_method == "max":
+        out = sampled.max(1)[0]
+    elif volume_aggregation_method == "softmax":
+        out = (sampled * torch.softmax(sampled, dim=1)).sum(1)
+    else:
+        raise ValueError("Unknown volume_aggregation_method: {}".format(volume_aggregation_method))
+    return out.reshape(B, C, *vol_shape)
+
+
+def integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax=True):
+    """Same contract as reference op.py:84-96."""
+    B, J = volumes.shape[:2]
+    flat = volumes.reshape(B, J, -1)
+    flat = torch.softmax(flat, dim=2) if softmax else F.relu(flat)
+    coords = flat @ coord_volumes.reshape(B, -1, 3)
+    return coords, flat.reshape(volumes.shape)

@@ -1,0 +1,152 @@
+"""Drop-in `VolumetricTriangulationNet` (reference mvn/models/triangulation.py:203-355).
+
+Same constructor (`config`, `device`), same `forward(images, proj_matricies, batch)` 7-tuple, same
+attribute names (`backbone`, `process_features`, `volume_net`) and `state_dict()` keys, same
+config side effects (triangulation.py:228-231) -- so the reference `train.py` can construct, load,
+wrap in DDP and call it unchanged.
+
+backend="native" (default; eval/no-grad on a CUDA device): host geometry is vectorised numpy
+(float64, cast last, like the reference) and everything on the device runs in the hand-written
+sm_100a kernels through engine.NativeEngine.  backend="torch": autograd-capable torch ops
+(training, CPU plumbing).  Nothing switches backend silently.
+"""
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import multiview, op, pose_resnet, torch_ops, volumetric
+from .v2v import V2VModel
+
+
+def _base_points(batch, batch_size, kind, use_gt_pelvis):
+    """Pelvis (mpii: joint 6) or hip midpoint (coco) per sample, float64 (triangulation.py:286-296)."""
+    pts = np.empty((batch_size, 3), dtype=np.float64)
+    for b in range(batch_size):
+        kp = batch["keypoints_3d"][b] if use_gt_pelvis else batch["pred_keypoints_3d"][b]
+        if kind == "coco":
+            pts[b] = (kp[11, :3] + kp[12, :3]) / 2
+        elif kind == "mpii":
+            pts[b] = kp[6, :3]
+        else:
+            raise KeyError("unknown skeleton kind {!r}".format(kind))
+    return pts
+
+
+class VolumetricTriangulationNet(nn.Module):
+    def __init__(self, config, device="cuda:0", backend=None, conv_mode=None, use_cuda_graph=True):
+        super().__init__()
+        m = config.model
+        self.num_joints = m.backbone.num_joints
+        self.volume_aggregation_method = m.volume_aggregation_method
+        self.volume_softmax = m.volume_softmax
+        self.volume_multiplier = m.volume_multiplier
+        self.volume_size = m.volume_size
+        self.cuboid_side = m.cuboid_side
+        self.kind = m.kind
+        self.use_gt_pelvis = m.use_gt_pelvis
+        self.heatmap_softmax = m.heatmap_softmax
+        self.heatmap_multiplier = m.heatmap_multiplier
+        self.transfer_cmu_to_human36m = m.transfer_cmu_to_human36m if hasattr(m, "transfer_cmu_to_human36m") else False
+
+        # the reference mutates the caller's config here (triangulation.py:228-231); so do we
+        m.backbone.alg_confidences = False
+        m.backbone.vol_confidences = False
+        if self.volume_aggregation_method.startswith("conf"):
+            m.backbone.vol_confidences = True
+
+        self.backbone = pose_resnet.get_pose_net(m.backbone, device=device)
+        for p in self.backbone.final_layer.parameters():
+            p.requires_grad = False
+        self.process_features = nn.Sequential(nn.Conv2d(256, 32, 1))
+        self.volume_net = V2VModel(32, self.num_joints)
+
+        self.backend = backend or os.environ.get("LT_B200_BACKEND", "native")
+        self.conv_mode = conv_mode or os.environ.get("LT_B200_CONV", "tc")
+        self.use_cuda_graph = use_cuda_graph
+        self.clone_outputs = True
+        self._engine = None
+
+    # ---------------------------------------------------------------- host-side geometry
+    def _host_geometry(self, batch, batch_size, image_shape, heatmap_shape):
+        proj = multiview.stack_projections(batch["cameras"], image_shape, heatmap_shape)      # (B, V, 3, 4) f32
+        base = _base_points(batch, batch_size, self.kind, self.use_gt_pelvis)                 # (B, 3) f64
+        sides = np.array([self.cuboid_side] * 3, dtype=np.float64)
+        position = base - sides / 2
+        cuboids = [volumetric.Cuboid3D(position[b], sides) for b in range(batch_size)]
+        axis = [0, 1, 0] if self.kind == "coco" else [0, 0, 1]
+        rots = np.empty((batch_size, 3, 3), dtype=np.float64)
+        for b in range(batch_size):
+            theta = np.random.uniform(0.0, 2 * np.pi) if self.training else 0.0   # triangulation.py:318-321
+            rots[b] = volumetric.get_rotation_matrix(axis, theta)
+        step = sides / (self.volume_size - 1)
+        return proj, base, position, step, rots, cuboids
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import NativeEngine
+            self._engine = NativeEngine(self, mode=self.conv_mode, use_graph=self.use_cuda_graph)
+        return self._engine
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, images, proj_matricies, batch):
+        if self.backend == "torch":
+            return self._forward_torch(images, batch)
+        if self.backend != "native":
+            raise ValueError("unknown backend {!r}".format(self.backend))
+        if not images.is_cuda:
+            raise RuntimeError("lt_b200 native backend needs CUDA tensors (got %s); construct the model with "
+                               "backend='torch' for the CPU/autograd path" % images.device)
+        if self.training or torch.is_grad_enabled():
+            raise RuntimeError("lt_b200 native backend is inference-only: call model.eval() under torch.no_grad(), "
+                               "or construct the model with backend='torch' (LT_B200_BACKEND=torch) for training")
+        if self.volume_aggregation_method.startswith("conf"):
+            raise NotImplementedError("conf/conf_norm aggregation needs the vol_confidences head: use backend='torch'")
+
+        B, V = images.shape[:2]
+        H, W = images.shape[3:]
+        hm_shape = (H // 4, W // 4)   # stem /2, maxpool /2, three stride-2 stages, three x2 deconvs
+        proj, base, position, step, rots, cuboids = self._host_geometry(batch, B, (H, W), hm_shape)
+        dev = images.device
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=True)
+
+        kp, features, volumes, coord = self.engine().forward(
+            images.float().contiguous(), up(proj), up(position), up(base), up(step), up(rots.reshape(B, 9)))
+        base_points = up(base)
+        if self.clone_outputs and self.use_cuda_graph:
+            kp, features, volumes, coord = kp.clone(), features.clone(), volumes.clone(), coord.clone()
+        return kp, features, volumes, None, cuboids, coord, base_points
+
+    def _forward_torch(self, images, batch):
+        dev = images.device
+        B, V = images.shape[:2]
+        flat = images.reshape(-1, *images.shape[2:])
+        heatmaps, features, _, vol_conf = self.backbone(flat)
+        if vol_conf is not None:
+            vol_conf = vol_conf.view(B, V, *vol_conf.shape[1:])
+            if self.volume_aggregation_method == "conf_norm":
+                vol_conf = vol_conf / vol_conf.sum(dim=1, keepdim=True)
+        image_shape, hm_shape = tuple(images.shape[3:]), tuple(heatmaps.shape[2:])
+        proj, base, position, step, rots, cuboids = self._host_geometry(batch, B, image_shape, hm_shape)
+        proj_t = torch.from_numpy(proj).to(dev)
+        n = self.volume_size
+        idx = torch.arange(n, device=dev, dtype=torch.float)
+        grid = torch.stack(torch.meshgrid(idx, idx, idx, indexing="ij"), dim=-1)              # (n, n, n, 3)
+        pos_t = torch.from_numpy(position).float().to(dev)
+        cen_t = torch.from_numpy(base).float().to(dev)
+        step_t = torch.from_numpy(step).float().to(dev)
+        rot_t = torch.from_numpy(rots).float().to(dev)
+        coord = pos_t.view(B, 1, 1, 1, 3) + step_t * grid.unsqueeze(0)
+        coord = coord - cen_t.view(B, 1, 1, 1, 3)
+        coord = torch.einsum("bij,bxyzj->bxyzi", rot_t, coord) + cen_t.view(B, 1, 1, 1, 3)
+        if self.transfer_cmu_to_human36m:
+            coord = coord.permute(0, 1, 3, 2, 4).flip(2)
+        features = self.process_features(features)
+        features = features.view(B, V, *features.shape[1:])
+        volumes = torch_ops.unproject_heatmaps(features, proj_t, coord, self.volume_aggregation_method, vol_conf)
+        volumes = self.volume_net(volumes)
+        kp, volumes = torch_ops.integrate_tensor_3d_with_coordinates(volumes * self.volume_multiplier, coord, self.volume_softmax)
+        return kp, features, volumes, vol_conf, cuboids, coord, cen_t

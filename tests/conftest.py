@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = "/root/reference"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def has_reference():
+    return os.path.isdir(os.path.join(REFERENCE, "mvn"))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def rel_err(a, b):
+    """max|a-b| relative to max(|b|, spread(b)) -- SURVEY.md section 8d parity definition."""
+    import numpy as np
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    denom = max(float(np.abs(b).max()), float(b.std()), 1e-30)
+    return float(np.abs(a - b).max()) / denom
