@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Benchmark of the volumetric-triangulation hot path (BASELINE.json metric: volumetric samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--mode tc|tc1|simt]
+
+One "step" = one eval forward of a batch of synthetic multi-view samples (4 views of 3x384x384 -> 17 joints,
+ResNet-152 backbone, 64^3 grid, softmax aggregation: BASELINE config #2, batch 8 per GPU) through the native
+sm_100a path.  Prints ONE JSON line (rank 0).  See the module docstrings / DESIGN.md for the field definitions.
+
+  value     device-timed throughput, inputs resident in HBM (CUDA events around K graph replays, max over ranks)
+  e2e       same metric through the public nn.Module call with pinned-host images copied H2D and the keypoints
+            read back D2H inside the timed region
+  roofline  dominant kernel (tcgen05 conv): algorithmic conv FLOPs / summed per-launch CUDA-event time, vs the
+            measured dense bf16 peak (MEASURED_PEAKS.json); unprojection / soft-argmax HBM rooflines alongside
+  cpu_baseline  the CPU oracle port of the reference path timed on this box's host cores (rank 0, bounded sample)
+
+--impl reference times the reference's CPU implementation of the path (the oracle port: the reference is pure
+Python and is not present on the GPU box) with all host threads, same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "volumetric samples/sec (4-view 384x384, 64^3 grid)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("LT_B200_CONV", "tc"), choices=["tc", "tc1", "simt"])
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step")
+    ap.add_argument("--views", type=int, default=4)
+    ap.add_argument("--image", type=int, default=384)
+    ap.add_argument("--volume", type=int, default=64)
+    ap.add_argument("--layers", type=int, default=152)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-calibrate", action="store_true", help="keep PyTorch default init (faster start, degenerate signal)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_oracle_rate(args, steps, warmup):
+    """samples/sec of the CPU oracle port of the reference path on this box's host cores (bounded sample: B=1)."""
+    from oracle import vol_oracle as O
+    import lt_b200
+    from lt_b200 import testing
+    torch.set_num_threads(os.cpu_count())
+    cfg = testing.make_config(num_layers=args.layers, volume_size=args.volume)
+    model = lt_b200.VolumetricTriangulationNet(cfg, device="cpu", backend="torch")   # parameter holder only
+    sd = model.state_dict()
+    images, batch = testing.make_batch(1, args.views, image_size=args.image, seed=0)
+    base = np.stack([k[6, :3] for k in batch["keypoints_3d"]])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.volumetric_forward(sd, images, batch["cameras"], base, volume_size=args.volume)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return 1.0 / dt, dt, torch.get_num_threads()
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, dt, threads = cpu_oracle_rate(args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch 1 per step (bounded CPU sample)"
+                   % (args.layers, args.views, args.image, args.image, args.volume)},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": "%d timed forwards of one %d-view sample, CPU oracle port (torch fp32 + numpy), %d threads"
+                                   % (steps, args.views, threads)},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main_native(args, rank, world, local_rank):
+    import lt_b200
+    from lt_b200 import testing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (the native path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, V, S, n = args.batch, args.views, args.image, args.volume
+    cfg = testing.make_config(num_layers=args.layers, volume_size=n)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="native", conv_mode=args.mode, use_cuda_graph=True)
+    if not args.no_calibrate:
+        model.backend = "torch"
+        testing.randomize_weights(model, seed=0, calib_size=S, calib_views=1)
+        model.backend = "native"
+    model = model.to(dev).eval()
+    images, batch = testing.make_batch(B, V, image_size=S, seed=rank)
+    pinned = images.pin_memory()
+    images_dev = images.to(dev)
+    h2d = images.numel() * 4
+    eng = model.engine()
+    model.clone_outputs = False
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.no_grad():
+        # ---- device-resident arm: graph replays, CUDA events, L2 flushed between iterations ----
+        for _ in range(max(args.warmup, 3)):
+            out = model(images_dev, None, batch)
+        barrier()
+        launches = eng.launches
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = model(images_dev, None, batch)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        clocks = sampler.summary()
+
+        # ---- end-to-end arm: public module call, pinned host images -> device, keypoints -> host ----
+        for _ in range(2):
+            kp = model(pinned.to(dev, non_blocking=True), None, batch)[0].cpu()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            kp = model(pinned.to(dev, non_blocking=True), None, batch)[0].cpu()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        d2h = kp.numel() * 4
+
+        # ---- per-kernel timing for the roofline: one eager (non-graph) forward with event pairs per launch ----
+        eng.use_graph = False
+        model.use_cuda_graph = False
+        model(images_dev, None, batch)
+        eng.timeline = []
+        model(images_dev, None, batch)
+        torch.cuda.synchronize()
+        agg = {}
+        for label, flops, nbytes, a, b in eng.timeline:
+            r = agg.setdefault(label, [0.0, 0.0, 0.0, 0])
+            r[0] += a.elapsed_time(b); r[1] += flops; r[2] += nbytes; r[3] += 1
+        eng.timeline = None
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    total_samples = B * world * args.steps
+    value = total_samples / (dev_ms / 1e3)
+    e2e = total_samples / e2e_s
+
+    pk = peaks()
+    roof = None
+    extra = {}
+    conv_key = "conv_tc" if "conv_tc" in agg else "conv_ffma"
+    if conv_key in agg:
+        ms, fl, _, cnt = agg[conv_key]
+        ach = fl / (ms / 1e3) / 1e12
+        peak = pk["bf16_tflops"] if conv_key == "conv_tc" else 75.0
+        roof = {"kernel": conv_key + "_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "launches": cnt, "ms_per_step": ms,
+                "peak_source": pk["src"] + (" sustained dense bf16 (cuBLAS)" if conv_key == "conv_tc" else " nominal fp32 FFMA")}
+    for key in ("unproject", "softargmax", "conv_ffma"):
+        if key in agg and key != conv_key:
+            ms, fl, nb, cnt = agg[key]
+            if nb > 0:
+                ach = nb / (ms / 1e3) / 1e9
+                extra["roofline_" + key] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                            "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt}
+            else:
+                extra["time_" + key] = {"ms_per_step": ms, "tflops": fl / (ms / 1e3) / 1e12, "launches": cnt}
+    extra["step_breakdown_ms"] = {k: round(v[0], 3) for k, v in agg.items()}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, dt, threads = cpu_oracle_rate(args, 2, 1)
+        cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "2 timed forwards of one %d-view sample (same config), CPU oracle port, %d threads" % (V, threads)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"tc": "bf16x3 (split-bf16 3-term products, fp32 accumulate)", "tc1": "bf16", "simt": "f32"}[args.mode],
+            "data": "synthetic",
+            "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch %d per GPU"
+                                   % (args.layers, V, S, S, n, B),
+                       "global_batch": B * world, "parallelism": "dp%d (batch replicas, no data-path collective)" % world,
+                       "conv_mode": args.mode, "l2": "256 MB buffer written between timed iterations (L2 flush)",
+                       "weights": "random (seeded recipe, BN calibrated)" if not args.no_calibrate else "random (default init)"},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank)
+    else:
+        main_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

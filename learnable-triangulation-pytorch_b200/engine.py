@@ -46,7 +46,7 @@ class Act:
 
 class ConvPack:
     """One (phase of a) convolution, ready to launch: packed filter + folded scale/shift + geometry."""
-    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt")
+    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs")
 
 
 def _fold_bn(conv_bias, bn, cout, device):
@@ -65,6 +65,24 @@ def _fold_bn(conv_bias, bn, cout, device):
     return scale.float(), shift.float()
 
 
+class _Timed:
+    """CUDA-event bracket around one launch (only when a timeline list is installed; never during graph capture)."""
+
+    def __init__(self, timeline, label, flops, nbytes):
+        self.tl, self.label, self.flops, self.nbytes = timeline, label, flops, nbytes
+
+    def __enter__(self):
+        if self.tl is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.tl is not None:
+            self.e1.record()
+            self.tl.append((self.label, self.flops, self.nbytes, self.e0, self.e1))
+        return False
+
+
 class NativeEngine:
     def __init__(self, model, mode="tc", use_graph=True):
         assert mode in ("simt", "tc", "tc1")
@@ -77,6 +95,7 @@ class NativeEngine:
         self._packs_version = None
         self._graphs = {}
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
+        self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
 
     # ------------------------------------------------------------------ weight packing
@@ -90,6 +109,7 @@ class NativeEngine:
         out_fmt = self.act_fmt if out_fmt is None else out_fmt
         pk = ConvPack()
         pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
+        pk.kmacs = taps * cin * cout   # algorithmic MACs per output position
         use_tc = (self.mode != "simt") and not force_simt and max(stride) == 1
         scale, shift = _fold_bn(bias, bn, cout, dev)
         if use_tc:
@@ -125,7 +145,9 @@ class NativeEngine:
             wz = torch.zeros((wt.shape[0], cin_pad, wt.shape[2]), dtype=wt.dtype, device=wt.device)
             wz[:, :wt.shape[1]] = wt
             wt = wz
-        return self._pack(wt.contiguous(), conv.bias, bn, k, stride, pad, **kw)
+        pk = self._pack(wt.contiguous(), conv.bias, bn, k, stride, pad, **kw)
+        pk.kmacs = pk.taps * w.shape[1] * w.shape[0]
+        return pk
 
     def _pack_deconv2d_k4s2(self, deconv, bn):
         """ConvTranspose2d(k=4, s=2, p=1) as four 2x2 stride-1 convs, one per output parity.
@@ -236,9 +258,14 @@ class NativeEngine:
                           relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt)
         if residual is not None:
             assert residual.fmt == out.fmt and residual.C == out.C
-        capi.conv_nd(d, x.data, pk.w, pk.scale, pk.shift, None if residual is None else residual.data, out.data, pk.impl)
+        with self._timed("conv_tc" if pk.impl != CONV_SIMT else "conv_ffma",
+                         flops=2.0 * x.N * od * oh * ow * pk.kmacs):
+            capi.conv_nd(d, x.data, pk.w, pk.scale, pk.shift, None if residual is None else residual.data, out.data, pk.impl)
         self.launches += 1
         return out
+
+    def _timed(self, label, flops=0.0, nbytes=0.0):
+        return _Timed(self.timeline, label, flops, nbytes)
 
     def _maxpool(self, x, k, s, p):
         od = (x.D + 2 * p[0] - k[0]) // s[0] + 1
@@ -304,8 +331,11 @@ class NativeEngine:
         """feats: Act (B*V, 1, h, w, C) float32 -> volume Act (B, n, n, n, C) in the conv operand format."""
         n = coord.shape[1]
         vol = Act(B, n, n, n, feats.C, self.act_fmt, feats.data.device)
-        capi.unproject_aggregate(feats.data.view(B, V, feats.H, feats.W, feats.C), proj, coord.view(B, n * n * n, 3), conf,
-                                 vol.data, vol.fmt, agg)
+        # algorithmic bytes: volume write + compulsory feature read + coordinate read (DESIGN.md)
+        nbytes = B * (n ** 3 * feats.C * 4 + V * feats.H * feats.W * feats.C * 4 + n ** 3 * 12)
+        with self._timed("unproject", nbytes=nbytes):
+            capi.unproject_aggregate(feats.data.view(B, V, feats.H, feats.W, feats.C), proj, coord.view(B, n * n * n, 3), conf,
+                                     vol.data, vol.fmt, agg)
         self.launches += 1
         return vol
 
@@ -336,7 +366,8 @@ class NativeEngine:
         volumes = torch.empty((B, J, n, n, n), dtype=torch.float32, device=dev)
         keypoints = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
         ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=dev)
-        capi.softargmax3d(logits.data, nvox * logits.C, logits.C, 1, coord, volumes, keypoints, ws, B, J, nvox, multiplier, softmax)
+        with self._timed("softargmax", nbytes=B * (2 * J * nvox * 4 + nvox * 12)):
+            capi.softargmax3d(logits.data, nvox * logits.C, logits.C, 1, coord, volumes, keypoints, ws, B, J, nvox, multiplier, softmax)
         self.launches += 3
         return keypoints, volumes
 

@@ -105,7 +105,16 @@ def gen_forward():
     print("forward_r50: max prob", float(flat.max()), "uniform", 1.0 / n ** 3, "kp spread", kp.std(dim=1))
 
 
+def gen_state_dict_keys():
+    """Key -> shape table of the reference ResNet-152 volumetric model (1311 tensors)."""
+    import json
+    ref = RefNet(testing.make_config(num_layers=152), device="cpu")
+    with open(os.path.join(HERE, "state_dict_r152.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in ref.state_dict().items()}, f)
+
+
 if __name__ == "__main__":
+    gen_state_dict_keys()
     gen_unproject()
     gen_softargmax()
     gen_forward()

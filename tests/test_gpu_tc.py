@@ -1,0 +1,125 @@
+"""GPU parity tests of the tcgen05/TMA convolution path (through the C ABI): GEMM core self-test, conv vs the
+fp32 torch reference of the same op, transposed-conv phases, and tensor-core vs FFMA kernels at larger sizes."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from lt_b200 import capi
+from test_gpu_ops import _engine, _bn_for, act_from_nchw, act_to_nchw, DEV
+
+pytestmark = pytest.mark.gpu
+
+# fp32-grade: 3-term split-bf16 products;  bf16-grade: high parts only
+TOL = {"tc": 5e-5, "tc1": 2e-2}
+
+
+@pytest.mark.parametrize("mnk", [(128, 16, 64), (128, 32, 128), (256, 64, 64), (384, 128, 256), (200, 256, 512), (128, 48, 64)])
+def test_tc_gemm_selftest(mnk):
+    M, N, K = mnk
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV).bfloat16().contiguous()
+    b = torch.randn(N, K, generator=g).to(DEV).bfloat16().contiguous()
+    d = torch.zeros(M * N + 2 * N, dtype=torch.float32, device=DEV)
+    capi.tc_gemm_selftest(a, b, d, M, N, K)
+    torch.cuda.synchronize()
+    got = d[:M * N].view(M, N).cpu().double()
+    want = a.cpu().double() @ b.cpu().double().t()
+    assert rel_err(got.numpy(), want.numpy()) < 1e-5     # bf16 products are exact in fp32; only summation order differs
+
+
+TC_CASES = [
+    # (dims, cin, cout, k, pad, spatial, batch)
+    (2, 64, 64, 1, 0, (16, 8), 1),
+    (2, 64, 64, 1, 0, (12, 12), 3),
+    (2, 256, 64, 1, 0, (24, 24), 2),
+    (2, 64, 256, 1, 0, (12, 12), 2),
+    (2, 64, 64, 3, 1, (12, 12), 2),
+    (2, 128, 128, 3, 1, (9, 7), 3),
+    (3, 32, 32, 3, 1, (8, 8, 8), 2),
+    (3, 32, 16, 7, 3, (8, 8, 8), 1),
+    (3, 16, 32, 3, 1, (8, 8, 8), 1),
+    (3, 32, 17, 1, 0, (8, 8, 8), 2),
+    (3, 128, 128, 3, 1, (2, 2, 2), 2),
+    (3, 64, 128, 3, 1, (4, 4, 4), 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("mode", ["tc", "tc1"])
+def test_conv_tc_vs_torch(case, mode):
+    dims, cin, cout, k, pad, spatial, N = case
+    torch.manual_seed(cin * 13 + cout + k)
+    conv = (torch.nn.Conv2d if dims == 2 else torch.nn.Conv3d)(cin, cout, k, 1, pad, bias=(dims == 3)).eval()
+    bn = _bn_for(conv, 7)
+    x = torch.randn(N, cin, *spatial)
+    with torch.no_grad():
+        y0 = bn(conv(x))
+        res = torch.randn_like(y0)
+        want = F.relu(y0 + res)
+    e = _engine(mode)
+    cin_p = (cin + 31) // 32 * 32
+    cout_p = (cout + 31) // 32 * 32
+    pk = e._pack_conv(conv.to(DEV), bn.to(DEV), cin_pad=cin_p)
+    assert pk.impl in (capi.CONV_TC, capi.CONV_TC1)
+    xa = act_from_nchw(x, capi.FMT_S32, pad_c=cin_p)
+    ra = act_from_nchw(res, capi.FMT_S32, pad_c=cout_p)
+    ya = e._conv(xa, pk, relu=True, residual=ra, res_mode=capi.RES_BEFORE_RELU)
+    torch.cuda.synchronize()
+    full = act_to_nchw(ya).cpu()
+    got = full[:, :cout]
+    if dims == 2:
+        got = got.squeeze(2)
+    assert rel_err(got.numpy(), want.numpy()) < TOL[mode]
+    if cout_p > cout:
+        assert float(full[:, cout:].abs().max()) == 0.0, "padding channels must be written as zeros"
+
+
+def test_conv_tc_fp32_output_and_no_residual():
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(256, 32, 1).eval()
+    x = torch.randn(2, 256, 24, 24)
+    with torch.no_grad():
+        want = conv(x)
+    e = _engine("tc")
+    pk = e._pack_conv(conv.to(DEV), None, out_fmt=capi.FMT_F32)
+    ya = e._conv(act_from_nchw(x, capi.FMT_S32), pk, relu=False, out_fmt=capi.FMT_F32)
+    assert ya.fmt == capi.FMT_F32
+    assert rel_err(act_to_nchw(ya, 32).squeeze(2).cpu().numpy(), want.numpy()) < TOL["tc"]
+
+
+def test_deconv_phases_tc_vs_torch():
+    torch.manual_seed(4)
+    e = _engine("tc")
+    dc = torch.nn.ConvTranspose2d(64, 64, 4, 2, 1, 0, bias=False).eval()
+    bn = _bn_for(dc, 2)
+    x = torch.randn(2, 64, 6, 12)
+    with torch.no_grad():
+        want = F.relu(bn(dc(x)))
+    got = act_to_nchw(e._deconv2d(act_from_nchw(x, capi.FMT_S32), e._pack_deconv2d_k4s2(dc.to(DEV), bn.to(DEV)))).squeeze(2).cpu()
+    assert rel_err(got.numpy(), want.numpy()) < TOL["tc"]
+    dc3 = torch.nn.ConvTranspose3d(64, 32, 2, 2).eval()
+    bn3 = _bn_for(dc3, 3)
+    x3 = torch.randn(2, 64, 4, 4, 4)
+    skip = torch.randn(2, 32, 8, 8, 8)
+    with torch.no_grad():
+        want3 = F.relu(bn3(dc3(x3))) + skip
+    got3 = act_to_nchw(e._deconv3d(act_from_nchw(x3, capi.FMT_S32), e._pack_deconv3d_k2s2(dc3.to(DEV), bn3.to(DEV)),
+                                   act_from_nchw(skip, capi.FMT_S32))).cpu()
+    assert rel_err(got3.numpy(), want3.numpy()) < TOL["tc"]
+
+
+@pytest.mark.parametrize("case", [(2, 256, 1024, 1, 0, (24, 24), 32), (2, 256, 256, 3, 1, (24, 24), 32), (3, 32, 32, 3, 1, (64, 64, 64), 1)])
+def test_conv_tc_vs_ffma_at_config2_sizes(case):
+    """Sizes of BASELINE config #2 the CPU oracle cannot reach quickly: tensor-core kernel vs the exact-fp32 FFMA kernel."""
+    dims, cin, cout, k, pad, spatial, N = case
+    torch.manual_seed(9)
+    conv = (torch.nn.Conv2d if dims == 2 else torch.nn.Conv3d)(cin, cout, k, 1, pad, bias=False).eval().to(DEV)
+    bn = _bn_for(conv, 1).to(DEV)
+    x = torch.randn(N, cin, *spatial, device=DEV)
+    e_tc, e_ff = _engine("tc"), _engine("simt")
+    y_tc = act_to_nchw(e_tc._conv(act_from_nchw(x, capi.FMT_S32), e_tc._pack_conv(conv, bn), relu=True))
+    y_ff = act_to_nchw(e_ff._conv(act_from_nchw(x, capi.FMT_F32), e_ff._pack_conv(conv, bn), relu=True))
+    torch.cuda.synchronize()
+    assert rel_err(y_tc.cpu().numpy(), y_ff.cpu().numpy()) < TOL["tc"]
