@@ -208,9 +208,15 @@ def main_native(args, rank, world, local_rank):
         model(images_dev, None, batch)
         torch.cuda.synchronize()
         agg = {}
-        for label, flops, nbytes, a, b in eng.timeline:
+        per_launch = []
+        for label, flops, nbytes, a, b, desc in eng.timeline:
             r = agg.setdefault(label, [0.0, 0.0, 0.0, 0])
-            r[0] += a.elapsed_time(b); r[1] += flops; r[2] += nbytes; r[3] += 1
+            ms = a.elapsed_time(b)
+            r[0] += ms; r[1] += flops; r[2] += nbytes; r[3] += 1
+            per_launch.append({"kernel": label, "desc": desc, "ms": round(ms, 4), "gflop": round(flops / 1e9, 3), "mb": round(nbytes / 1e6, 3)})
+        if os.environ.get("LT_BENCH_TIMELINE"):
+            with open(os.environ["LT_BENCH_TIMELINE"], "w") as f:
+                json.dump(per_launch, f)
         eng.timeline = None
 
     # max over ranks
@@ -254,7 +260,7 @@ def main_native(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"tc": "bf16x3 (split-bf16 3-term products, fp32 accumulate)", "tc1": "bf16", "simt": "f32"}[args.mode],
+            "dtype": {"tc": "fp16x3 (split-fp16 operands, 3 tcgen05 products per term, fp32 accumulate)", "tc1": "fp16", "simt": "f32"}[args.mode],
             "data": "synthetic",
             "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch %d per GPU"
                                    % (args.layers, V, S, S, n, B),

@@ -14,9 +14,10 @@
  *   - return value: 0 on success, negative lt_status on failure; lt_last_error_string()
  *     returns a thread-local description of the last failure;
  *   - activation tensors are channels-last: [N][D][H][W][C] (2-D maps have D = 1);
- *   - LT_FMT_F32 is plain float; LT_FMT_S32 is "split-bf16": channels in blocks of 32, each
- *     block stored as 32 bf16 high parts followed by 32 bf16 low parts (x = hi + lo, 128 bytes
- *     per block, same footprint as fp32) -- the tensor-core operand format.
+ *   - LT_FMT_F32 is plain float; LT_FMT_S32 is "split-fp16": channels in blocks of 32, each
+ *     block stored as 32 fp16 high parts followed by 32 fp16 low parts (x = hi + lo/2048, 128
+ *     bytes per block, same footprint as fp32, ~22 significand bits) -- the tensor-core operand
+ *     format.
  */
 #ifndef LT_B200_H
 #define LT_B200_H
@@ -43,8 +44,8 @@ enum lt_agg { LT_AGG_SUM = 0, LT_AGG_MAX = 1, LT_AGG_SOFTMAX = 2, LT_AGG_CONF = 
 /* conv implementation selector */
 enum lt_conv_impl {
   LT_CONV_SIMT = 0, /* fp32 FFMA implicit GEMM (exact, any shape) */
-  LT_CONV_TC = 1,   /* tcgen05, split-bf16 3-term products (fp32-grade) */
-  LT_CONV_TC1 = 2   /* tcgen05, high parts only (plain bf16 precision, fast mode) */
+  LT_CONV_TC = 1,   /* tcgen05, split-fp16 3-term products (fp32-grade) */
+  LT_CONV_TC1 = 2   /* tcgen05, high parts only (plain fp16 precision, fast mode) */
 };
 
 /* residual placement in the conv epilogue */
@@ -139,7 +140,7 @@ int lt_conv_nd_fwd(const lt_conv_desc* desc, const void* in, const void* weight,
                    const float* shift, const void* residual, void* out, int impl, void* stream);
 
 /* Tensor-core (tcgen05) weight packing: float32 [taps][Cin][Cout] (host or device? -> DEVICE)
- * to split-bf16 [taps][Cin/32][CoutP][64], CoutP = round_up(Cout, 16); Cin % 32 == 0. */
+ * to split-fp16 [taps][Cin/32][CoutP][64], CoutP = round_up(Cout, 16); Cin % 32 == 0. */
 size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout);
 int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
 
@@ -155,16 +156,16 @@ int lt_maxpool_fwd(const void* in, void* out, int format, int N, int ID, int IH,
  * ---------------------------------------------------------------------------------------- */
 /* images [N][C][H][W] float32 -> [N][H][W][Cp] float32, channels >= C zero filled */
 int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, int Cp, void* stream);
-/* channels-last [P][C] float32 <-> split-bf16 (C % 32 == 0) */
+/* channels-last [P][C] float32 <-> split-fp16 (C % 32 == 0) */
 int lt_f32_to_s32(const float* in, void* out, long pixels, int C, void* stream);
 int lt_s32_to_f32(const void* in, float* out, long pixels, int C, void* stream);
 /* channels-last [N][P][Cs] (first C channels) -> channels-first [N][C][P] float32 */
 int lt_cl_to_cf_f32(const float* in, float* out, int N, long P, int Cs, int C, void* stream);
 
-/* Self test of the tcgen05/TMA GEMM core: D[M][N] = A[M][K] * B[N][K]^T with bf16 inputs
+/* Self test of the tcgen05/TMA GEMM core: D[M][N] = A[M][K] * B[N][K]^T with fp16 inputs
  * (row-major, K contiguous), float32 output.  variant selects descriptor conventions
  * (bring-up aid; 0 is the shipped one). */
-int lt_tc_gemm_selftest(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K,
+int lt_tc_gemm_selftest(const void* a_fp16, const void* b_fp16, float* d, int M, int N, int K,
                         int variant, void* stream);
 
 #ifdef __cplusplus

@@ -176,5 +176,5 @@ def cl_to_cf(inp, out, N, P, Cs, C):
     _check(lib().lt_cl_to_cf_f32(_ptr(inp), _ptr(out), N, P, Cs, C, _stream()), "lt_cl_to_cf_f32")
 
 
-def tc_gemm_selftest(a_bf16, b_bf16, d, M, N, K, variant=0):
-    _check(lib().lt_tc_gemm_selftest(_ptr(a_bf16), _ptr(b_bf16), _ptr(d), M, N, K, variant, _stream()), "lt_tc_gemm_selftest")
+def tc_gemm_selftest(a_fp16, b_fp16, d, M, N, K, variant=0):
+    _check(lib().lt_tc_gemm_selftest(_ptr(a_fp16), _ptr(b_fp16), _ptr(d), M, N, K, variant, _stream()), "lt_tc_gemm_selftest")

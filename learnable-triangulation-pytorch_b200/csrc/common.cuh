@@ -1,7 +1,7 @@
 // Shared helpers for the lt_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -28,37 +28,45 @@ int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
-// ---- split-bf16 ("S32") format ----------------------------------------------------------------
-// x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi): 16 significand bits, fp32 range.
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// ---- split-fp16 ("S32") format ----------------------------------------------------------------
+// x ~= hi + lo / 2048 with hi = fp16_rn(x), lo = fp16_rn((x - hi) * 2048): 22 significand bits in two
+// fp16 tensor-core operands.  The low part is pre-scaled by 2^11 so that it stays in the fp16 normal
+// range (|x - hi| <= 2^-11 |x|); the tensor-core kernel accumulates the cross terms separately and
+// applies 2^-11 in the epilogue.  |x| is saturated at the fp16 maximum (65504).
+typedef __half sh_t;
+constexpr float kLoScale = 2048.0f;
+constexpr float kLoInv = 1.0f / 2048.0f;
+
+__device__ __forceinline__ void split_s32(float x, sh_t& hi, sh_t& lo) {
+  x = fminf(fmaxf(x, -65504.0f), 65504.0f);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
 }
-__device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
-  return __bfloat162float(hi) + __bfloat162float(lo);
+__device__ __forceinline__ float join_s32(sh_t hi, sh_t lo) {
+  return fmaf(__half2float(lo), kLoInv, __half2float(hi));
 }
-// element offset (in bf16 units) of the high part of channel c of a pixel whose row starts at 0;
+// element offset (in 2-byte units) of the high part of channel c of a pixel whose row starts at 0;
 // low part is +32.
 __device__ __host__ __forceinline__ int s32_off(int c) { return ((c >> 5) << 6) + (c & 31); }
 
 // 4 consecutive channels (c % 4 == 0) <-> split storage
-__device__ __forceinline__ void store_s32x4(__nv_bfloat16* row, int c, float4 v) {
-  __nv_bfloat16 h[4], l[4];
-  split_bf16(v.x, h[0], l[0]);
-  split_bf16(v.y, h[1], l[1]);
-  split_bf16(v.z, h[2], l[2]);
-  split_bf16(v.w, h[3], l[3]);
-  __nv_bfloat16* p = row + s32_off(c);
+__device__ __forceinline__ void store_s32x4(sh_t* row, int c, float4 v) {
+  sh_t h[4], l[4];
+  split_s32(v.x, h[0], l[0]);
+  split_s32(v.y, h[1], l[1]);
+  split_s32(v.z, h[2], l[2]);
+  split_s32(v.w, h[3], l[3]);
+  sh_t* p = row + s32_off(c);
   *reinterpret_cast<uint2*>(p) = *reinterpret_cast<uint2*>(h);
   *reinterpret_cast<uint2*>(p + 32) = *reinterpret_cast<uint2*>(l);
 }
-__device__ __forceinline__ float4 load_s32x4(const __nv_bfloat16* row, int c) {
-  const __nv_bfloat16* p = row + s32_off(c);
+__device__ __forceinline__ float4 load_s32x4(const sh_t* row, int c) {
+  const sh_t* p = row + s32_off(c);
   uint2 hu = *reinterpret_cast<const uint2*>(p);
   uint2 lu = *reinterpret_cast<const uint2*>(p + 32);
-  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&hu);
-  const __nv_bfloat16* l = reinterpret_cast<const __nv_bfloat16*>(&lu);
-  return make_float4(join_bf16(h[0], l[0]), join_bf16(h[1], l[1]), join_bf16(h[2], l[2]), join_bf16(h[3], l[3]));
+  const sh_t* h = reinterpret_cast<const sh_t*>(&hu);
+  const sh_t* l = reinterpret_cast<const sh_t*>(&lu);
+  return make_float4(join_s32(h[0], l[0]), join_s32(h[1], l[1]), join_s32(h[2], l[2]), join_s32(h[3], l[3]));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

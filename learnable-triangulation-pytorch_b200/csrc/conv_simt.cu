@@ -158,13 +158,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvSimtParams p) 
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
       if (d.residual != LT_RES_NONE) {
         if (d.out_format == LT_FMT_F32) r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + opix * d.FC + co);
-        else r = load_s32x4(reinterpret_cast<const __nv_bfloat16*>(p.res) + opix * 2 * d.FC, co);
+        else r = load_s32x4(reinterpret_cast<const sh_t*>(p.res) + opix * 2 * d.FC, co);
       }
       if (d.residual == LT_RES_BEFORE_RELU) { v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
       if (d.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (d.residual == LT_RES_AFTER_RELU) { v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
       if (d.out_format == LT_FMT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * d.FC + co) = v;
-      else store_s32x4(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * 2 * d.FC, co, v);
+      else store_s32x4(reinterpret_cast<sh_t*>(p.out) + opix * 2 * d.FC, co, v);
     }
   }
 }
@@ -186,7 +186,7 @@ int conv_simt_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
                   const void* residual, void* out, void* stream) {
   LT_REQUIRE(d->in_format == LT_FMT_F32, "conv_simt: input must be float32 channels-last");
   LT_REQUIRE(d->FC % 4 == 0, "conv_simt: output channel stride FC=%d must be a multiple of 4", d->FC);
-  LT_REQUIRE(d->out_format == LT_FMT_F32 || d->FC % 32 == 0, "conv_simt: split-bf16 output needs FC %% 32 == 0");
+  LT_REQUIRE(d->out_format == LT_FMT_F32 || d->FC % 32 == 0, "conv_simt: split-fp16 output needs FC %% 32 == 0");
   ConvSimtParams p;
   p.d = *d;
   p.in = reinterpret_cast<const float*>(in);

@@ -1,5 +1,5 @@
 // Tensor-core implicit-GEMM convolution for sm_100a: TMA-staged channels-last tiles ->
-// shared memory (128B swizzle) -> tcgen05.mma (UMMA 128 x Nt x 16, bf16 in, fp32 accumulate in
+// shared memory (128B swizzle) -> tcgen05.mma (UMMA 128 x Nt x 16, fp16 in, fp32 accumulate in
 // TMEM) -> tcgen05.ld epilogue with folded-BN scale/shift, residual, ReLU and strided
 // channels-last store (plain conv, stride-phase transposed conv).
 //
@@ -8,9 +8,10 @@
 // For every filter tap the A tile is ONE TMA box load of the input tensor shifted by the tap
 // offset; out-of-range coordinates are zero-filled by TMA, which implements the padding.
 //
-// Precision: activations and weights travel as split-bf16 (x = hi + lo, see common.cuh).  Per
-// 16-wide K slice the kernel issues hi*hi + hi*lo + lo*hi (3 MMAs, relative error ~2^-17 per
-// product, i.e. fp32-grade results from the bf16 pipe) or hi*hi only (LT_CONV_TC1, fast mode).
+// Precision: activations and weights travel as split-fp16 (x = hi + lo/2048, see common.cuh).  Per
+// 16-wide K slice the kernel issues hi*hi into accumulator D1 and hi*lo + lo*hi into accumulator D2
+// (3 MMAs; the epilogue forms D1 + D2/2048: ~22 significand bits per operand, dropped lo*lo term
+// 2^-22 relative -- fp32-grade results from the fp16 pipe), or hi*hi only (LT_CONV_TC1, fast mode).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = epilogue (one TMEM lane quadrant each).
@@ -78,7 +79,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -103,9 +104,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ inline uint32_t make_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=fp16 (format 0), both K-major, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -128,7 +129,7 @@ struct TcParams {
   void* out;
 };
 
-constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
 
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -184,8 +185,9 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(p.Nt);
-      uint32_t accumulate = 0;
+      const uint32_t idesc = make_idesc_f16(p.Nt);
+      uint32_t accumulate = 0, accumulate2 = 0;
+      const uint32_t tmem_d2 = tmem_base + (uint32_t)p.Nt;   // second accumulator: cross terms (scaled by 2^11)
       for (int q = 0; q < nchunks; ++q) {
         const int s = q % p.stages;
         const uint32_t ph = (uint32_t)((q / p.stages) & 1);
@@ -195,28 +197,29 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const uint32_t b_addr = a_addr + kATileBytes;
         const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw128_desc(b_addr);
         if (p.terms == 3) {
-          // row = [32 hi | 32 lo] bf16: hi slices at +0,+32 B, lo slices at +64,+96 B (>>4 units: 2 per 32 B)
+          // row = [32 hi | 32 lo] fp16: hi slices at +0,+32 B, lo slices at +64,+96 B (>>4 units: 2 per 32 B)
 #pragma unroll
           for (int sl = 0; sl < 2; ++sl) {
             const uint64_t ah = ad + (uint64_t)(sl * 2), al = ad + (uint64_t)(4 + sl * 2);
             const uint64_t bh = bd + (uint64_t)(sl * 2), bl = bd + (uint64_t)(4 + sl * 2);
-            umma_bf16(tmem_base, ah, bh, idesc, accumulate);
+            umma_f16(tmem_base, ah, bh, idesc, accumulate);
             accumulate = 1;
-            umma_bf16(tmem_base, ah, bl, idesc, 1);
-            umma_bf16(tmem_base, al, bh, idesc, 1);
+            umma_f16(tmem_d2, ah, bl, idesc, accumulate2);
+            accumulate2 = 1;
+            umma_f16(tmem_d2, al, bh, idesc, 1);
           }
         } else if (p.terms == 1) {
           // split storage, high parts only
 #pragma unroll
           for (int sl = 0; sl < 2; ++sl) {
-            umma_bf16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
+            umma_f16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
             accumulate = 1;
           }
         } else {
-          // plain bf16 rows (self test): 4 slices of 16
+          // plain fp16 rows (self test): 4 slices of 16
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl) {
-            umma_bf16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
+            umma_f16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
             accumulate = 1;
           }
         }
@@ -242,6 +245,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     for (int c0 = 0; c0 < p.Nt; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);   // whole warp (sync.aligned)
+      if (p.terms == 3) {
+        uint32_t v2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.Nt + c0), v2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v2[j]), kLoInv, __uint_as_float(v[j])));
+      }
       if (!valid) continue;
       const int co0 = n0 + c0;
 #pragma unroll
@@ -255,13 +264,13 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.residual != LT_RES_NONE) {
           if (p.out_format == LT_FMT_F32) rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + opix * p.FC + co);
-          else rr = load_s32x4(reinterpret_cast<const __nv_bfloat16*>(p.res) + opix * 2 * p.FC, co);
+          else rr = load_s32x4(reinterpret_cast<const sh_t*>(p.res) + opix * 2 * p.FC, co);
         }
         if (p.residual == LT_RES_BEFORE_RELU) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
         if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (p.residual == LT_RES_AFTER_RELU) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
         if (p.out_format == LT_FMT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.FC + co) = o;
-        else store_s32x4(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * 2 * p.FC, co, o);
+        else store_s32x4(reinterpret_cast<sh_t*>(p.out) + opix * 2 * p.FC, co, o);
       }
     }
   }
@@ -301,7 +310,7 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estrides ? estrides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -331,7 +340,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
   p.stages = stages;
-  p.tmem_cols = pow2_ceil(p.Nt) < 32 ? 32 : pow2_ceil(p.Nt);
+  const int acc_cols = (p.terms == 3 ? 2 : 1) * p.Nt;
+  p.tmem_cols = pow2_ceil(acc_cols) < 32 ? 32 : pow2_ceil(acc_cols);
   const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
@@ -349,7 +359,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p
 
 int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
                       const void* residual, void* out, int terms, void* stream) {
-  LT_REQUIRE(d->in_format == LT_FMT_S32, "conv_tc: input must be split-bf16");
+  LT_REQUIRE(d->in_format == LT_FMT_S32, "conv_tc: input must be split-fp16");
   LT_REQUIRE(d->Cin % 32 == 0, "conv_tc: Cin=%d must be a multiple of 32", d->Cin);
   LT_REQUIRE(d->sd == 1 && d->sh == 1 && d->sw == 1, "conv_tc: strided input not supported (use LT_CONV_SIMT)");
   LT_REQUIRE(d->FC % 4 == 0 && (d->out_format == LT_FMT_F32 || d->FC % 32 == 0), "conv_tc: bad output channel stride %d", d->FC);
@@ -374,7 +384,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
 
   CUtensorMap tmA, tmB;
   {
-    const uint64_t rowb = (uint64_t)d->Cin * 2 * 2;  // 2*Cin bf16 per position
+    const uint64_t rowb = (uint64_t)d->Cin * 2 * 2;  // 2*Cin fp16 per position
     const uint64_t dims[5] = {(uint64_t)d->Cin * 2, (uint64_t)d->IW, (uint64_t)d->IH, (uint64_t)d->ID, (uint64_t)d->N};
     const uint64_t str[4] = {rowb, rowb * d->IW, rowb * d->IW * d->IH, rowb * d->IW * d->IH * d->ID};
     const uint32_t bx[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
@@ -396,8 +406,8 @@ int conv_tc_fwd(const lt_conv_desc* d, const void* in, const void* weight, const
   return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 3, stream);
 }
 
-// ---- weight packing: fp32 [taps][Cin][Cout] -> split-bf16 [taps][Cin/32][CoutP][64] ----------------
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+// ---- weight packing: fp32 [taps][Cin][Cout] -> split-fp16 [taps][Cin/32][CoutP][64] ----------------
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, sh_t* __restrict__ out,
                                                            int taps, int Cin, int Cout, int CoutP) {
   const int CB = Cin / 32;
   const long total = (long)taps * CB * CoutP * 32;
@@ -408,9 +418,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     const int cb = (int)(r % CB);
     const int tap = (int)(r / CB);
     const float v = (n < Cout) ? w[((long)tap * Cin + cb * 32 + j) * Cout + n] : 0.0f;
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    __nv_bfloat16* row = out + (((long)tap * CB + cb) * CoutP + n) * 64;
+    sh_t hi, lo;
+    split_s32(v, hi, lo);
+    sh_t* row = out + (((long)tap * CB + cb) * CoutP + n) * 64;
     row[j] = hi;
     row[32 + j] = lo;
   }
@@ -437,12 +447,12 @@ extern "C" int lt_conv_tc_pack_weights(const float* w, void* packed, int taps, i
   const long total = (long)taps * (Cin / 32) * CoutP * 32;
   long blocks = (total + 255) / 256;
   if (blocks > 65535) blocks = 65535;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), taps, Cin, Cout, CoutP);
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<sh_t*>(packed), taps, Cin, Cout, CoutP);
   LT_CHECK_LAUNCH("pack_weights_kernel");
   return LT_OK;
 }
 
-// D[M][N] (fp32) = A[M][K] * B[N][K]^T, plain bf16 row-major operands; exercises the exact TMA /
+// D[M][N] (fp32) = A[M][K] * B[N][K]^T, plain fp16 row-major operands; exercises the exact TMA /
 // descriptor / tcgen05 / epilogue code of the conv kernel (terms = 0 selects plain rows).
 // `d` must hold M*N floats followed by 2*N floats of scratch (scale/shift).
 extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M, int N, int K, int variant, void* stream) {

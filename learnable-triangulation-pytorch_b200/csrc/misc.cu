@@ -64,14 +64,14 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolParams p) {
           const long pix = (((long)n * p.ID + id) * p.IH + ih) * p.IW + iw;
           float4 v;
           if (p.format == LT_FMT_F32) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + pix * p.C + c));
-          else v = load_s32x4(reinterpret_cast<const __nv_bfloat16*>(p.in) + pix * 2 * p.C, c);
+          else v = load_s32x4(reinterpret_cast<const sh_t*>(p.in) + pix * 2 * p.C, c);
           m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
         }
       }
     }
     const long opix = (((long)n * p.OD + od) * p.OH + oh) * p.OW + ow;
     if (p.format == LT_FMT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.C + c) = m;
-    else store_s32x4(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * 2 * p.C, c, m);
+    else store_s32x4(reinterpret_cast<sh_t*>(p.out) + opix * 2 * p.C, c, m);
   }
 }
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) f32_to_s32_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long pixels, int C) {
+__global__ void __launch_bounds__(256) f32_to_s32_kernel(const float* __restrict__ in, sh_t* __restrict__ out, long pixels, int C) {
   const int c4n = C / 4;
   const long total = pixels * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) f32_to_s32_kernel(const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(256) s32_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long pixels, int C) {
+__global__ void __launch_bounds__(256) s32_to_f32_kernel(const sh_t* __restrict__ in, float* __restrict__ out, long pixels, int C) {
   const int c4n = C / 4;
   const long total = pixels * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -152,7 +152,7 @@ extern "C" int lt_maxpool_fwd(const void* in, void* out, int format, int N, int 
                               int kw, int sd, int sh, int sw, int pd, int ph, int pw, int OD, int OH, int OW, void* stream) {
   LT_REQUIRE(in && out, "maxpool: null pointer");
   LT_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
-  LT_REQUIRE(format == LT_FMT_F32 || C % 32 == 0, "maxpool: split-bf16 needs C %% 32 == 0");
+  LT_REQUIRE(format == LT_FMT_F32 || C % 32 == 0, "maxpool: split-fp16 needs C %% 32 == 0");
   PoolParams p{in, out, format, N, ID, IH, IW, C, kd, kh, kw, sd, sh, sw, pd, ph, pw, OD, OH, OW};
   maxpool_kernel<<<grid_for((long)N * OD * OH * OW * (C / 4)), 256, 0, (cudaStream_t)stream>>>(p);
   LT_CHECK_LAUNCH("maxpool_kernel");
@@ -168,14 +168,14 @@ extern "C" int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, in
 
 extern "C" int lt_f32_to_s32(const float* in, void* out, long pixels, int C, void* stream) {
   LT_REQUIRE(in && out && C % 32 == 0, "f32_to_s32: C %% 32 != 0");
-  f32_to_s32_kernel<<<grid_for(pixels * (C / 4)), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<__nv_bfloat16*>(out), pixels, C);
+  f32_to_s32_kernel<<<grid_for(pixels * (C / 4)), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<sh_t*>(out), pixels, C);
   LT_CHECK_LAUNCH("f32_to_s32_kernel");
   return LT_OK;
 }
 
 extern "C" int lt_s32_to_f32(const void* in, float* out, long pixels, int C, void* stream) {
   LT_REQUIRE(in && out && C % 32 == 0, "s32_to_f32: C %% 32 != 0");
-  s32_to_f32_kernel<<<grid_for(pixels * (C / 4)), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, pixels, C);
+  s32_to_f32_kernel<<<grid_for(pixels * (C / 4)), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const sh_t*>(in), out, pixels, C);
   LT_CHECK_LAUNCH("s32_to_f32_kernel");
   return LT_OK;
 }

@@ -10,7 +10,7 @@
 // each tap as one coalesced 16-byte load per lane (C=32 -> one 128-byte line per tap per voxel
 // from the channels-last feature map), keeps the V per-view samples in registers, aggregates
 // (softmax / sum / max / conf) and writes the voxel's C channels once, channels-last, either as
-// float32 or directly in the split-bf16 operand format of the V2V tensor-core convs.
+// float32 or directly in the split-fp16 operand format of the V2V tensor-core convs.
 //
 // Algorithmic bytes per sample (V=4, C=32, 96x96 maps, 64^3 voxels, fp32 out):
 //   33.55 MB volume write + 4.72 MB feature read (compulsory) + 3.15 MB coordinate read = 41.42 MB.
@@ -109,11 +109,11 @@ __device__ __forceinline__ void store_out(const UnprojParams& p, long b, long vo
     if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
     else dst[0] = o[0];
   } else {
-    __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long)b * p.nvox + vox) * 2 * p.C;
+    sh_t* row = reinterpret_cast<sh_t*>(p.out) + ((long)b * p.nvox + vox) * 2 * p.C;
     if constexpr (VEC == 4) store_s32x4(row, c0, make_float4(o[0], o[1], o[2], o[3]));
     else {
-      __nv_bfloat16 hi, lo;
-      split_bf16(o[0], hi, lo);
+      sh_t hi, lo;
+      split_s32(o[0], hi, lo);
       row[s32_off(c0)] = hi;
       row[s32_off(c0) + 32] = lo;
     }
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) unproject_finalize_kernel(const float* __
     } else {
       const long pix = e / C;
       const int c = (int)(e % C);
-      store_s32x4(reinterpret_cast<__nv_bfloat16*>(out) + pix * 2 * C, c, o);
+      store_s32x4(reinterpret_cast<sh_t*>(out) + pix * 2 * C, c, o);
     }
   }
 }
@@ -285,7 +285,7 @@ static int launch_unproject(const float* features, const float* proj, const floa
   LT_REQUIRE(agg >= LT_AGG_SUM && agg <= LT_AGG_CONF, "unproject: unknown aggregation %d", agg);
   LT_REQUIRE(agg != LT_AGG_CONF || conf, "unproject: LT_AGG_CONF needs confidences");
   LT_REQUIRE(out_format == LT_FMT_F32 || (out_format == LT_FMT_S32 && C % 32 == 0),
-             "unproject: split-bf16 output needs C %% 32 == 0 (C=%d)", C);
+             "unproject: split-fp16 output needs C %% 32 == 0 (C=%d)", C);
   LT_REQUIRE(B <= 65535, "unproject: batch too large");
   UnprojParams p{features, proj, coord, conf, out, B, V, C, h, w, nvox, agg, out_format, 1, partial};
   const bool vec4 = (C % 4 == 0);
@@ -330,7 +330,7 @@ extern "C" int lt_unproject_finalize_fwd(const float* partial, void* out, int ou
   using namespace lt;
   LT_REQUIRE(partial && out, "unproject_finalize: null pointer");
   LT_REQUIRE(C % 4 == 0, "unproject_finalize: C %% 4 != 0");
-  LT_REQUIRE(out_format == LT_FMT_F32 || C % 32 == 0, "unproject_finalize: split-bf16 output needs C %% 32 == 0");
+  LT_REQUIRE(out_format == LT_FMT_F32 || C % 32 == 0, "unproject_finalize: split-fp16 output needs C %% 32 == 0");
   const long total4 = (long)B * nvox * C / 4;
   long blocks = (total4 + 255) / 256;
   const long cap = (long)sm_count() * 8;

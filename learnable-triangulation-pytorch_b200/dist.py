@@ -1,0 +1,92 @@
+"""View-sharded multi-GPU execution of the volumetric path (one process per GPU, torch.distributed plumbing).
+
+The reference has no view sharding (its only parallelism is batch DDP, train.py:452-453).  Views are independent
+until the aggregation inside the unprojection (op.py:150-162), so rank r of a G-rank *view group* owns views
+{v : v mod G == r} of every sample of the group's batch, runs the backbone + unprojection on them and produces a
+partial voxel aggregate; ONE collective over NVLink completes it; the V2V + soft-argmax then run batch-sharded.
+
+softmax aggregation is not a plain sum:  out = sum_v s_v e^{s_v} / sum_v e^{s_v}.  Each rank therefore emits the
+packed pair (numerator, denominator) [B][2][nvox][C] (lt_unproject_partial_fwd) and the collective is a SUM:
+  collective="all_reduce"      one NCCL all-reduce of the packed buffer (the contract of BASELINE.json north_star)
+  collective="reduce_scatter"  same bytes in, but each rank receives only the samples it will run V2V on
+then lt_unproject_finalize_fwd divides and converts to the conv operand format.
+
+With W ranks and V views: view-group size G = gcd-compatible min(W, V); the W/G groups are plain data-parallel
+replicas over different samples (no communication between groups).
+"""
+import math
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    rank: int
+    n_views: int
+    group_size: int      # G: ranks that share one batch and split its views
+    n_groups: int        # data-parallel replicas
+    group_index: int
+    view_rank: int       # rank inside the view group
+
+    @property
+    def views(self):
+        """View indices this rank owns."""
+        return list(range(self.view_rank, self.n_views, self.group_size))
+
+    def owned_samples(self, batch):
+        """Samples (indices into the group's batch) this rank runs V2V / soft-argmax on: a contiguous block."""
+        assert batch % self.group_size == 0, "group batch must be divisible by the view-group size"
+        per = batch // self.group_size
+        return list(range(self.view_rank * per, (self.view_rank + 1) * per))
+
+    @property
+    def group_ranks(self):
+        return list(range(self.group_index * self.group_size, (self.group_index + 1) * self.group_size))
+
+
+def make_plan(world, rank, n_views):
+    g = math.gcd(world, n_views)     # largest group size that divides both the world and the view count
+    return ShardPlan(world, rank, n_views, g, world // g, rank // g, rank % g)
+
+
+def new_view_groups(plan):
+    """Create every view group (collective call: all ranks must call it) and return this rank's group."""
+    import torch.distributed as dist
+    mine = None
+    for gi in range(plan.n_groups):
+        ranks = list(range(gi * plan.group_size, (gi + 1) * plan.group_size))
+        pg = dist.new_group(ranks)
+        if gi == plan.group_index:
+            mine = pg
+    return mine
+
+
+def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum"):
+    """partial: [B][P][nvox][C] float32 on every rank of the group -> the block of fully reduced samples this rank owns.
+
+    Returns a tensor [B/G][P][nvox][C].  `reduce_op` is "sum" (softmax num/den, sum, conf) or "max".
+    """
+    import torch.distributed as dist
+    if plan.group_size == 1:
+        return partial
+    op = dist.ReduceOp.SUM if reduce_op == "sum" else dist.ReduceOp.MAX
+    B = partial.shape[0]
+    per = B // plan.group_size
+    if collective == "reduce_scatter":
+        out = torch.empty((per,) + tuple(partial.shape[1:]), dtype=partial.dtype, device=partial.device)
+        dist.reduce_scatter_tensor(out, partial.contiguous(), op=op, group=pg)
+        return out
+    dist.all_reduce(partial, op=op, group=pg)
+    return partial[plan.view_rank * per:(plan.view_rank + 1) * per]
+
+
+def gather_keypoints(kp_local, plan, pg):
+    """[B/G][J][3] on each rank -> [B][J][3] on every rank of the group."""
+    import torch.distributed as dist
+    if plan.group_size == 1:
+        return kp_local
+    outs = [torch.empty_like(kp_local) for _ in range(plan.group_size)]
+    dist.all_gather(outs, kp_local.contiguous(), group=pg)
+    return torch.cat(outs, dim=0)

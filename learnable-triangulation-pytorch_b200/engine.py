@@ -8,8 +8,8 @@ C-ABI launches on the current CUDA stream -- optionally captured into one CUDA g
 
 Data layout in HBM: every activation is channels-last ([N][D][H][W][C]); 2-D maps use D = 1.
   mode "simt": float32 activations, exact-fp32 FFMA convs (parity mode / checker)
-  mode "tc"  : split-bf16 activations, tcgen05 convs with 3-term products (fp32-grade)
-  mode "tc1" : split-bf16 activations, tcgen05 convs with high parts only (bf16-grade, fast)
+  mode "tc"  : split-fp16 activations, tcgen05 convs with 3-term products (fp32-grade)
+  mode "tc1" : split-fp16 activations, tcgen05 convs with high parts only (bf16-grade, fast)
 Layers the tensor-core kernel does not cover (the 3-channel stem and the six stride-2 convs of
 the trunk) run on the FFMA kernel in every mode.
 """
@@ -27,7 +27,7 @@ def _round_up(v, m):
 
 
 class Act:
-    """Channels-last activation: `data` is float32 [N,D,H,W,C] or bfloat16 [N,D,H,W,2C] (split-bf16)."""
+    """Channels-last activation: `data` is float32 [N,D,H,W,C] or bfloat16 [N,D,H,W,2C] (split-fp16)."""
     __slots__ = ("data", "N", "D", "H", "W", "C", "fmt")
 
     def __init__(self, N, D, H, W, C, fmt, device, zero=False):
@@ -37,7 +37,7 @@ class Act:
             self.data = alloc((N, D, H, W, C), dtype=torch.float32, device=device)
         else:
             assert C % 32 == 0
-            self.data = alloc((N, D, H, W, 2 * C), dtype=torch.bfloat16, device=device)
+            self.data = alloc((N, D, H, W, 2 * C), dtype=torch.float16, device=device)
 
     @property
     def pixels(self):
@@ -68,8 +68,8 @@ def _fold_bn(conv_bias, bn, cout, device):
 class _Timed:
     """CUDA-event bracket around one launch (only when a timeline list is installed; never during graph capture)."""
 
-    def __init__(self, timeline, label, flops, nbytes):
-        self.tl, self.label, self.flops, self.nbytes = timeline, label, flops, nbytes
+    def __init__(self, timeline, label, flops, nbytes, desc=""):
+        self.tl, self.label, self.flops, self.nbytes, self.desc = timeline, label, flops, nbytes, desc
 
     def __enter__(self):
         if self.tl is not None:
@@ -79,7 +79,7 @@ class _Timed:
     def __exit__(self, *exc):
         if self.tl is not None:
             self.e1.record()
-            self.tl.append((self.label, self.flops, self.nbytes, self.e0, self.e1))
+            self.tl.append((self.label, self.flops, self.nbytes, self.e0, self.e1, self.desc))
         return False
 
 
@@ -117,7 +117,7 @@ class NativeEngine:
             cout_p = _round_up(cout, 32 if out_fmt == FMT_S32 else 16)
             wp = torch.zeros((taps, cin_p, cout_p), dtype=torch.float32, device=dev)
             wp[:, :cin, :cout] = w_taps
-            packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.bfloat16, device=dev)
+            packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
             capi.conv_tc_pack_weights(wp.contiguous(), packed, taps, cin_p, cout_p)
             pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = packed, cin_p, cout_p, self.tc_impl, FMT_S32
         else:
@@ -196,7 +196,7 @@ class NativeEngine:
                 P["deconv%d" % i] = self._pack_deconv2d_k4s2(bb.deconv_layers[i], bb.deconv_layers[i + 1])
             P["process_features"] = self._pack_conv(m.process_features[0], None, out_fmt=FMT_F32)
             v = m.volume_net
-            pad16 = 32 if self.mode != "simt" else None   # the 16-channel tensor is stored 32 wide in split-bf16
+            pad16 = 32 if self.mode != "simt" else None   # the 16-channel tensor is stored 32 wide in split-fp16
 
             def pack_res(name, blk):
                 cin_pad = pad16 if blk.res_branch[0].in_channels == 16 else None
@@ -258,14 +258,14 @@ class NativeEngine:
                           relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt)
         if residual is not None:
             assert residual.fmt == out.fmt and residual.C == out.C
-        with self._timed("conv_tc" if pk.impl != CONV_SIMT else "conv_ffma",
-                         flops=2.0 * x.N * od * oh * ow * pk.kmacs):
+        with self._timed("conv_tc" if pk.impl != CONV_SIMT else "conv_ffma", flops=2.0 * x.N * od * oh * ow * pk.kmacs,
+                         desc="N%d %dx%dx%d Cin%d Cout%d k%d%d%d s%d" % (x.N, od, oh, ow, pk.cin, pk.cout, kd, kh, kw, sw)):
             capi.conv_nd(d, x.data, pk.w, pk.scale, pk.shift, None if residual is None else residual.data, out.data, pk.impl)
         self.launches += 1
         return out
 
-    def _timed(self, label, flops=0.0, nbytes=0.0):
-        return _Timed(self.timeline, label, flops, nbytes)
+    def _timed(self, label, flops=0.0, nbytes=0.0, desc=""):
+        return _Timed(self.timeline, label, flops, nbytes, desc)
 
     def _maxpool(self, x, k, s, p):
         od = (x.D + 2 * p[0] - k[0]) // s[0] + 1
@@ -389,6 +389,40 @@ class NativeEngine:
         # (B, V, 32, h, w) view of the channels-last features (values identical, strides permuted)
         features = feats.data.view(B, V, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
         return keypoints, features, volumes, coord
+
+    def forward_view_sharded(self, images_local, proj_local, position, center, step, rot, plan, pg, collective="all_reduce"):
+        """Multi-GPU step of one rank (see dist.py): this rank's views of the group's batch in, all keypoints out.
+
+        images_local (B, V_local, 3, H, W), proj_local (B, V_local, 3, 4); the other inputs cover all B samples.
+        backbone + unprojection partials -> ONE collective over the view group -> V2V + soft-argmax on the
+        B / group_size samples this rank owns -> all-gather of the (B, 17, 3) keypoints.
+        """
+        from . import dist as lt_dist
+        self.prepare()
+        m = self.model
+        B, Vl = images_local.shape[:2]
+        n = m.volume_size
+        nvox = n * n * n
+        dev = images_local.device
+        self.launches = 0
+        coord = torch.empty((B, n, n, n, 3), dtype=torch.float32, device=dev)
+        capi.coord_volume(position, center, step, rot, coord, m.transfer_cmu_to_human36m)
+        feats = self.backbone_features(images_local.reshape(B * Vl, *images_local.shape[2:]))
+        agg = capi.AGG[m.volume_aggregation_method]
+        planes = 2 if m.volume_aggregation_method == "softmax" else 1
+        partial = torch.empty((B, planes, nvox, feats.C), dtype=torch.float32, device=dev)
+        capi.unproject_partial(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None, partial, agg)
+        mine = lt_dist.complete_partials(partial, plan, pg, collective, "max" if m.volume_aggregation_method == "max" else "sum")
+        Bl = mine.shape[0]
+        vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
+        capi.unproject_finalize(mine.contiguous(), vol.data, vol.fmt, Bl, feats.C, nvox, agg)
+        self.launches += 3
+        logits = self.v2v(vol)
+        own = plan.owned_samples(B)
+        kp, volumes = self.softargmax(logits, coord[own[0]:own[-1] + 1].contiguous(), m.num_joints, m.volume_multiplier, m.volume_softmax)
+        kp_all = lt_dist.gather_keypoints(kp, plan, pg)
+        features = feats.data.view(B, Vl, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
+        return kp_all, features, volumes, coord
 
     def forward(self, images, proj, position, center, step, rot):
         """All inputs are CUDA float32 tensors. Returns (keypoints, features, volumes, coord_volumes)."""

@@ -88,7 +88,7 @@ def make_batch(batch_size, n_views, image_size=384, seed=0, camera_cls=Camera, d
 
 
 @torch.no_grad()
-def randomize_weights(model, seed=0, calib_size=64, calib_views=2, feat_gain=4.0):
+def randomize_weights(model, seed=0, calib_size=64, calib_views=2, feat_gain=4.0, branch_gain=0.2):
     """Seeded, non-degenerate weights (SURVEY.md hard part H1).
 
     Default inits in eval mode collapse the signal (BN running stats are 0/1, deconv outputs ~5e-3),
@@ -108,16 +108,28 @@ def randomize_weights(model, seed=0, calib_size=64, calib_views=2, feat_gain=4.0
                 mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.05)
     bns = [m for m in model_cpu.modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d))]
     saved = [(m.momentum, m.training) for m in bns]
+    # last BatchNorm of every residual branch: small gain, so that the identity path dominates (as in trained
+    # residual nets; a random ResNet with unit-gain branches amplifies a 1e-5 perturbation ~250x, which would turn
+    # the parity check into a test of fp32 summation order)
+    last_of_branch = set()
+    for mod in model_cpu.modules():
+        if hasattr(mod, "stages") and hasattr(mod, "downsample"):
+            last_of_branch.add(mod.stages()[-1][1])
+        if hasattr(mod, "res_branch"):
+            last_of_branch.add(mod.res_branch[4])
     for m in bns:
         # affine parameters first, so that the calibration below sees the final network
-        m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+        lo, hi = (branch_gain * 0.5, branch_gain * 1.5) if m in last_of_branch else (0.75, 1.25)
+        m.weight.copy_(torch.rand(m.weight.shape, generator=g) * (hi - lo) + lo)
         m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
         m.momentum = 1.0
         m.train()
     # calibration pass: the whole torch formulation (backbone -> process_features -> unprojection -> V2V) on a
     # synthetic scene, so every BatchNorm sees the activation statistics it will see at test time
     model_cpu.process_features[0].weight.mul_(feat_gain)   # wider feature range: view-softmax becomes selective
-    images, batch = make_batch(2, calib_views, image_size=calib_size, seed=seed + 1000)
+    # enough samples that the deepest V2V level (1^3 voxels per sample at volume_size 32) has stable statistics
+    calib_batch = 2 if model_cpu.volume_size >= 64 else 6
+    images, batch = make_batch(calib_batch, calib_views, image_size=calib_size, seed=seed + 1000)
     grabbed = {}
     hook = model_cpu.volume_net.output_layer.register_forward_hook(lambda m, i, o: grabbed.update(logits=o))
     top_training = model_cpu.training

@@ -9,10 +9,9 @@ import torch
 import torch.nn.functional as F
 
 
-def unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregation_method="sum", vol_confidences=None):
-    """Same contract as reference op.py:99-166, batched."""
+def sample_views(heatmaps, proj_matricies, coord_volumes):
+    """Per-view bilinear samples of every voxel, (B, V, C, nvox), invalid-depth voxels zeroed (op.py:113-147)."""
     B, V, C, h, w = heatmaps.shape
-    vol_shape = coord_volumes.shape[1:4]
     pts = coord_volumes.reshape(B, 1, -1, 3)
     ones = torch.ones_like(pts[..., :1])
     proj = torch.cat([pts, ones], dim=-1) @ proj_matricies.transpose(-1, -2)       # (B, V, N, 3)
@@ -26,7 +25,31 @@ def unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregati
     grid = torch.stack([gx, gy], dim=-1).reshape(B * V, -1, 1, 2)
     sampled = F.grid_sample(heatmaps.reshape(B * V, C, h, w), grid, align_corners=True)   # (BV, C, N, 1)
     sampled = sampled.reshape(B, V, C, -1)
-    sampled = sampled.masked_fill(invalid.unsqueeze(2), 0.0)
+    return sampled.masked_fill(invalid.unsqueeze(2), 0.0)
+
+
+def partial_aggregate(sampled, volume_aggregation_method, vol_confidences=None):
+    """This rank's share of the view aggregation, (B, P, C, nvox): softmax -> (sum s e^s, sum e^s) [unshifted]."""
+    if volume_aggregation_method == "softmax":
+        e = torch.exp(sampled)
+        return torch.stack([(sampled * e).sum(1), e.sum(1)], dim=1)
+    if volume_aggregation_method == "max":
+        return sampled.max(1)[0].unsqueeze(1)
+    if volume_aggregation_method.startswith("conf"):
+        B, V, C = sampled.shape[:3]
+        return (sampled * vol_confidences.reshape(B, V, C, 1)).sum(1).unsqueeze(1)
+    return sampled.sum(1).unsqueeze(1)
+
+
+def finalize_aggregate(partial, volume_aggregation_method):
+    return partial[:, 0] / partial[:, 1] if volume_aggregation_method == "softmax" else partial[:, 0]
+
+
+def unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregation_method="sum", vol_confidences=None):
+    """Same contract as reference op.py:99-166, batched."""
+    B, V, C, h, w = heatmaps.shape
+    vol_shape = coord_volumes.shape[1:4]
+    sampled = sample_views(heatmaps, proj_matricies, coord_volumes)
     if volume_aggregation_method.startswith("conf"):
         out = (sampled * vol_confidences.reshape(B, V, C, 1)).sum(1)
     elif volume_aggregation_method == "sum":

@@ -40,13 +40,13 @@ class Recorder:
             cw = (d.Cout + 3) // 4 * 4
             assert w.numel() == d.KD * d.KH * d.KW * d.Cin * cw and scale.numel() >= cw
         else:
-            assert d.in_format == capi.FMT_S32 and x.dtype == torch.bfloat16
+            assert d.in_format == capi.FMT_S32 and x.dtype == torch.float16
             assert d.Cin % 32 == 0 and d.sd == d.sh == d.sw == 1
             cp = (d.Cout + 15) // 16 * 16
             assert w.numel() == d.KD * d.KH * d.KW * (d.Cin // 32) * cp * 64 and scale.numel() >= cp
             assert cp <= 128 or cp % 128 == 0
             if d.out_format == capi.FMT_S32:
-                assert d.FC % 32 == 0 and cp >= d.FC, "padding channels of a split-bf16 output must be written"
+                assert d.FC % 32 == 0 and cp >= d.FC, "padding channels of a split-fp16 output must be written"
         self.calls.append(("conv_nd", (impl, d.Cin, d.Cout, (d.KD, d.KH, d.KW))))
 
 

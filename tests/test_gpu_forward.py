@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 # (features, unprojected/logits, volumes) relative tolerances; keypoints in mm
-TOL = {"simt": (1e-4, 2e-4, 1e-3, 0.05), "tc": (2e-4, 5e-4, 1e-3, 0.05), "tc1": (5e-2, 2e-1, None, None)}
+# keypoints: 0.5 mm = 2e-4 of the 2500 mm cuboid (the contract is 1e-3 relative)
+TOL = {"simt": (1e-4, 2e-4, 1e-3, 0.5), "tc": (2e-4, 5e-4, 1e-3, 0.5), "tc1": (5e-2, 2e-1, None, None)}
 
 
 @pytest.fixture(scope="module")
@@ -108,7 +109,7 @@ def test_config2_sizes_tensor_core_vs_exact_fp32():
     e_feat, e_vol = rel_err(a[1].cpu().numpy(), b[1].cpu().numpy()), rel_err(a[2].cpu().numpy(), b[2].cpu().numpy())
     e_kp = float((a[0] - b[0]).abs().max())
     print("config2 shapes: features %.3e volumes %.3e keypoints %.4f mm" % (e_feat, e_vol, e_kp))
-    assert e_feat < 3e-4 and e_vol < 1e-3 and e_kp < 0.05
+    assert e_feat < 3e-4 and e_vol < 1e-3 and e_kp < 0.5
     assert torch.equal(a[2].reshape(B, 17, -1).argmax(-1), b[2].reshape(B, 17, -1).argmax(-1))
     # size-independent properties of the softmaxed volumes / soft-argmax
     s = a[2].reshape(B, 17, -1).sum(-1)

@@ -57,12 +57,12 @@ def test_unproject_split_output_and_partial_sum():
     want = O.unproject_heatmaps(heat, proj, coord, "softmax")
     feats = cu(heat).permute(0, 1, 3, 4, 2).contiguous()
     nvox = n ** 3
-    out_s = torch.empty((B, nvox, 2 * C), dtype=torch.bfloat16, device=DEV)
+    out_s = torch.empty((B, nvox, 2 * C), dtype=torch.float16, device=DEV)
     capi.unproject_aggregate(feats, cu(proj), cu(coord).view(B, nvox, 3), None, out_s, capi.FMT_S32, capi.AGG["softmax"])
     out_f = torch.empty((B, nvox, C), dtype=torch.float32, device=DEV)
     capi.s32_to_f32(out_s, out_f, B * nvox, C)
     got = out_f.view(B, n, n, n, C).permute(0, 4, 1, 2, 3).cpu().numpy()
-    assert rel_err(got, want) < 3e-5          # split-bf16 keeps ~16 significand bits
+    assert rel_err(got, want) < 3e-5          # split-fp16 keeps ~22 significand bits
     # view-sharded: two "ranks" with two views each, summed partials == single pass
     parts = []
     for r in range(2):
@@ -137,7 +137,7 @@ def _engine(mode):
     e.model, e.mode, e.use_graph = _Holder(), mode, False
     e.act_fmt = capi.FMT_F32 if mode == "simt" else capi.FMT_S32
     e.tc_impl = {"simt": capi.CONV_SIMT, "tc": capi.CONV_TC, "tc1": capi.CONV_TC1}[mode]
-    e._packs, e._graphs, e.launches = {}, {}, 0
+    e._packs, e._graphs, e.launches, e.timeline = {}, {}, 0, None
     return e
 
 
@@ -196,7 +196,7 @@ CONV_CASES = [
 def test_conv_simt_vs_torch(case, out_fmt):
     dims, cin, cout, k, stride, pad, spatial, N = case
     if out_fmt == capi.FMT_S32 and cout % 32:
-        pytest.skip("split-bf16 output needs 32-channel blocks")
+        pytest.skip("split-fp16 output needs 32-channel blocks")
     torch.manual_seed(cin * 7 + cout)
     conv = (torch.nn.Conv2d if dims == 2 else torch.nn.Conv3d)(cin, cout, k, stride, pad, bias=(dims == 3)).eval()
     bn = _bn_for(conv, 5)
@@ -250,13 +250,14 @@ def test_maxpool(fmt):
     assert rel_err(got3.numpy(), F.max_pool3d(x3, 2, 2).numpy()) < 2e-5
 
 
-def test_split_bf16_round_trip_precision():
-    x = (torch.randn(1000, 64, device=DEV) * torch.logspace(-6, 6, 64, device=DEV)).contiguous()
-    s = torch.empty((1000, 128), dtype=torch.bfloat16, device=DEV)
+def test_split_fp16_round_trip_precision():
+    x = (torch.randn(1000, 64, device=DEV) * torch.logspace(-3, 4, 64, device=DEV)).contiguous()
+    s = torch.empty((1000, 128), dtype=torch.float16, device=DEV)
     capi.f32_to_s32(x, s, 1000, 64)
     y = torch.empty_like(x)
     capi.s32_to_f32(s, y, 1000, 64)
-    assert float(((x - y).abs() / x.abs().clamp_min(1e-30)).max()) < 2 ** -16
+    # 22 significand bits; values below the fp16 normal range keep an absolute error of 2^-24 / 2048
+    assert bool(((x - y).abs() <= x.abs() * 2 ** -21 + 3e-11).all())
 
 
 def test_nchw_to_nhwc_and_back():
