@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--image", type=int, default=384)
     ap.add_argument("--volume", type=int, default=64)
     ap.add_argument("--layers", type=int, default=152)
+    ap.add_argument("--collective", default="all_reduce", choices=["all_reduce", "reduce_scatter"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-calibrate", action="store_true", help="keep PyTorch default init (faster start, degenerate signal)")
     return ap.parse_args()
@@ -148,19 +149,13 @@ def main_native(args, rank, world, local_rank):
     cfg = testing.make_config(num_layers=args.layers, volume_size=n)
     torch.manual_seed(0)
     np.random.seed(0)
-    model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="native", conv_mode=args.mode, use_cuda_graph=True)
+    sharded = world > 1
+    model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="native", conv_mode=args.mode, use_cuda_graph=not sharded)
     if not args.no_calibrate:
-        model.backend = "torch"
         testing.randomize_weights(model, seed=0, calib_size=S, calib_views=1)
-        model.backend = "native"
     model = model.to(dev).eval()
-    images, batch = testing.make_batch(B, V, image_size=S, seed=rank)
-    pinned = images.pin_memory()
-    images_dev = images.to(dev)
-    h2d = images.numel() * 4
     eng = model.engine()
     model.clone_outputs = False
-
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -169,10 +164,39 @@ def main_native(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if not sharded:
+        images, batch = testing.make_batch(B, V, image_size=S, seed=rank)
+        pinned = images.pin_memory()
+        images_dev = images.to(dev)
+        parallelism = "dp1"
+
+        def step(img):
+            return model(img, None, batch)[0]
+    else:
+        # view-sharded: G ranks share a group batch of B*G samples and split its views; W/G groups are replicas
+        from lt_b200 import dist as lt_dist
+        plan = lt_dist.make_plan(world, rank, V)
+        pg = lt_dist.new_view_groups(plan)
+        Bg = B * plan.group_size
+        images_g, batch = testing.make_batch(Bg, V, image_size=S, seed=100 + plan.group_index)
+        views = plan.views
+        images = images_g[:, views].contiguous()
+        pinned = images.pin_memory()
+        images_dev = images.to(dev)
+        proj, base, position, stepv, rots, _ = model._host_geometry(batch, Bg, (S, S), (S // 4, S // 4))
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        geo = (up(proj[:, views]), up(position), up(base), up(stepv), up(rots.reshape(Bg, 9)))
+        parallelism = "view-sharded: %d group(s) x %d ranks, %d view(s)/rank, packed num/den %s over NCCL, V2V batch-sharded" % (
+            plan.n_groups, plan.group_size, len(views), args.collective)
+
+        def step(img):
+            return eng.forward_view_sharded(img, geo[0], geo[1], geo[2], geo[3], geo[4], plan, pg, args.collective)[0]
+    h2d = images.numel() * 4
+
     with torch.no_grad():
-        # ---- device-resident arm: graph replays, CUDA events, L2 flushed between iterations ----
+        # ---- device-resident arm: CUDA events, L2 flushed between iterations ----
         for _ in range(max(args.warmup, 3)):
-            out = model(images_dev, None, batch)
+            step(images_dev)
         barrier()
         launches = eng.launches
         sampler = ClockSampler(local_rank)
@@ -182,20 +206,20 @@ def main_native(args, rank, world, local_rank):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = model(images_dev, None, batch)
+            step(images_dev)
             e1.record()
             evs.append((e0, e1))
         barrier()
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
         clocks = sampler.summary()
 
-        # ---- end-to-end arm: public module call, pinned host images -> device, keypoints -> host ----
+        # ---- end-to-end arm: pinned host images -> device, forward, keypoints -> host ----
         for _ in range(2):
-            kp = model(pinned.to(dev, non_blocking=True), None, batch)[0].cpu()
+            kp = step(pinned.to(dev, non_blocking=True)).cpu()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            kp = model(pinned.to(dev, non_blocking=True), None, batch)[0].cpu()
+            kp = step(pinned.to(dev, non_blocking=True)).cpu()
         barrier()
         e2e_s = time.perf_counter() - t0
         d2h = kp.numel() * 4
@@ -203,9 +227,9 @@ def main_native(args, rank, world, local_rank):
         # ---- per-kernel timing for the roofline: one eager (non-graph) forward with event pairs per launch ----
         eng.use_graph = False
         model.use_cuda_graph = False
-        model(images_dev, None, batch)
+        step(images_dev)
         eng.timeline = []
-        model(images_dev, None, batch)
+        step(images_dev)
         torch.cuda.synchronize()
         agg = {}
         per_launch = []
@@ -214,7 +238,7 @@ def main_native(args, rank, world, local_rank):
             ms = a.elapsed_time(b)
             r[0] += ms; r[1] += flops; r[2] += nbytes; r[3] += 1
             per_launch.append({"kernel": label, "desc": desc, "ms": round(ms, 4), "gflop": round(flops / 1e9, 3), "mb": round(nbytes / 1e6, 3)})
-        if os.environ.get("LT_BENCH_TIMELINE"):
+        if os.environ.get("LT_BENCH_TIMELINE") and rank == 0:
             with open(os.environ["LT_BENCH_TIMELINE"], "w") as f:
                 json.dump(per_launch, f)
         eng.timeline = None
@@ -264,7 +288,7 @@ def main_native(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch %d per GPU"
                                    % (args.layers, V, S, S, n, B),
-                       "global_batch": B * world, "parallelism": "dp%d (batch replicas, no data-path collective)" % world,
+                       "global_batch": B * world, "parallelism": parallelism,
                        "conv_mode": args.mode, "l2": "256 MB buffer written between timed iterations (L2 flush)",
                        "weights": "random (seeded recipe, BN calibrated)" if not args.no_calibrate else "random (default init)"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

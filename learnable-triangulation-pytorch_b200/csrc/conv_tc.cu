@@ -17,6 +17,8 @@
 // warps 2-5 = epilogue (one TMEM lane quadrant each).
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace lt {
 
@@ -64,6 +66,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// byte offset of 16-byte chunk c16 of row `row` inside a [rows][128 B] tile with the 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128_off(int row, int c16) { return (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4)); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -117,10 +140,12 @@ struct TcParams {
   int bw, bh, bd, bn;      // M-tile box, product 128
   int tw, th, td, tn;      // tiles per dim
   int KW, KH, KD, pw, ph, pd;
+  int sw, sh, sd;          // input stride (TMA element strides)
   int CB;                  // 64-element K chunks per tap
   int b_step0, b_step1;    // B-map coordinates of chunk q: (q*b_step0, q*b_step1 + n0)
   int Nt, stages, terms;   // N tile, pipeline depth, 1 or 3 product terms
   int tmem_cols;
+  int tma_epi;             // 1: epilogue stages 32-channel blocks through smem and uses TMA store / residual load
   // epilogue
   int FC, FD, FH, FW, osd, osh, osw, ood, ooh, oow, relu, residual, out_format;
   const float* scale;
@@ -132,7 +157,9 @@ struct TcParams {
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
 
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmOut,
+                                                      const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.Nt * 128;
@@ -140,7 +167,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* res_full = tmem_full + 1;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -157,6 +185,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
+    mbar_init(&res_full[0], 1);
+    mbar_init(&res_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
@@ -178,7 +208,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         uint8_t* a_dst = smem + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + kATileBytes;
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-        tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 - p.pw + kw, oh0 - p.ph + kh, od0 - p.pd + kd, nb0);
+        tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 * p.sw - p.pw + kw, oh0 * p.sh - p.ph + kh, od0 * p.sd - p.pd + kd, nb0);
         tma_load_2d(b_dst, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0);
       }
     }
@@ -242,6 +272,113 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (p.tma_epi) {
+      // ---- staged epilogue: 32-channel blocks -> swizzled smem tile -> TMA store; residual tiles arrive by TMA ----
+      // All MMAs have completed (tmem_full), so the operand ring is free: reuse its first 64 KB.
+      uint8_t* out_stage = smem;              // 2 x 16 KB
+      uint8_t* res_stage = smem + 32768;      // 2 x 16 KB
+      const bool leader = threadIdx.x == 64;
+      const int nblk = p.Nt >> 5;
+      const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;   // tensor-map elements per channel
+      const int cbase = n0 * esz;
+      if (leader && p.residual != LT_RES_NONE) {
+        for (int i = 0; i < 2 && i < nblk; ++i) {
+          mbar_expect_tx(&res_full[i], 16384u);
+          tma_load_5d(res_stage + i * 16384, &tmRes, &res_full[i], cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+        }
+      }
+      for (int i = 0; i < nblk; ++i) {
+        const int buf = i & 1;
+        float v[32];
+        {
+          uint32_t t[16];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(i * 32 + h * 16), t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[h * 16 + j] = __uint_as_float(t[j]);
+            if (p.terms == 3) {
+              tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.Nt + i * 32 + h * 16), t);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[h * 16 + j] = fmaf(__uint_as_float(t[j]), kLoInv, v[h * 16 + j]);
+            }
+          }
+        }
+        const int co = n0 + i * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co + j));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + co + j));
+          v[j] = fmaf(v[j], sc.x, sh.x); v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+          v[j + 2] = fmaf(v[j + 2], sc.z, sh.z); v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+        }
+        float r[32];
+        if (p.residual != LT_RES_NONE) {
+          mbar_wait(&res_full[buf], (uint32_t)((i >> 1) & 1));
+          const uint32_t rb = smem_u32(res_stage + buf * 16384);
+          if (p.out_format == LT_FMT_F32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 q = lds128(rb + sw128_off(row, c));
+              r[c * 4] = __uint_as_float(q.x); r[c * 4 + 1] = __uint_as_float(q.y);
+              r[c * 4 + 2] = __uint_as_float(q.z); r[c * 4 + 3] = __uint_as_float(q.w);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 qh = lds128(rb + sw128_off(row, c)), ql = lds128(rb + sw128_off(row, c + 4));
+              const sh_t* hh = reinterpret_cast<const sh_t*>(&qh);
+              const sh_t* ll = reinterpret_cast<const sh_t*>(&ql);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) r[c * 8 + e] = join_s32(hh[e], ll[e]);
+            }
+          }
+        }
+        if (p.residual == LT_RES_BEFORE_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.residual == LT_RES_AFTER_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j];
+        }
+        if (leader) bulk_wait_read<1>();      // the store that last read out_stage[buf] (block i-2) is done with it
+        epi_bar_sync();
+        const uint32_t ob = smem_u32(out_stage + buf * 16384);
+        if (p.out_format == LT_FMT_F32) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts128(ob + sw128_off(row, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
+                                                       __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 qh, ql;
+            sh_t* hh = reinterpret_cast<sh_t*>(&qh);
+            sh_t* ll = reinterpret_cast<sh_t*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_s32(v[c * 8 + e], hh[e], ll[e]);
+            sts128(ob + sw128_off(row, c), qh);
+            sts128(ob + sw128_off(row, c + 4), ql);
+          }
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (leader) {
+          tma_store_5d(&tmOut, out_stage + buf * 16384, cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+          bulk_commit();
+          if (p.residual != LT_RES_NONE && i + 2 < nblk) {
+            mbar_expect_tx(&res_full[buf], 16384u);
+            tma_load_5d(res_stage + buf * 16384, &tmRes, &res_full[buf], cbase + (i + 2) * 32 * esz, ow0, oh0, od0, nb0);
+          }
+        }
+      }
+      if (leader) bulk_wait<0>();
+    } else
     for (int c0 = 0; c0 < p.Nt; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);   // whole warp (sync.aligned)
@@ -303,14 +440,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* estrides, int swizzle128) {
+                    const uint32_t* box, const uint32_t* estrides, int swizzle128, int f32 = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estrides ? estrides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -334,7 +471,21 @@ static void pick_box(int OW, int OH, int OD, int N, int* box) {
   if (best == 1e300) { box[0] = pow2_ceil(OW) > 128 ? 128 : pow2_ceil(OW); box[1] = box[2] = 1; box[3] = 128 / box[0]; }
 }
 
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, int n_tiles, cudaStream_t st) {
+// Tensor map over the output (or residual) tensor as seen by this launch: the stride-phase mapping
+// (out coordinate = o * os + oo) becomes a base offset plus scaled strides; box = one 32-channel block of an M tile.
+static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* d, const TcParams& p) {
+  const uint64_t rowb = (uint64_t)d->FC * 4;   // 4 bytes per channel in both formats
+  const uint8_t* b0 = reinterpret_cast<const uint8_t*>(base) +
+                      (((uint64_t)d->ood * d->FH + d->ooh) * d->FW + d->oow) * rowb;
+  const int f32 = d->out_format == LT_FMT_F32;
+  const uint64_t dims[5] = {(uint64_t)d->FC * (f32 ? 1 : 2), (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->OD, (uint64_t)d->N};
+  const uint64_t str[4] = {rowb * d->osw, rowb * d->FW * d->osh, rowb * d->FW * d->FH * d->osd, rowb * d->FW * d->FH * d->FD};
+  const uint32_t bx[5] = {(uint32_t)(f32 ? 32 : 64), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  return make_map(map, b0, 5, dims, str, bx, nullptr, 1, f32);
+}
+
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+                     TcParams& p, int n_tiles, cudaStream_t st) {
   const int stage_bytes = kATileBytes + p.Nt * 128;
   int stages = (96 * 1024) / stage_bytes;   // aim at two resident CTAs per SM
   if (stages < 2) stages = 2;
@@ -342,7 +493,8 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p
   p.stages = stages;
   const int acc_cols = (p.terms == 3 ? 2 : 1) * p.Nt;
   p.tmem_cols = pow2_ceil(acc_cols) < 32 ? 32 : pow2_ceil(acc_cols);
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 3) * 8 + 16 + 1024;
+  if (p.tma_epi && (size_t)stages * stage_bytes < 65536) return fail(LT_ERR_INVALID, "conv_tc: operand ring too small for the staged epilogue");
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
@@ -351,7 +503,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p
   }
   const long m_tiles = (long)p.tw * p.th * p.td * p.tn;
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
-  conv_tc_kernel<<<grid, 192, smem, st>>>(tmA, tmB, p);
+  conv_tc_kernel<<<grid, 192, smem, st>>>(tmA, tmB, tmOut, tmRes, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_kernel: %s", cudaGetErrorString(e));
   return LT_OK;
@@ -361,7 +513,6 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
                       const void* residual, void* out, int terms, void* stream) {
   LT_REQUIRE(d->in_format == LT_FMT_S32, "conv_tc: input must be split-fp16");
   LT_REQUIRE(d->Cin % 32 == 0, "conv_tc: Cin=%d must be a multiple of 32", d->Cin);
-  LT_REQUIRE(d->sd == 1 && d->sh == 1 && d->sw == 1, "conv_tc: strided input not supported (use LT_CONV_SIMT)");
   LT_REQUIRE(d->FC % 4 == 0 && (d->out_format == LT_FMT_F32 || d->FC % 32 == 0), "conv_tc: bad output channel stride %d", d->FC);
   const int CoutP = (d->Cout + 15) & ~15;
   const int Nt = CoutP <= 128 ? CoutP : 128;
@@ -376,6 +527,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
   p.bw = box[0]; p.bh = box[1]; p.bd = box[2]; p.bn = box[3];
   p.tw = ceil_div(d->OW, p.bw); p.th = ceil_div(d->OH, p.bh); p.td = ceil_div(d->OD, p.bd); p.tn = ceil_div(d->N, p.bn);
   p.KW = d->KW; p.KH = d->KH; p.KD = d->KD; p.pw = d->pw; p.ph = d->ph; p.pd = d->pd;
+  p.sw = d->sw; p.sh = d->sh; p.sd = d->sd;
   p.CB = CB; p.b_step0 = 0; p.b_step1 = CoutP; p.Nt = Nt; p.terms = terms;
   p.FC = d->FC; p.FD = d->FD; p.FH = d->FH; p.FW = d->FW;
   p.osd = d->osd; p.osh = d->osh; p.osw = d->osw; p.ood = d->ood; p.ooh = d->ooh; p.oow = d->oow;
@@ -387,8 +539,14 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     const uint64_t rowb = (uint64_t)d->Cin * 2 * 2;  // 2*Cin fp16 per position
     const uint64_t dims[5] = {(uint64_t)d->Cin * 2, (uint64_t)d->IW, (uint64_t)d->IH, (uint64_t)d->ID, (uint64_t)d->N};
     const uint64_t str[4] = {rowb, rowb * d->IW, rowb * d->IW * d->IH, rowb * d->IW * d->IH * d->ID};
-    const uint32_t bx[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
-    int rc = make_map(&tmA, in, 5, dims, str, bx, nullptr, 1);
+    // strided convs: TMA traversal strides; the box spans (b-1)*s+1 input positions and delivers b of them
+    static const int box_is_count = getenv("LT_TMA_STRIDE_MODE") && atoi(getenv("LT_TMA_STRIDE_MODE")) == 1;
+    const uint32_t es[5] = {1, (uint32_t)d->sw, (uint32_t)d->sh, (uint32_t)d->sd, 1};
+    uint32_t bx[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+    if (!box_is_count)
+      for (int i = 1; i <= 3; ++i) bx[i] = (bx[i] - 1) * es[i] + 1;
+    LT_REQUIRE(bx[1] <= 256 && bx[2] <= 256 && bx[3] <= 256, "conv_tc: strided box exceeds 256");
+    int rc = make_map(&tmA, in, 5, dims, str, bx, es, 1);
     if (rc) return rc;
   }
   {
@@ -398,7 +556,18 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
     if (rc) return rc;
   }
-  return launch_tc(tmA, tmB, p, CoutP / Nt, (cudaStream_t)stream);
+  CUtensorMap tmOut = tmA, tmRes = tmA;
+  static const int direct_epi = getenv("LT_TC_EPILOGUE") && !strcmp(getenv("LT_TC_EPILOGUE"), "direct");
+  p.tma_epi = (!direct_epi && d->FC % 32 == 0 && Nt % 32 == 0 && CoutP <= d->FC) ? 1 : 0;
+  if (p.tma_epi) {
+    int rc = make_out_map(&tmOut, out, d, p);
+    if (rc) return rc;
+    if (d->residual != LT_RES_NONE) {
+      rc = make_out_map(&tmRes, residual, d, p);
+      if (rc) return rc;
+    }
+  }
+  return launch_tc(tmA, tmB, tmOut, tmRes, p, CoutP / Nt, (cudaStream_t)stream);
 }
 
 int conv_tc_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
@@ -468,7 +637,7 @@ extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M
   p.OW = M; p.OH = 1; p.OD = 1; p.N = 1;
   p.bw = 128; p.bh = 1; p.bd = 1; p.bn = 1;
   p.tw = ceil_div(M, 128); p.th = 1; p.td = 1; p.tn = 1;
-  p.KW = p.KH = p.KD = 1; p.pw = p.ph = p.pd = 0;
+  p.KW = p.KH = p.KD = 1; p.pw = p.ph = p.pd = 0; p.sw = p.sh = p.sd = 1;
   p.CB = K / 64; p.b_step0 = 64; p.b_step1 = 0; p.Nt = Nt; p.terms = 0;
   p.FC = N; p.FD = 1; p.FH = 1; p.FW = M; p.osd = p.osh = p.osw = 1; p.ood = p.ooh = p.oow = 0;
   p.relu = 0; p.residual = LT_RES_NONE; p.out_format = LT_FMT_F32;
@@ -488,5 +657,6 @@ extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M
     int rc = make_map(&tmB, b, 2, dims, str, bx, nullptr, 1);
     if (rc) return rc;
   }
-  return launch_tc(tmA, tmB, p, N / Nt, (cudaStream_t)stream);
+  p.tma_epi = 0;
+  return launch_tc(tmA, tmB, tmA, tmA, p, N / Nt, (cudaStream_t)stream);
 }

@@ -35,6 +35,8 @@ struct UnprojParams {
 struct Taps {
   int o00, o01, o10, o11;  // pixel offsets (y*w + x), valid only when the matching weight flag is set
   float w00, w01, w10, w11;
+  float fx, fy;            // fractional position inside the cell (exact: ix - floor(ix))
+  int xi, yi;              // integer cell coordinates (clamped to [-2, size])
   unsigned mask;           // bit i set -> tap i inside the map; 0 when depth <= 0
 };
 
@@ -55,6 +57,8 @@ __device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float X, 
   const float iy = ((gy + 1.0f) / 2.0f) * (float)(h - 1);
   const float x0 = floorf(ix), y0 = floorf(iy);
   const float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+  t.fx = ix - x0;
+  t.fy = iy - y0;
   t.w00 = (x1 - ix) * (y1 - iy);  // nw
   t.w01 = (ix - x0) * (y1 - iy);  // ne
   t.w10 = (x1 - ix) * (iy - y0);  // sw
@@ -65,6 +69,7 @@ __device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float X, 
   // NaN/inf-safe integer conversion (comparisons above are false for NaN)
   const int xi = (int)fminf(fmaxf(x0, -2.0f), wm + 1.0f);
   const int yi = (int)fminf(fmaxf(y0, -2.0f), hm + 1.0f);
+  t.xi = xi; t.yi = yi;
   t.o00 = yi * w + xi;
   t.o01 = t.o00 + 1;
   t.o10 = t.o00 + w;
@@ -252,6 +257,136 @@ __global__ void __launch_bounds__(256) unproject_kernel(const UnprojParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path (C = 4*G channels, V <= 8): the G lanes of a voxel group split the per-view ray setup
+// (lane j builds the taps of view j and the group shares them with width-G shuffles), per-view samples
+// stay in registers and the view softmax is one pass (max, then exp once: num = sum s*e, den = sum e).
+// ------------------------------------------------------------------------------------------------
+template <int G, int MAXV>
+__global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams p) {
+  __shared__ float sP[kMaxStoredViews * 12];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < p.V * 12; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
+  __syncthreads();
+
+  constexpr int C = 4 * G;
+  const int sub = threadIdx.x % G;
+  const int slot = threadIdx.x / G;
+  constexpr int VPB = 256 / G;
+  const long map_elems = (long)p.h * p.w * C;
+  const float* fbase = p.features + (long)b * p.V * map_elems + sub * 4;
+  const int c0 = sub * 4;
+  const int wm = p.w - 1, hm = p.h - 1;
+
+  // block-uniform trip count: the width-G shuffles below need every lane of the warp present
+  for (long vbase = (long)blockIdx.x * VPB; vbase < p.nvox; vbase += (long)gridDim.x * VPB) {
+    const bool live = vbase + slot < p.nvox;
+    const long vox = live ? vbase + slot : p.nvox - 1;
+    const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
+    const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
+    float s[MAXV][4];
+#pragma unroll
+    for (int v0 = 0; v0 < MAXV; v0 += G) {
+      if (v0 >= p.V) break;
+      // my share of the ray setup: view v0 + sub
+      int xi_m = 0, yi_m = 0; float fx_m = 0.f, fy_m = 0.f; unsigned mask_m = 0u;
+      if (v0 + sub < p.V) {
+        const Taps t = make_taps(sP + (v0 + sub) * 12, X, Y, Z, p.h, p.w);
+        xi_m = t.xi; yi_m = t.yi; mask_m = t.mask;
+        fx_m = t.fx; fy_m = t.fy;
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int v = v0 + j;
+        if (v >= MAXV) break;
+        if (v < p.V) {
+          const int xi = __shfl_sync(0xffffffffu, xi_m, j, G);
+          const int yi = __shfl_sync(0xffffffffu, yi_m, j, G);
+          const float fx = __shfl_sync(0xffffffffu, fx_m, j, G);
+          const float fy = __shfl_sync(0xffffffffu, fy_m, j, G);
+          const unsigned mask = __shfl_sync(0xffffffffu, mask_m, j, G);
+          // unconditional, clamped loads (independent -> all 4 taps of all views in flight); invalid taps get weight 0
+          const int x0 = min(max(xi, 0), wm), x1 = min(max(xi + 1, 0), wm);
+          const int y0 = min(max(yi, 0), hm), y1 = min(max(yi + 1, 0), hm);
+          const float* f = fbase + (long)v * map_elems;
+          const float4 q00 = __ldg(reinterpret_cast<const float4*>(f + (long)(y0 * p.w + x0) * C));
+          const float4 q01 = __ldg(reinterpret_cast<const float4*>(f + (long)(y0 * p.w + x1) * C));
+          const float4 q10 = __ldg(reinterpret_cast<const float4*>(f + (long)(y1 * p.w + x0) * C));
+          const float4 q11 = __ldg(reinterpret_cast<const float4*>(f + (long)(y1 * p.w + x1) * C));
+          const float gx = 1.0f - fx, gy = 1.0f - fy;
+          const float w00 = (mask & 1u) ? gx * gy : 0.0f, w01 = (mask & 2u) ? fx * gy : 0.0f;
+          const float w10 = (mask & 4u) ? gx * fy : 0.0f, w11 = (mask & 8u) ? fx * fy : 0.0f;
+          s[v][0] = fmaf(q11.x, w11, fmaf(q10.x, w10, fmaf(q01.x, w01, q00.x * w00)));
+          s[v][1] = fmaf(q11.y, w11, fmaf(q10.y, w10, fmaf(q01.y, w01, q00.y * w00)));
+          s[v][2] = fmaf(q11.z, w11, fmaf(q10.z, w10, fmaf(q01.z, w01, q00.z * w00)));
+          s[v][3] = fmaf(q11.w, w11, fmaf(q10.w, w10, fmaf(q01.w, w01, q00.w * w00)));
+        }
+      }
+    }
+
+    float o[4], o2[4];
+    if (p.agg == LT_AGG_SOFTMAX) {
+      if (p.partial) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[i] = 0.f; o2[i] = 0.f; }
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v)
+          if (v < p.V) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float e = __expf(s[v][i]); o[i] = fmaf(s[v][i], e, o[i]); o2[i] += e; }
+          }
+      } else {
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v)
+          if (v < p.V) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[i], s[v][i]);
+          }
+        float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v)
+          if (v < p.V) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float e = __expf(s[v][i] - m[i]); num[i] = fmaf(s[v][i], e, num[i]); den[i] += e; }
+          }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = num[i] / den[i];
+      }
+    } else if (p.agg == LT_AGG_MAX) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = -INFINITY;
+#pragma unroll
+      for (int v = 0; v < MAXV; ++v)
+        if (v < p.V) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], s[v][i]);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int v = 0; v < MAXV; ++v)
+        if (v < p.V) {
+          float cf[4] = {1.f, 1.f, 1.f, 1.f};
+          if (p.agg == LT_AGG_CONF) load_vec<4>(p.conf + ((long)b * p.V + v) * C + c0, cf);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = fmaf(s[v][i], cf[i], o[i]);
+        }
+    }
+
+    if (!live) continue;
+    if (p.partial) {
+      const int planes = (p.agg == LT_AGG_SOFTMAX) ? 2 : 1;
+      float* d0 = reinterpret_cast<float*>(p.out) + (((long)b * planes) * p.nvox + vox) * C + c0;
+      *reinterpret_cast<float4*>(d0) = make_float4(o[0], o[1], o[2], o[3]);
+      if (planes == 2) *reinterpret_cast<float4*>(d0 + p.nvox * C) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+    } else {
+      store_out<4>(p, b, vox, c0, o);
+    }
+  }
+}
+
 // partial[B][P][nvox][C] -> out[B][nvox][C] (divide numerator by denominator for softmax)
 __global__ void __launch_bounds__(256) unproject_finalize_kernel(const float* __restrict__ partial, void* out, int out_format,
                                                                  int B, int C, long nvox, int agg) {
@@ -300,7 +435,21 @@ static int launch_unproject(const float* features, const float* proj, const floa
   dim3 grid((unsigned)blocks, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool stored = V <= kMaxStoredViews;
-  if (vec4) {
+  if (vec4 && stored && units == G && C <= 128) {   // C = 4*G exactly: one float4 per lane per tap
+#define LT_UNPROJ_FAST(GG)                                                              \
+    if (V <= 2) unproject_fast_kernel<GG, 2><<<grid, 256, 0, st>>>(p);                  \
+    else if (V <= 4) unproject_fast_kernel<GG, 4><<<grid, 256, 0, st>>>(p);             \
+    else unproject_fast_kernel<GG, 8><<<grid, 256, 0, st>>>(p)
+    switch (G) {
+      case 1: LT_UNPROJ_FAST(1); break;
+      case 2: LT_UNPROJ_FAST(2); break;
+      case 4: LT_UNPROJ_FAST(4); break;
+      case 8: LT_UNPROJ_FAST(8); break;
+      case 16: LT_UNPROJ_FAST(16); break;
+      default: LT_UNPROJ_FAST(32); break;
+    }
+#undef LT_UNPROJ_FAST
+  } else if (vec4) {
     if (stored) unproject_kernel<4, true><<<grid, 256, 0, st>>>(p);
     else unproject_kernel<4, false><<<grid, 256, 0, st>>>(p);
   } else {

@@ -14,6 +14,7 @@ Layers the tensor-core kernel does not cover (the 3-channel stem and the six str
 the trunk) run on the FFMA kernel in every mode.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -95,6 +96,7 @@ class NativeEngine:
         self._packs_version = None
         self._graphs = {}
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
+        self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
 
@@ -110,7 +112,7 @@ class NativeEngine:
         pk = ConvPack()
         pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
         pk.kmacs = taps * cin * cout   # algorithmic MACs per output position
-        use_tc = (self.mode != "simt") and not force_simt and max(stride) == 1
+        use_tc = (self.mode != "simt") and not force_simt and (max(stride) == 1 or self.tc_strided)
         scale, shift = _fold_bn(bias, bn, cout, dev)
         if use_tc:
             cin_p = _round_up(cin, 32)

@@ -41,7 +41,7 @@ class Recorder:
             assert w.numel() == d.KD * d.KH * d.KW * d.Cin * cw and scale.numel() >= cw
         else:
             assert d.in_format == capi.FMT_S32 and x.dtype == torch.float16
-            assert d.Cin % 32 == 0 and d.sd == d.sh == d.sw == 1
+            assert d.Cin % 32 == 0
             cp = (d.Cout + 15) // 16 * 16
             assert w.numel() == d.KD * d.KH * d.KW * (d.Cin // 32) * cp * 64 and scale.numel() >= cp
             assert cp <= 128 or cp % 128 == 0
@@ -76,4 +76,4 @@ def test_engine_plan_is_consistent(monkeypatch, mode, layers):
     assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] == "conv_tc_pack_weights") + 2   # softargmax = 3 launches
     if mode == "tc":
         simt = [c for c in convs if c[1][0] == capi.CONV_SIMT]
-        assert len(simt) == 1 + (3 if layers == 18 else 3) + n_ds - (1 if layers == 50 else 0), len(simt)
+        assert len(simt) == 1, "only the 3-channel stem stays on the FFMA kernel"

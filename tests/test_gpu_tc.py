@@ -78,6 +78,27 @@ def test_conv_tc_vs_torch(case, mode):
         assert float(full[:, cout:].abs().max()) == 0.0, "padding channels must be written as zeros"
 
 
+@pytest.mark.parametrize("case", [(64, 64, 3, 2, 1, (12, 12), 2), (64, 128, 1, 2, 0, (12, 12), 2), (128, 128, 3, 2, 1, (48, 48), 4),
+                                  (256, 512, 1, 2, 0, (48, 48), 4)])
+def test_conv_tc_stride2_vs_torch(case):
+    """Stride-2 convs of the trunk (pose_resnet.py:62-69,236-243) through TMA traversal strides."""
+    cin, cout, k, stride, pad, spatial, N = case
+    torch.manual_seed(cin + cout + k)
+    conv = torch.nn.Conv2d(cin, cout, k, stride, pad, bias=False).eval()
+    bn = _bn_for(conv, 11)
+    x = torch.randn(N, cin, *spatial)
+    with torch.no_grad():
+        want = F.relu(bn(conv(x)))
+    e = _engine("tc")
+    pk = e._pack_conv(conv.to(DEV), bn.to(DEV))
+    assert pk.impl == capi.CONV_TC
+    ya = e._conv(act_from_nchw(x, capi.FMT_S32), pk, relu=True)
+    torch.cuda.synchronize()
+    err = rel_err(act_to_nchw(ya, cout).squeeze(2).cpu().numpy(), want.numpy())
+    print("conv_tc stride2 %s rel err %.2e" % (case, err))
+    assert err < TOL["tc"]
+
+
 def test_conv_tc_fp32_output_and_no_residual():
     torch.manual_seed(3)
     conv = torch.nn.Conv2d(256, 32, 1).eval()
