@@ -45,7 +45,9 @@ enum lt_agg { LT_AGG_SUM = 0, LT_AGG_MAX = 1, LT_AGG_SOFTMAX = 2, LT_AGG_CONF = 
 enum lt_conv_impl {
   LT_CONV_SIMT = 0, /* fp32 FFMA implicit GEMM (exact, any shape) */
   LT_CONV_TC = 1,   /* tcgen05, split-fp16 3-term products (fp32-grade) */
-  LT_CONV_TC1 = 2   /* tcgen05, high parts only (plain fp16 precision, fast mode) */
+  LT_CONV_TC1 = 2,  /* tcgen05, high parts only (plain fp16 precision, fast mode) */
+  LT_CONV_TC_FOLD = 3 /* tcgen05, kw taps folded into N, persistent (Cin = 32 cubic 3^3 / 7^3 stride-1 layers; weights from
+                         lt_conv_fold_pack_weights; desc->Cout = real channel count <= 32, FC = 32) */
 };
 
 /* residual placement in the conv epilogue */
@@ -143,6 +145,10 @@ int lt_conv_nd_fwd(const lt_conv_desc* desc, const void* in, const void* weight,
  * to split-fp16 [taps][Cin/32][CoutP][64], CoutP = round_up(Cout, 16); Cin % 32 == 0. */
 size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout);
 int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
+
+/* kw-folded weight packing: float32 [K^3][32][Cout] (DEVICE) -> split-fp16 [kd][kh][kw*NC + co][64], NC = round_up(Cout, 16). */
+size_t lt_conv_fold_weight_bytes(int K, int Cout);
+int lt_conv_fold_pack_weights(const float* w_tap_ci_co, void* packed, int K, int Cout, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Max pooling, channels-last (pose_resnet.py:208 3x3 s2 p1; v2v.py:51 2x2x2 s2).

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 
 FMT_F32, FMT_S32 = 0, 1
 AGG = {"sum": 0, "max": 1, "softmax": 2, "conf": 3, "conf_norm": 3}
-CONV_SIMT, CONV_TC, CONV_TC1 = 0, 1, 2
+CONV_SIMT, CONV_TC, CONV_TC1, CONV_TC_FOLD = 0, 1, 2, 3
 RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU = 0, 1, 2
 
 c_int, c_long, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
@@ -51,6 +51,8 @@ SIGNATURES = {
     "lt_conv_nd_fwd": (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6 + [c_int, c_void_p]),
     "lt_conv_tc_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lt_conv_fold_weight_bytes": (c_size_t, [c_int, c_int]),
+    "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
     "lt_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "lt_f32_to_s32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
@@ -153,6 +155,14 @@ def conv_tc_weight_bytes(taps, cin, cout):
 
 def conv_tc_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
     _check(lib().lt_conv_tc_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), taps, cin, cout, _stream()), "lt_conv_tc_pack_weights")
+
+
+def conv_fold_weight_bytes(k, cout):
+    return lib().lt_conv_fold_weight_bytes(k, cout)
+
+
+def conv_fold_pack_weights(w_tap_ci_co, packed, k, cout):
+    _check(lib().lt_conv_fold_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), k, cout, _stream()), "lt_conv_fold_pack_weights")
 
 
 def maxpool(inp, out, fmt, N, ID, IH, IW, C, k, s, p, OD, OH, OW):

@@ -35,6 +35,9 @@ int conv_simt_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
 int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
                       const void* residual, void* out, int terms, void* stream);
 
+int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                  const void* residual, void* out, void* stream);
+
 }  // namespace lt
 
 extern "C" int lt_version(void) { return 100; }
@@ -67,6 +70,7 @@ extern "C" int lt_conv_nd_fwd(const lt_conv_desc* d, const void* in, const void*
   LT_REQUIRE(d->residual >= LT_RES_NONE && d->residual <= LT_RES_AFTER_RELU, "conv_nd: bad residual mode");
   if (impl == LT_CONV_SIMT) return conv_simt_fwd(d, in, weight, scale, shift, residual, out, stream);
   if (impl == LT_CONV_TC) return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 3, stream);
+  if (impl == LT_CONV_TC_FOLD) return conv_fold_fwd(d, in, weight, scale, shift, residual, out, stream);
   if (impl == LT_CONV_TC1) return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 1, stream);
   return fail(LT_ERR_INVALID, "conv_nd: unknown impl %d", impl);
 }

@@ -1,0 +1,418 @@
+// kw-folded tensor-core convolution for the narrow (Cin = 32) stride-1 cubic layers of the V2V net at
+// full resolution (v2v.py:146 7^3 32->16, :24-28 3^3 32->32) -- the layers that dominate the step.
+//
+// Why: with 32 input channels an implicit-GEMM tap carries only K = 32, so a generic "one shifted A tile per
+// tap" kernel re-streams 128 x 128 B from L2 for every tap and is pinned to the L2->smem bandwidth, and a 128 x N
+// UMMA with N = 16/32 is bound by the shared-memory read of A (32 cycles) rather than by the tensor pipe.
+// Here the kw taps are folded into the MMA's N dimension:
+//     D[(line, xi)][kw*NC + co] = sum_{kd,kh,ci} in[z+kd-p][y+line+kh-p][x0-p+xi][ci] * W[kd][kh][kw][ci][co]
+//     out[(line, xo)][co]       = sum_kw D[(line, xo+kw)][kw*NC + co]          (shift-add in the epilogue)
+// so one un-shifted 16-position line tile feeds N = K*NC = 96 / 112 columns (MMA is math-bound, not A-read-bound),
+// a z-slab of (8+K-1) lines is loaded ONCE per kd and reused for all kh via the descriptor start address, and
+// the 3^3 weights (108 KB) stay resident in shared memory for the whole persistent CTA.  Each M tile yields
+// 16-K+1 output positions per line (14 for K=3, 10 for K=7).
+//
+// Persistent CTAs (one per SM), warp roles as in conv_tc.cu; TMEM holds two accumulator stages of 2*NF columns
+// (hi*hi and the 2^11-scaled cross terms) so the epilogue of tile i overlaps the MMAs of tile i+1; the epilogue
+// shift-adds with warp shuffles, applies scale/shift/residual/ReLU, compacts the valid rows into a 128B-swizzled
+// staging tile and stores it with TMA (which also clips partial tiles).
+#include "tc_common.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+namespace lt {
+
+struct FoldParams {
+  int N, D, H, W;
+  int K, pad;
+  int NC, NF, OWt;
+  int xwins, yblks;
+  long tiles;
+  int slab_bytes, a_slots;
+  int b_resident, b_slots, b_bytes;
+  int stage_rows;        // 8 * OWt
+  int out_format, relu, residual;
+  const float* scale;
+  const float* shift;
+  // smem offsets (bytes from the 1024-aligned base)
+  int off_b, off_a, off_out, off_res, off_bar;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmOut,
+                                                           const __grid_constant__ CUtensorMap tmRes, const FoldParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* b_smem = smem + p.off_b;
+  uint8_t* a_smem = smem + p.off_a;
+  uint8_t* out_stage = smem + p.off_out;
+  uint8_t* res_stage = smem + p.off_res;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* a_full = bars;                 // [a_slots]
+  uint64_t* a_empty = a_full + p.a_slots;  // [a_slots]
+  uint64_t* b_full = a_empty + p.a_slots;  // [b_slots] (streamed) or [1] (resident: all weights)
+  uint64_t* b_empty = b_full + p.b_slots;  // [b_slots]
+  uint64_t* acc_full = b_empty + p.b_slots;  // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint64_t* res_full = acc_empty + 2;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps2 = p.K * p.K;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_init(res_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_expect_tx(&b_full[0], (uint32_t)(taps2 * p.b_bytes));
+        for (int t = 0; t < taps2; ++t) tma_load_2d(b_smem + (size_t)t * p.b_bytes, &tmB, &b_full[0], 0, t * p.NF);
+      }
+      uint32_t pa = 0, pb = 0;
+      for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        long t = tile;
+        const int xw = (int)(t % p.xwins); t /= p.xwins;
+        const int yb = (int)(t % p.yblks); t /= p.yblks;
+        const int z = (int)(t % p.D);
+        const int n = (int)(t / p.D);
+        for (int kd = 0; kd < p.K; ++kd) {
+          const uint32_t slot = pa % p.a_slots;
+          mbar_wait(&a_empty[slot], ((pa / p.a_slots) & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[slot], (uint32_t)p.slab_bytes);
+          tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.pad, yb * 8 - p.pad,
+                      z + kd - p.pad, n);
+          ++pa;
+          if (!p.b_resident) {
+            for (int kh = 0; kh < p.K; ++kh) {
+              const uint32_t bs = pb % p.b_slots;
+              mbar_wait(&b_empty[bs], ((pb / p.b_slots) & 1u) ^ 1u);
+              mbar_expect_tx(&b_full[bs], (uint32_t)p.b_bytes);
+              tma_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, &b_full[bs], 0, (kd * p.K + kh) * p.NF);
+              ++pb;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.NF);
+      if (p.b_resident) { mbar_wait(&b_full[0], 0); }
+      uint32_t pa = 0, pb = 0, it = 0;
+      for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1u;
+        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d1 = tmem_base + as * 2u * (uint32_t)p.NF;
+        const uint32_t d2 = d1 + (uint32_t)p.NF;
+        uint32_t acc1 = 0, acc2 = 0;
+        for (int kd = 0; kd < p.K; ++kd) {
+          const uint32_t slot = pa % p.a_slots;
+          mbar_wait(&a_full[slot], (pa / p.a_slots) & 1u);
+          tc_fence_after();
+          const uint32_t slab = smem_u32(a_smem + (size_t)slot * p.slab_bytes);
+          for (int kh = 0; kh < p.K; ++kh) {
+            uint32_t b_addr;
+            uint32_t bs = 0;
+            if (p.b_resident) {
+              b_addr = smem_u32(b_smem + (size_t)(kd * p.K + kh) * p.b_bytes);
+            } else {
+              bs = pb % p.b_slots;
+              mbar_wait(&b_full[bs], (pb / p.b_slots) & 1u);
+              tc_fence_after();
+              b_addr = smem_u32(b_smem + (size_t)bs * p.b_bytes);
+            }
+            const uint64_t ad = make_sw128_desc(slab + (uint32_t)kh * 2048u);   // line kh of the slab: 16 rows x 128 B
+            const uint64_t bd = make_sw128_desc(b_addr);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+              const uint64_t ah = ad + (uint64_t)(sl * 2), al = ad + (uint64_t)(4 + sl * 2);
+              const uint64_t bh = bd + (uint64_t)(sl * 2), bl = bd + (uint64_t)(4 + sl * 2);
+              umma_f16(d1, ah, bh, idesc, acc1);
+              acc1 = 1;
+              umma_f16(d2, ah, bl, idesc, acc2);
+              acc2 = 1;
+              umma_f16(d2, al, bh, idesc, 1);
+            }
+            if (!p.b_resident) { umma_commit(&b_empty[bs]); ++pb; }
+          }
+          umma_commit(&a_empty[slot]);
+          ++pa;
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int line = row >> 4, xi = row & 15;
+    const bool keep = xi < p.OWt;
+    const int srow = line * p.OWt + xi;        // compacted staging row
+    const bool leader = threadIdx.x == 64;
+    const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
+    const uint32_t stage_bytes = (uint32_t)p.stage_rows * 128u;
+    uint32_t it = 0;
+    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      long t = tile;
+      const int xw = (int)(t % p.xwins); t /= p.xwins;
+      const int yb = (int)(t % p.yblks); t /= p.yblks;
+      const int z = (int)(t % p.D);
+      const int n = (int)(t / p.D);
+      const uint32_t as = it & 1u;
+      if (leader && p.residual != LT_RES_NONE) {
+        mbar_expect_tx(res_full, stage_bytes);
+        tma_load_5d(res_stage, &tmRes, res_full, 0, xw * p.OWt, yb * 8, z, n);
+      }
+      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      tc_fence_after();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+      const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 2u * (uint32_t)p.NF;
+      for (int kw = 0; kw < p.K; ++kw) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h * 16 >= p.NC) break;
+          uint32_t t1[16], t2[16];
+          tmem_ld16(tb + (uint32_t)(kw * p.NC + h * 16), t1);
+          tmem_ld16(tb + (uint32_t)(p.NF + kw * p.NC + h * 16), t2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float d = fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j]));
+            v[h * 16 + j] += __shfl_down_sync(0xffffffffu, d, kw);    // row (line, xi + kw) -> output (line, xi)
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);              // accumulator stage drained: the MMA warp may start tile it+2
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + j));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + j));
+        v[j] = fmaf(v[j], sc.x, sh.x); v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+        v[j + 2] = fmaf(v[j + 2], sc.z, sh.z); v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+      }
+      float r[32];
+      if (p.residual != LT_RES_NONE) {
+        mbar_wait(res_full, it & 1u);
+        const uint32_t rb = smem_u32(res_stage);
+        if (keep) {
+          if (p.out_format == LT_FMT_F32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 q = lds128(rb + sw128_off(srow, c));
+              r[c * 4] = __uint_as_float(q.x); r[c * 4 + 1] = __uint_as_float(q.y);
+              r[c * 4 + 2] = __uint_as_float(q.z); r[c * 4 + 3] = __uint_as_float(q.w);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 qh = lds128(rb + sw128_off(srow, c)), ql = lds128(rb + sw128_off(srow, c + 4));
+              const sh_t* hh = reinterpret_cast<const sh_t*>(&qh);
+              const sh_t* ll = reinterpret_cast<const sh_t*>(&ql);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) r[c * 8 + e] = join_s32(hh[e], ll[e]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0.0f;
+        }
+      }
+      if (p.residual == LT_RES_BEFORE_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.residual == LT_RES_AFTER_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
+      }
+      if (leader) bulk_wait_read<0>();          // previous tile's store has finished reading out_stage
+      epi_bar_sync();
+      if (keep) {
+        const uint32_t ob = smem_u32(out_stage);
+        if (p.out_format == LT_FMT_F32) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            sts128(ob + sw128_off(srow, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
+                                                        __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 qh, ql;
+            sh_t* hh = reinterpret_cast<sh_t*>(&qh);
+            sh_t* ll = reinterpret_cast<sh_t*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_s32(v[c * 8 + e], hh[e], ll[e]);
+            sts128(ob + sw128_off(srow, c), qh);
+            sts128(ob + sw128_off(srow, c + 4), ql);
+          }
+        }
+      }
+      fence_proxy_async();
+      epi_bar_sync();
+      if (leader) {
+        tma_store_5d(&tmOut, out_stage, 0, xw * p.OWt, yb * 8, z, n);
+        bulk_commit();
+      }
+      (void)esz;
+    }
+    if (leader) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// fp32 [K^3 taps (kd,kh,kw)][32][Cout] -> split-fp16 [kd][kh][kw*NC + co][64]
+__global__ void __launch_bounds__(256) pack_fold_weights_kernel(const float* __restrict__ w, sh_t* __restrict__ out, int K, int Cout, int NC) {
+  const int NF = K * NC;
+  const long total = (long)K * K * NF * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % 32);
+    long r = i / 32;
+    const int col = (int)(r % NF); r /= NF;
+    const int kh = (int)(r % K);
+    const int kd = (int)(r / K);
+    const int kw = col / NC, co = col % NC;
+    const float v = (co < Cout) ? w[((((long)kd * K + kh) * K + kw) * 32 + ci) * Cout + co] : 0.0f;
+    sh_t hi, lo;
+    split_s32(v, hi, lo);
+    sh_t* row = out + (((long)kd * K + kh) * NF + col) * 64;
+    row[ci] = hi;
+    row[32 + ci] = lo;
+  }
+}
+
+int conv_fold_supported(const lt_conv_desc* d) {
+  const bool cubic = d->KD == d->KH && d->KH == d->KW && (d->KW == 3 || d->KW == 7);
+  const int p = d->KW / 2;
+  const int NC = (d->Cout + 15) & ~15;
+  return cubic && d->Cin == 32 && NC <= 32 && d->KW * NC <= 128 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == p &&
+         d->ph == p && d->pw == p && d->OD == d->ID && d->OH == d->IH && d->OW == d->IW && d->osd == 1 && d->osh == 1 &&
+         d->osw == 1 && d->ood == 0 && d->ooh == 0 && d->oow == 0 && d->FD == d->OD && d->FH == d->OH && d->FW == d->OW &&
+         d->FC == 32 && d->in_format == LT_FMT_S32 && d->IW >= 16;
+}
+
+static inline int up1024(int v) { return (v + 1023) & ~1023; }
+
+int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                  const void* residual, void* out, void* stream) {
+  LT_REQUIRE(conv_fold_supported(d), "conv_fold: unsupported layer shape");
+  FoldParams p;
+  p.N = d->N; p.D = d->ID; p.H = d->IH; p.W = d->IW;
+  p.K = d->KW; p.pad = d->KW / 2;
+  p.NC = (d->Cout + 15) & ~15;
+  p.NF = p.K * p.NC;
+  p.OWt = 16 - p.K + 1;
+  p.xwins = ceil_div(p.W, p.OWt);
+  p.yblks = ceil_div(p.H, 8);
+  p.tiles = (long)p.N * p.D * p.yblks * p.xwins;
+  const int slab_lines = 8 + p.K - 1;
+  p.slab_bytes = 16 * slab_lines * 128;
+  p.b_bytes = p.NF * 128;
+  p.b_resident = (p.K * p.K * p.b_bytes <= 112 * 1024) ? 1 : 0;
+  p.b_slots = p.b_resident ? 1 : 4;
+  p.a_slots = 3;
+  p.stage_rows = 8 * p.OWt;
+  p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
+  p.scale = scale; p.shift = shift;
+  const int b_region = p.b_resident ? p.K * p.K * p.b_bytes : p.b_slots * p.b_bytes;
+  p.off_b = 0;
+  p.off_a = up1024(b_region);
+  p.off_out = p.off_a + up1024(p.a_slots * p.slab_bytes);
+  p.off_res = p.off_out + up1024(p.stage_rows * 128);
+  p.off_bar = p.off_res + up1024(p.stage_rows * 128);
+  const size_t smem = (size_t)p.off_bar + (2 * p.a_slots + 2 * p.b_slots + 5) * 8 + 16 + 1024;
+  LT_REQUIRE(smem <= 227 * 1024, "conv_fold: shared memory budget exceeded (%zu)", smem);
+
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  {
+    const uint64_t rowb = 128;  // 32 channels split-fp16
+    const uint64_t dims[5] = {64, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N};
+    const uint64_t str[4] = {rowb, rowb * p.W, rowb * p.W * p.H, rowb * p.W * p.H * p.D};
+    const uint32_t bx[5] = {64, 16, (uint32_t)slab_lines, 1, 1};
+    int rc = make_map(&tmA, in, 5, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {64, (uint64_t)p.K * p.K * p.NF};
+    const uint64_t str[1] = {128};
+    const uint32_t bx[2] = {64, (uint32_t)p.NF};
+    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  {
+    const int f32 = d->out_format == LT_FMT_F32;
+    const uint64_t rowb = 128;
+    const uint64_t dims[5] = {(uint64_t)(f32 ? 32 : 64), (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N};
+    const uint64_t str[4] = {rowb, rowb * p.W, rowb * p.W * p.H, rowb * p.W * p.H * p.D};
+    const uint32_t bx[5] = {(uint32_t)(f32 ? 32 : 64), (uint32_t)p.OWt, 8, 1, 1};
+    int rc = make_map(&tmOut, out, 5, dims, str, bx, nullptr, 1, f32);
+    if (rc) return rc;
+    tmRes = tmOut;
+    if (d->residual != LT_RES_NONE) {
+      rc = make_map(&tmRes, residual, 5, dims, str, bx, nullptr, 1, f32);
+      if (rc) return rc;
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long grid = p.tiles < sm_count() ? p.tiles : sm_count();
+  conv_fold_kernel<<<(unsigned)grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, tmOut, tmRes, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold_kernel: %s", cudaGetErrorString(e));
+  return LT_OK;
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" size_t lt_conv_fold_weight_bytes(int K, int Cout) {
+  const int NC = (Cout + 15) & ~15;
+  return (size_t)K * K * K * NC * 64 * 2;
+}
+
+extern "C" int lt_conv_fold_pack_weights(const float* w_tap_ci_co, void* packed, int K, int Cout, void* stream) {
+  LT_REQUIRE(w_tap_ci_co && packed && (K == 3 || K == 7) && Cout > 0 && Cout <= 32, "conv_fold_pack_weights: bad arguments");
+  const int NC = (Cout + 15) & ~15;
+  const long total = (long)K * K * K * NC * 32;
+  long blocks = (total + 255) / 256;
+  if (blocks > 65535) blocks = 65535;
+  pack_fold_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_tap_ci_co, reinterpret_cast<sh_t*>(packed), K, Cout, NC);
+  LT_CHECK_LAUNCH("pack_fold_weights_kernel");
+  return LT_OK;
+}

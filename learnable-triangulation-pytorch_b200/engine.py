@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import capi
-from .capi import FMT_F32, FMT_S32, CONV_SIMT, CONV_TC, CONV_TC1, RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU
+from .capi import FMT_F32, FMT_S32, CONV_SIMT, CONV_TC, CONV_TC1, CONV_TC_FOLD, RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU
 
 
 def _round_up(v, m):
@@ -47,7 +47,7 @@ class Act:
 
 class ConvPack:
     """One (phase of a) convolution, ready to launch: packed filter + folded scale/shift + geometry."""
-    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs")
+    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs", "w_fold")
 
 
 def _fold_bn(conv_bias, bn, cout, device):
@@ -96,6 +96,7 @@ class NativeEngine:
         self._packs_version = None
         self._graphs = {}
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
+        self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
@@ -112,6 +113,7 @@ class NativeEngine:
         pk = ConvPack()
         pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
         pk.kmacs = taps * cin * cout   # algorithmic MACs per output position
+        pk.w_fold = None
         use_tc = (self.mode != "simt") and not force_simt and (max(stride) == 1 or self.tc_strided)
         scale, shift = _fold_bn(bias, bn, cout, dev)
         if use_tc:
@@ -122,6 +124,12 @@ class NativeEngine:
             packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
             capi.conv_tc_pack_weights(wp.contiguous(), packed, taps, cin_p, cout_p)
             pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = packed, cin_p, cout_p, self.tc_impl, FMT_S32
+            # narrow cubic stride-1 layers (V2V at full resolution): also pack for the kw-folded persistent kernel
+            if (self.use_fold and self.mode == "tc" and cin_p == 32 and cout <= 32 and k[0] == k[1] == k[2] and k[0] in (3, 7)
+                    and tuple(pad) == (k[0] // 2,) * 3 and max(stride) == 1):
+                wf = torch.empty(capi.conv_fold_weight_bytes(k[0], cout) // 2, dtype=torch.float16, device=dev)
+                capi.conv_fold_pack_weights(wp[:, :, :cout].contiguous(), wf, k[0], cout)
+                pk.w_fold = wf
         else:
             cout_p = _round_up(cout, 4)
             wp = torch.zeros((taps, cin, cout_p), dtype=torch.float32, device=dev)
@@ -260,9 +268,13 @@ class NativeEngine:
                           relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt)
         if residual is not None:
             assert residual.fmt == out.fmt and residual.C == out.C
+        impl, weight = pk.impl, pk.w
+        if (pk.w_fold is not None and x.W >= 16 and out.C == 32 and out_scale == (1, 1, 1) and (od, oh, ow) == (x.D, x.H, x.W)):
+            impl, weight = CONV_TC_FOLD, pk.w_fold
+            d.Cout = pk.cout
         with self._timed("conv_tc" if pk.impl != CONV_SIMT else "conv_ffma", flops=2.0 * x.N * od * oh * ow * pk.kmacs,
                          desc="N%d %dx%dx%d Cin%d Cout%d k%d%d%d s%d" % (x.N, od, oh, ow, pk.cin, pk.cout, kd, kh, kw, sw)):
-            capi.conv_nd(d, x.data, pk.w, pk.scale, pk.shift, None if residual is None else residual.data, out.data, pk.impl)
+            capi.conv_nd(d, x.data, weight, pk.scale, pk.shift, None if residual is None else residual.data, out.data, impl)
         self.launches += 1
         return out
 

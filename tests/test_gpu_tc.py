@@ -99,6 +99,51 @@ def test_conv_tc_stride2_vs_torch(case):
     assert err < TOL["tc"]
 
 
+FOLD_CASES = [
+    # (cin, cout, k, (D, H, W), batch)   -- Cin = 32 cubic stride-1 layers of the V2V net (v2v.py:146, :24-28)
+    (32, 32, 3, (8, 8, 16), 1),
+    (32, 32, 3, (9, 11, 18), 2),      # partial tiles in x (18 = 14 + 4) and y (11 = 8 + 3)
+    (16, 32, 3, (6, 16, 32), 1),      # 16 input channels stored 32 wide
+    (32, 16, 7, (8, 8, 16), 1),       # 7^3, weights streamed
+    (32, 16, 7, (7, 13, 25), 2),
+    (32, 32, 3, (32, 32, 32), 2),     # many tiles per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", FOLD_CASES)
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_fold_vs_torch(case, with_res):
+    cin, cout, k, spatial, N = case
+    torch.manual_seed(cin + cout + k + spatial[2])
+    conv = torch.nn.Conv3d(cin, cout, k, 1, k // 2, bias=True).eval()
+    bn = _bn_for(conv, 13)
+    x = torch.randn(N, cin, *spatial)
+    with torch.no_grad():
+        y0 = bn(conv(x))
+        res = torch.randn_like(y0)
+        want = F.relu(y0 + res) if with_res else F.relu(y0)
+    e = _engine("tc")
+    pk = e._pack_conv(conv.to(DEV), bn.to(DEV), cin_pad=32)
+    assert pk.w_fold is not None
+    xa = act_from_nchw(x, capi.FMT_S32, pad_c=32)
+    ra = act_from_nchw(res, capi.FMT_S32, pad_c=32) if with_res else None
+    launched = []
+    orig = capi.conv_nd
+    capi.conv_nd = lambda d, *a: (launched.append(a[-1]), orig(d, *a))[1]
+    try:
+        ya = e._conv(xa, pk, relu=True, residual=ra, res_mode=capi.RES_BEFORE_RELU if with_res else capi.RES_NONE)
+    finally:
+        capi.conv_nd = orig
+    torch.cuda.synchronize()
+    assert launched == [capi.CONV_TC_FOLD], "the kw-folded kernel must have been selected"
+    full = act_to_nchw(ya).cpu()
+    err = rel_err(full[:, :cout].numpy(), want.numpy())
+    print("conv_fold %s res=%s rel err %.2e" % (case, with_res, err))
+    assert err < TOL["tc"]
+    if cout < 32:
+        assert float(full[:, cout:].abs().max()) == 0.0
+
+
 def test_conv_tc_fp32_output_and_no_residual():
     torch.manual_seed(3)
     conv = torch.nn.Conv2d(256, 32, 1).eval()
