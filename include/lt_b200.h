@@ -162,6 +162,9 @@ int lt_maxpool_fwd(const void* in, void* out, int format, int N, int ID, int IH,
  * ---------------------------------------------------------------------------------------- */
 /* images [N][C][H][W] float32 -> [N][H][W][Cp] float32, channels >= C zero filled */
 int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, int Cp, void* stream);
+/* stem input packing: images [N][C<=8][H][W] float32 -> 2x2 space-to-depth split-fp16 [N][H/2][W/2][32],
+ * channel (r*2+s)*C + c = in[c][2y+r][2x+s]; turns the 7x7 stride-2 stem conv (pose_resnet.py:205) into a 4x4 stride-1 conv */
+int lt_stem_s2d_fwd(const float* in, void* out, int N, int C, int H, int W, void* stream);
 /* channels-last [P][C] float32 <-> split-fp16 (C % 32 == 0) */
 int lt_f32_to_s32(const float* in, void* out, long pixels, int C, void* stream);
 int lt_s32_to_f32(const void* in, float* out, long pixels, int C, void* stream);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
     "lt_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "lt_stem_s2d_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "lt_f32_to_s32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
     "lt_s32_to_f32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
     "lt_cl_to_cf_f32": (c_int, [c_void_p, c_void_p, c_int, c_long, c_int, c_int, c_void_p]),
@@ -172,6 +173,10 @@ def maxpool(inp, out, fmt, N, ID, IH, IW, C, k, s, p, OD, OH, OW):
 
 def nchw_to_nhwc(inp, out, N, C, H, W, Cp):
     _check(lib().lt_nchw_to_nhwc_f32(_ptr(inp), _ptr(out), N, C, H, W, Cp, _stream()), "lt_nchw_to_nhwc_f32")
+
+
+def stem_s2d(inp, out, N, C, H, W):
+    _check(lib().lt_stem_s2d_fwd(_ptr(inp), _ptr(out), N, C, H, W, _stream()), "lt_stem_s2d_fwd")
 
 
 def f32_to_s32(inp, out, pixels, C):

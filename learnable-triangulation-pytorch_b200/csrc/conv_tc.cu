@@ -376,9 +376,12 @@ static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* 
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                      TcParams& p, int n_tiles, cudaStream_t st) {
   const int stage_bytes = kATileBytes + p.Nt * 128;
-  int stages = (96 * 1024) / stage_bytes;   // aim at two resident CTAs per SM
+  const long ctas = (long)p.tw * p.th * p.td * p.tn * n_tiles;
+  // two resident CTAs per SM when the grid fills the chip; small grids (deep V2V levels) are latency-bound on the
+  // K loop instead, so give each CTA the whole shared memory as pipeline depth
+  int stages = ((ctas > (long)sm_count() ? 96 : 200) * 1024) / stage_bytes;
   if (stages < 2) stages = 2;
-  if (stages > 8) stages = 8;
+  if (stages > 10) stages = 10;
   p.stages = stages;
   const int acc_cols = (p.terms == 3 ? 2 : 1) * p.Nt;
   p.tmem_cols = pow2_ceil(acc_cols) < 32 ? 32 : pow2_ceil(acc_cols);

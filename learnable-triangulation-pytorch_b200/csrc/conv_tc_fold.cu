@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant
       const int n = (int)(t / p.D);
       const uint32_t as = it & 1u;
       if (leader && p.residual != LT_RES_NONE) {
+        bulk_wait_read<0>();                    // staging buffer is shared: the previous tile's store must have drained it
         mbar_expect_tx(res_full, stage_bytes);
         tma_load_5d(res_stage, &tmRes, res_full, 0, xw * p.OWt, yb * 8, z, n);
       }
@@ -340,8 +341,8 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.slab_bytes = 16 * slab_lines * 128;
   p.b_bytes = p.NF * 128;
   p.b_resident = (p.K * p.K * p.b_bytes <= 112 * 1024) ? 1 : 0;
-  p.b_slots = p.b_resident ? 1 : 4;
-  p.a_slots = 3;
+  p.b_slots = p.b_resident ? 1 : 8;     // streamed weights: 8 x 14 KB in flight hide the L2 latency of a (kd,kh) step
+  p.a_slots = p.b_resident ? 5 : 3;     // slabs in flight
   p.stage_rows = 8 * p.OWt;
   p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
   p.scale = scale; p.shift = shift;
@@ -349,8 +350,8 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.off_b = 0;
   p.off_a = up1024(b_region);
   p.off_out = p.off_a + up1024(p.a_slots * p.slab_bytes);
-  p.off_res = p.off_out + up1024(p.stage_rows * 128);
-  p.off_bar = p.off_res + up1024(p.stage_rows * 128);
+  p.off_res = p.off_out;   // residual tile and output tile share one staging buffer (read -> barrier -> overwrite)
+  p.off_bar = p.off_out + up1024(p.stage_rows * 128);
   const size_t smem = (size_t)p.off_bar + (2 * p.a_slots + 2 * p.b_slots + 5) * 8 + 16 + 1024;
   LT_REQUIRE(smem <= 227 * 1024, "conv_fold: shared memory budget exceeded (%zu)", smem);
 

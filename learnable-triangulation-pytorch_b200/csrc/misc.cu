@@ -87,6 +87,33 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+// Stem input packing: images [N][3][H][W] fp32 -> 2x2 space-to-depth, channels-last split-fp16 [N][H/2][W/2][32]
+// with channel (r*2 + s)*3 + c = in[c][2y + r][2x + s] (12 used, 20 zero), so that the 7x7 stride-2 stem conv
+// (pose_resnet.py:205) becomes a 4x4 stride-1 conv with 32 input channels on the tensor-core kernel.
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ in, sh_t* __restrict__ out, int N, int C, int H, int W) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long total = (long)N * H2 * W2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W2);
+    const int y = (int)((i / W2) % H2);
+    const long n = i / ((long)W2 * H2);
+    sh_t hi[32], lo[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { hi[k] = __float2half_rn(0.f); lo[k] = hi[k]; }
+    for (int r = 0; r < 2; ++r)
+      for (int s = 0; s < 2; ++s)
+        for (int c = 0; c < C; ++c) {
+          const float v = __ldg(in + ((n * C + c) * H + (2 * y + r)) * W + (2 * x + s));
+          split_s32(v, hi[(r * 2 + s) * C + c], lo[(r * 2 + s) * C + c]);
+        }
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 64);
+    const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+    const uint4* l4 = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dst[k] = h4[k]; dst[4 + k] = l4[k]; }
+  }
+}
+
 __global__ void __launch_bounds__(256) f32_to_s32_kernel(const float* __restrict__ in, sh_t* __restrict__ out, long pixels, int C) {
   const int c4n = C / 4;
   const long total = pixels * c4n;
@@ -163,6 +190,13 @@ extern "C" int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, in
   LT_REQUIRE(in && out && Cp >= C, "nchw_to_nhwc: bad arguments");
   nchw_to_nhwc_kernel<<<grid_for((long)N * H * W), 256, 0, (cudaStream_t)stream>>>(in, out, N, C, H, W, Cp);
   LT_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_stem_s2d_fwd(const float* in, void* out, int N, int C, int H, int W, void* stream) {
+  LT_REQUIRE(in && out && C * 4 <= 32 && H % 2 == 0 && W % 2 == 0, "stem_s2d: need C <= 8 and even H, W");
+  stem_s2d_kernel<<<grid_for((long)N * (H / 2) * (W / 2)), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<sh_t*>(out), N, C, H, W);
+  LT_CHECK_LAUNCH("stem_s2d_kernel");
   return LT_OK;
 }
 

@@ -97,6 +97,7 @@ class NativeEngine:
         self._graphs = {}
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
         self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
+        self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
@@ -159,6 +160,28 @@ class NativeEngine:
         pk.kmacs = pk.taps * w.shape[1] * w.shape[0]
         return pk
 
+    def _pack_stem_s2d(self, conv, bn):
+        """7x7 stride-2 pad-3 conv == 4x4 stride-1 conv (front pad 2) over the 2x2 space-to-depth input.
+
+        Input row 2*oy - 3 + ky = 2*(oy + a) + r with a = tap offset in {-2..1}, r = row parity:
+        ky = 2a + r + 3 (taps with ky outside [0, 7) get zero weights).  Channel order (r*2 + s)*3 + c.
+        """
+        w = conv.weight.detach().float()          # (64, 3, 7, 7)
+        assert tuple(w.shape[1:]) == (3, 7, 7) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (3, 3)
+        cout = w.shape[0]
+        wt = torch.zeros((4, 4, 32, cout), dtype=torch.float32, device=w.device)
+        for ai, a in enumerate(range(-2, 2)):
+            for bi, b in enumerate(range(-2, 2)):
+                for r in (0, 1):
+                    for s in (0, 1):
+                        ky, kx = 2 * a + r + 3, 2 * b + s + 3
+                        if 0 <= ky < 7 and 0 <= kx < 7:
+                            c0 = (r * 2 + s) * 3
+                            wt[ai, bi, c0:c0 + 3] = w[:, :, ky, kx].t()
+        pk = self._pack(wt.reshape(16, 32, cout).contiguous(), conv.bias, bn, (1, 4, 4), (1, 1, 1), (0, 2, 2))
+        pk.kmacs = 49 * 3 * cout
+        return pk
+
     def _pack_deconv2d_k4s2(self, deconv, bn):
         """ConvTranspose2d(k=4, s=2, p=1) as four 2x2 stride-1 convs, one per output parity.
 
@@ -193,8 +216,12 @@ class NativeEngine:
         m = self.model
         bb, P = m.backbone, {}
         with torch.no_grad():
-            # stem: 3 input channels padded to 4 (float4 per pixel), always on the FFMA kernel
-            P["stem"] = self._pack_conv(bb.conv1, bb.bn1, cin_pad=4, force_simt=True)
+            # stem: exact-fp32 mode pads 3 -> 4 channels (float4 per pixel) for the FFMA kernel; the tensor-core modes
+            # rewrite the 7x7 stride-2 conv as a 4x4 stride-1 conv over the 2x2 space-to-depth image (12 -> 32 channels)
+            if self.mode == "simt" or not self.tc_stem:
+                P["stem"] = self._pack_conv(bb.conv1, bb.bn1, cin_pad=4, force_simt=True)
+            else:
+                P["stem_s2d"] = self._pack_stem_s2d(bb.conv1, bb.bn1)
             for li in range(1, 5):
                 for ui, unit in enumerate(getattr(bb, "layer%d" % li)):
                     key = "layer%d.%d" % (li, ui)
@@ -322,10 +349,16 @@ class NativeEngine:
         P = self._packs
         bv, c, H, W = images_nchw.shape
         dev = images_nchw.device
-        x = Act(bv, 1, H, W, 4, FMT_F32, dev)
-        capi.nchw_to_nhwc(images_nchw, x.data, bv, c, H, W, 4)
-        self.launches += 1
-        x = self._conv(x, P["stem"], relu=True)
+        if "stem_s2d" in P:
+            x = Act(bv, 1, H // 2, W // 2, 32, FMT_S32, dev)
+            capi.stem_s2d(images_nchw, x.data, bv, c, H, W)
+            self.launches += 1
+            x = self._conv(x, P["stem_s2d"], relu=True, out_dims=(1, H // 2, W // 2))
+        else:
+            x = Act(bv, 1, H, W, 4, FMT_F32, dev)
+            capi.nchw_to_nhwc(images_nchw, x.data, bv, c, H, W, 4)
+            self.launches += 1
+            x = self._conv(x, P["stem"], relu=True)
         x = self._maxpool(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
         bb = self.model.backbone
         for li in range(1, 5):

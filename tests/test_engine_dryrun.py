@@ -18,7 +18,7 @@ class Recorder:
                 self.calls.append((name, a))
             return f
         monkeypatch.setattr(capi, "conv_fold_weight_bytes", lambda k, co: k * k * k * ((co + 15) // 16 * 16) * 64 * 2)
-        for name in ("conv_fold_pack_weights", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
+        for name in ("conv_fold_pack_weights", "stem_s2d", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
                      "s32_to_f32", "cl_to_cf", "conv_tc_pack_weights"):
             monkeypatch.setattr(capi, name, rec(name))
         monkeypatch.setattr(capi, "lib", lambda: None)
@@ -80,4 +80,4 @@ def test_engine_plan_is_consistent(monkeypatch, mode, layers):
     assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights")) + 2   # softargmax = 3 launches
     if mode == "tc":
         simt = [c for c in convs if c[1][0] == capi.CONV_SIMT]
-        assert len(simt) == 1, "only the 3-channel stem stays on the FFMA kernel"
+        assert len(simt) == 0, "every conv runs on the tensor-core kernels"

@@ -99,6 +99,26 @@ def test_conv_tc_stride2_vs_torch(case):
     assert err < TOL["tc"]
 
 
+def test_stem_space_to_depth_vs_torch():
+    """7x7 stride-2 stem (pose_resnet.py:205-208) as a 4x4 conv over the space-to-depth image, on the tensor cores."""
+    torch.manual_seed(5)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).eval()
+    bn = _bn_for(conv, 4)
+    x = torch.randn(3, 3, 64, 96)
+    with torch.no_grad():
+        want = F.relu(bn(conv(x)))
+    e = _engine("tc")
+    pk = e._pack_stem_s2d(conv.to(DEV), bn.to(DEV))
+    from lt_b200.engine import Act
+    xa = Act(3, 1, 32, 48, 32, capi.FMT_S32, DEV)
+    capi.stem_s2d(x.to(DEV).contiguous(), xa.data, 3, 3, 64, 96)
+    ya = e._conv(xa, pk, relu=True, out_dims=(1, 32, 48))
+    torch.cuda.synchronize()
+    err = rel_err(act_to_nchw(ya, 64).squeeze(2).cpu().numpy(), want.numpy())
+    print("stem s2d rel err %.2e" % err)
+    assert err < TOL["tc"]
+
+
 FOLD_CASES = [
     # (cin, cout, k, (D, H, W), batch)   -- Cin = 32 cubic stride-1 layers of the V2V net (v2v.py:146, :24-28)
     (32, 32, 3, (8, 8, 16), 1),
