@@ -142,7 +142,8 @@ int lt_conv_nd_fwd(const lt_conv_desc* desc, const void* in, const void* weight,
                    const float* shift, const void* residual, void* out, int impl, void* stream);
 
 /* Tensor-core (tcgen05) weight packing: float32 [taps][Cin][Cout] (host or device? -> DEVICE)
- * to split-fp16 [taps][Cin/32][CoutP][64], CoutP = round_up(Cout, 16); Cin % 32 == 0. */
+ * to fp16 [taps][Cin/32][n tile][hi|lo][Nt][32] (64-byte rows; Nt = min(CoutP, 128), CoutP = round_up(Cout, 16));
+ * Cin % 32 == 0. */
 size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout);
 int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
 

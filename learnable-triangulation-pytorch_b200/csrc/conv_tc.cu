@@ -13,8 +13,8 @@
 // (3 MMAs; the epilogue forms D1 + D2/2048: ~22 significand bits per operand, dropped lo*lo term
 // 2^-22 relative -- fp32-grade results from the fp16 pipe), or hi*hi only (LT_CONV_TC1, fast mode).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue (one TMEM lane quadrant each).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = epilogue (two warps per TMEM lane quadrant, each converting 16 of a block's 32 channels).
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -31,7 +31,8 @@ struct TcParams {
   int KW, KH, KD, pw, ph, pd;
   int sw, sh, sd;          // input stride (TMA element strides)
   int CB;                  // 64-element K chunks per tap
-  int b_step0, b_step1;    // B-map coordinates of chunk q: (q*b_step0, q*b_step1 + n0)
+  int b_step0, b_step1;    // B-map coordinates of chunk q: (q*b_step0, q*b_step1 + n0*b_nmul)
+  int b_nmul;
   int Nt, stages, terms;   // N tile, pipeline depth, 1 or 3 product terms
   int tmem_cols;
   int tma_epi;             // 1: epilogue stages 32-channel blocks through smem and uses TMA store / residual load
@@ -45,7 +46,7 @@ struct TcParams {
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
 
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
                                                       const __grid_constant__ CUtensorMap tmOut,
                                                       const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   uint64_t* res_full = tmem_full + 1;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
   // tile coordinates
   int t = blockIdx.x;
@@ -86,78 +87,75 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      for (int q = 0; q < nchunks; ++q) {
-        const int s = q % p.stages;
-        const uint32_t ph = (uint32_t)((q / p.stages) & 1);
-        mbar_wait(&empty[s], ph ^ 1u);
-        const int tap = q / p.CB, cb = q % p.CB;
-        const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
-        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + kATileBytes;
+    // ================= TMA producer (whole warp runs the loop; one elected lane issues) =================
+    for (int q = 0; q < nchunks; ++q) {
+      const int s = q % p.stages;
+      const uint32_t ph = (uint32_t)((q / p.stages) & 1);
+      mbar_wait(&empty[s], ph ^ 1u);
+      const int tap = q / p.CB, cb = q % p.CB;
+      const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+      uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+      uint8_t* b_dst = a_dst + kATileBytes;
+      if (elect_one()) {
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
         tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 * p.sw - p.pw + kw, oh0 * p.sh - p.ph + kh, od0 * p.sd - p.pd + kd, nb0);
-        tma_load_2d(b_dst, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0);
+        tma_load_2d(b_dst, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0 * p.b_nmul);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.Nt);
-      uint32_t accumulate = 0, accumulate2 = 0;
-      const uint32_t tmem_d2 = tmem_base + (uint32_t)p.Nt;   // second accumulator: cross terms (scaled by 2^11)
-      for (int q = 0; q < nchunks; ++q) {
-        const int s = q % p.stages;
-        const uint32_t ph = (uint32_t)((q / p.stages) & 1);
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + kATileBytes;
-        const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw128_desc(b_addr);
+    // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+    const uint32_t idesc = make_idesc_f16(p.Nt), idesc2 = make_idesc_f16(2 * p.Nt);
+    const uint32_t tmem_d2 = tmem_base + (uint32_t)p.Nt;   // second accumulator: cross terms (scaled by 2^11)
+    for (int q = 0; q < nchunks; ++q) {
+      const int s = q % p.stages;
+      const uint32_t ph = (uint32_t)((q / p.stages) & 1);
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t b_addr = a_addr + kATileBytes;
+      const uint64_t ad = make_sw128_desc(a_addr);
+      const uint64_t bd = (p.terms == 0) ? make_sw128_desc(b_addr) : make_sw64_desc(b_addr);
+      const uint32_t first = (q == 0) ? 0u : 1u;
+      if (elect_one()) {
         if (p.terms == 3) {
-          // row = [32 hi | 32 lo] fp16: hi slices at +0,+32 B, lo slices at +64,+96 B (>>4 units: 2 per 32 B)
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            const uint64_t ah = ad + (uint64_t)(sl * 2), al = ad + (uint64_t)(4 + sl * 2);
-            const uint64_t bh = bd + (uint64_t)(sl * 2), bl = bd + (uint64_t)(4 + sl * 2);
-            umma_f16(tmem_base, ah, bh, idesc, accumulate);
-            accumulate = 1;
-            umma_f16(tmem_d2, ah, bl, idesc, accumulate2);
-            accumulate2 = 1;
-            umma_f16(tmem_d2, al, bh, idesc, 1);
-          }
+          // A row = [32 hi | 32 lo] fp16: hi slices at +0,+32 B, lo slices at +64,+96 B (descriptor units of 16 B).
+          // B tile = [Nt hi rows ; Nt lo rows] x 64 B (64B swizzle): one N = 2*Nt MMA per slice forms hi*hi -> D1 and
+          // hi*lo -> D2 from a single pass over A_hi; the lo*hi term is a second N = Nt MMA into D2.
+          umma_f16(tmem_base, ad, bd, idesc2, first);
+          umma_f16(tmem_d2, ad + 4, bd, idesc, 1);
+          umma_f16(tmem_base, ad + 2, bd + 2, idesc2, 1);
+          umma_f16(tmem_d2, ad + 6, bd + 2, idesc, 1);
         } else if (p.terms == 1) {
-          // split storage, high parts only
-#pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            umma_f16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
-            accumulate = 1;
-          }
+          // high parts only: A_hi x B_hi rows
+          umma_f16(tmem_base, ad, bd, idesc, first);
+          umma_f16(tmem_base, ad + 2, bd + 2, idesc, 1);
         } else {
           // plain fp16 rows (self test): 4 slices of 16
-#pragma unroll
-          for (int sl = 0; sl < 4; ++sl) {
-            umma_f16(tmem_base, ad + (uint64_t)(sl * 2), bd + (uint64_t)(sl * 2), idesc, accumulate);
-            accumulate = 1;
-          }
+          umma_f16(tmem_base, ad, bd, idesc, first);
+          umma_f16(tmem_base, ad + 2, bd + 2, idesc, 1);
+          umma_f16(tmem_base, ad + 4, bd + 4, idesc, 1);
+          umma_f16(tmem_base, ad + 6, bd + 6, idesc, 1);
         }
-        umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        umma_commit(&empty[s]);                       // frees the smem slot once these MMAs have read it
+        if (q == nchunks - 1) umma_commit(tmem_full); // accumulator complete
       }
-      umma_commit(tmem_full);    // accumulator complete
+      __syncwarp();
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9: two per TMEM lane quadrant, 16 channels of each block each) =================
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;        // which 16 channels of every 32-channel block
     const int row = quad * 32 + lane;
-    int r = row;
-    const int dw = r % p.bw; r /= p.bw;
-    const int dh = r % p.bh; r /= p.bh;
-    const int dd = r % p.bd; r /= p.bd;
-    const int dn = r;
+    int r_ = row;
+    const int dw = r_ % p.bw; r_ /= p.bw;
+    const int dh = r_ % p.bh; r_ /= p.bh;
+    const int dd = r_ % p.bd; r_ /= p.bd;
+    const int dn = r_;
     const int ow = ow0 + dw, oh = oh0 + dh, od = od0 + dd, nb = nb0 + dn;
     const bool valid = ow < p.OW && oh < p.OH && od < p.OD && nb < p.N;
     const long opix = (((long)nb * p.FD + (od * p.osd + p.ood)) * p.FH + (oh * p.osh + p.ooh)) * p.FW + (ow * p.osw + p.oow);
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -178,83 +176,25 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       }
       for (int i = 0; i < nblk; ++i) {
         const int buf = i & 1;
-        float v[32];
+        float v[16], r[16];
         {
-          uint32_t t[16];
+          uint32_t t1[16], t2[16];
+          tmem_ld16_nowait(tlane + (uint32_t)(i * 32 + half * 16), t1);
+          if (p.terms == 3) tmem_ld16_nowait(tlane + (uint32_t)(p.Nt + i * 32 + half * 16), t2);
+          tmem_wait_ld();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(i * 32 + h * 16), t);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[h * 16 + j] = __uint_as_float(t[j]);
-            if (p.terms == 3) {
-              tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.Nt + i * 32 + h * 16), t);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[h * 16 + j] = fmaf(__uint_as_float(t[j]), kLoInv, v[h * 16 + j]);
-            }
-          }
+          for (int j = 0; j < 16; ++j)
+            v[j] = (p.terms == 3) ? fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j])) : __uint_as_float(t1[j]);
         }
-        const int co = n0 + i * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co + j));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + co + j));
-          v[j] = fmaf(v[j], sc.x, sh.x); v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
-          v[j + 2] = fmaf(v[j + 2], sc.z, sh.z); v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
-        }
-        float r[32];
+        epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
         if (p.residual != LT_RES_NONE) {
           mbar_wait(&res_full[buf], (uint32_t)((i >> 1) & 1));
-          const uint32_t rb = smem_u32(res_stage + buf * 16384);
-          if (p.out_format == LT_FMT_F32) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 q = lds128(rb + sw128_off(row, c));
-              r[c * 4] = __uint_as_float(q.x); r[c * 4 + 1] = __uint_as_float(q.y);
-              r[c * 4 + 2] = __uint_as_float(q.z); r[c * 4 + 3] = __uint_as_float(q.w);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 qh = lds128(rb + sw128_off(row, c)), ql = lds128(rb + sw128_off(row, c + 4));
-              const sh_t* hh = reinterpret_cast<const sh_t*>(&qh);
-              const sh_t* ll = reinterpret_cast<const sh_t*>(&ql);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) r[c * 8 + e] = join_s32(hh[e], ll[e]);
-            }
-          }
+          epi_load16(smem_u32(res_stage + buf * 16384), row, half, p.out_format, r);
         }
-        if (p.residual == LT_RES_BEFORE_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.residual == LT_RES_AFTER_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
-        }
+        epi_activate16(v, r, p.residual, p.relu);
         if (leader) bulk_wait_read<1>();      // the store that last read out_stage[buf] (block i-2) is done with it
         epi_bar_sync();
-        const uint32_t ob = smem_u32(out_stage + buf * 16384);
-        if (p.out_format == LT_FMT_F32) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts128(ob + sw128_off(row, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
-                                                       __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 qh, ql;
-            sh_t* hh = reinterpret_cast<sh_t*>(&qh);
-            sh_t* ll = reinterpret_cast<sh_t*>(&ql);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split_s32(v[c * 8 + e], hh[e], ll[e]);
-            sts128(ob + sw128_off(row, c), qh);
-            sts128(ob + sw128_off(row, c + 4), ql);
-          }
-        }
+        epi_store16(smem_u32(out_stage + buf * 16384), row, half, p.out_format, v);
         fence_proxy_async();
         epi_bar_sync();
         if (leader) {
@@ -268,12 +208,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       }
       if (leader) bulk_wait<0>();
     } else
-    for (int c0 = 0; c0 < p.Nt; c0 += 16) {
+    for (int c0 = half * 16; c0 < p.Nt; c0 += 32) {
       uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);   // whole warp (sync.aligned)
+      tmem_ld16(tlane + (uint32_t)c0, v);   // whole warp (sync.aligned)
       if (p.terms == 3) {
         uint32_t v2[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.Nt + c0), v2);
+        tmem_ld16(tlane + (uint32_t)(p.Nt + c0), v2);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v2[j]), kLoInv, __uint_as_float(v[j])));
       }
@@ -337,7 +277,8 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estrides ? estrides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return LT_OK;
@@ -395,7 +336,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   const long m_tiles = (long)p.tw * p.th * p.td * p.tn;
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
-  conv_tc_kernel<<<grid, 192, smem, st>>>(tmA, tmB, tmOut, tmRes, p);
+  conv_tc_kernel<<<grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_kernel: %s", cudaGetErrorString(e));
   return LT_OK;
@@ -420,7 +361,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
   p.tw = ceil_div(d->OW, p.bw); p.th = ceil_div(d->OH, p.bh); p.td = ceil_div(d->OD, p.bd); p.tn = ceil_div(d->N, p.bn);
   p.KW = d->KW; p.KH = d->KH; p.KD = d->KD; p.pw = d->pw; p.ph = d->ph; p.pd = d->pd;
   p.sw = d->sw; p.sh = d->sh; p.sd = d->sd;
-  p.CB = CB; p.b_step0 = 0; p.b_step1 = CoutP; p.Nt = Nt; p.terms = terms;
+  p.CB = CB; p.b_step0 = 0; p.b_step1 = 2 * CoutP; p.b_nmul = 2; p.Nt = Nt; p.terms = terms;
   p.FC = d->FC; p.FD = d->FD; p.FH = d->FH; p.FW = d->FW;
   p.osd = d->osd; p.osh = d->osh; p.osw = d->osw; p.ood = d->ood; p.ooh = d->ooh; p.oow = d->oow;
   p.relu = d->relu; p.residual = d->residual; p.out_format = d->out_format;
@@ -442,10 +383,11 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {64, (uint64_t)taps * CB * CoutP};
-    const uint64_t str[1] = {128};
-    const uint32_t bx[2] = {64, (uint32_t)Nt};
-    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
+    // weights: [tap][cb][n tile][hi|lo][Nt rows][32 channels] fp16, 64-byte rows, 64B swizzle
+    const uint64_t dims[2] = {32, (uint64_t)taps * CB * 2 * CoutP};
+    const uint64_t str[1] = {64};
+    const uint32_t bx[2] = {32, (uint32_t)(2 * Nt)};
+    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 2);
     if (rc) return rc;
   }
   CUtensorMap tmOut = tmA, tmRes = tmA;
@@ -467,9 +409,9 @@ int conv_tc_fwd(const lt_conv_desc* d, const void* in, const void* weight, const
   return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 3, stream);
 }
 
-// ---- weight packing: fp32 [taps][Cin][Cout] -> split-fp16 [taps][Cin/32][CoutP][64] ----------------
+// ---- weight packing: fp32 [taps][Cin][Cout] -> fp16 [taps][Cin/32][n tile][hi|lo][Nt][32] (64-byte rows) ----------
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, sh_t* __restrict__ out,
-                                                           int taps, int Cin, int Cout, int CoutP) {
+                                                           int taps, int Cin, int Cout, int CoutP, int Nt) {
   const int CB = Cin / 32;
   const long total = (long)taps * CB * CoutP * 32;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -481,9 +423,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     const float v = (n < Cout) ? w[((long)tap * Cin + cb * 32 + j) * Cout + n] : 0.0f;
     sh_t hi, lo;
     split_s32(v, hi, lo);
-    sh_t* row = out + (((long)tap * CB + cb) * CoutP + n) * 64;
-    row[j] = hi;
-    row[32 + j] = lo;
+    const int nt = n / Nt, ni = n % Nt;
+    sh_t* tile = out + ((((long)tap * CB + cb) * (CoutP / Nt) + nt) * 2) * (long)Nt * 32;
+    tile[(long)ni * 32 + j] = hi;
+    tile[((long)Nt + ni) * 32 + j] = lo;
   }
 }
 
@@ -508,7 +451,9 @@ extern "C" int lt_conv_tc_pack_weights(const float* w, void* packed, int taps, i
   const long total = (long)taps * (Cin / 32) * CoutP * 32;
   long blocks = (total + 255) / 256;
   if (blocks > 65535) blocks = 65535;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<sh_t*>(packed), taps, Cin, Cout, CoutP);
+  const int Nt = CoutP <= 128 ? CoutP : 128;
+  LT_REQUIRE(CoutP % Nt == 0, "conv_tc_pack_weights: Cout not tileable");
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<sh_t*>(packed), taps, Cin, Cout, CoutP, Nt);
   LT_CHECK_LAUNCH("pack_weights_kernel");
   return LT_OK;
 }
@@ -530,7 +475,7 @@ extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M
   p.bw = 128; p.bh = 1; p.bd = 1; p.bn = 1;
   p.tw = ceil_div(M, 128); p.th = 1; p.td = 1; p.tn = 1;
   p.KW = p.KH = p.KD = 1; p.pw = p.ph = p.pd = 0; p.sw = p.sh = p.sd = 1;
-  p.CB = K / 64; p.b_step0 = 64; p.b_step1 = 0; p.Nt = Nt; p.terms = 0;
+  p.CB = K / 64; p.b_step0 = 64; p.b_step1 = 0; p.b_nmul = 1; p.Nt = Nt; p.terms = 0;
   p.FC = N; p.FD = 1; p.FH = 1; p.FW = M; p.osd = p.osh = p.osw = 1; p.ood = p.ooh = p.oow = 0;
   p.relu = 0; p.residual = LT_RES_NONE; p.out_format = LT_FMT_F32;
   p.scale = ones; p.shift = zeros; p.res = nullptr; p.out = d;

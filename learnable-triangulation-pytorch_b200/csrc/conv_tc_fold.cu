@@ -12,6 +12,12 @@
 // the 3^3 weights (108 KB) stay resident in shared memory for the whole persistent CTA.  Each M tile yields
 // 16-K+1 output positions per line (14 for K=3, 10 for K=7).
 //
+// Products: activations are split-fp16 rows [32 hi | 32 lo]; the weights of a (kd,kh) step are stored as a
+// 2*NF-row, 64-byte-swizzled tile  [hi rows (kw,co) ; lo rows (kw,co)] x 32 channels, so that per 16-wide K slice
+//     MMA1: A_hi x [B_hi ; B_lo]  (N = 2*NF)  -> [D1 | D2]     (hi*hi and hi*lo in one pass over A_hi)
+//     MMA2: A_lo x  B_hi          (N =   NF)  ->       D2
+// i.e. two MMAs instead of three (a single-CTA SS-mode UMMA costs ~(128 + N)/2 cycles of operand fetch).
+//
 // Persistent CTAs (one per SM), warp roles as in conv_tc.cu; TMEM holds two accumulator stages of 2*NF columns
 // (hi*hi and the 2^11-scaled cross terms) so the epilogue of tile i overlaps the MMAs of tile i+1; the epilogue
 // shift-adds with warp shuffles, applies scale/shift/residual/ReLU, compacts the valid rows into a 128B-swizzled
@@ -36,13 +42,22 @@ struct FoldParams {
   const float* shift;
   // smem offsets (bytes from the 1024-aligned base)
   int off_b, off_a, off_out, off_res, off_bar;
+  unsigned long long* prof;   // optional [16] cycle counters (LT_FOLD_PROF=1): time spent waiting per role / barrier
+  int dbg;               // bring-up knobs (LT_FOLD_DBG): 1 = hi*hi MMAs only, 2 = skip epilogue math/stores, 3 = load slabs once
 };
+
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmOut,
                                                            const __grid_constant__ CUtensorMap tmRes, const FoldParams p) {
@@ -62,13 +77,13 @@ __global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant
   uint64_t* res_full = acc_empty + 2;        // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int taps2 = p.K * p.K;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads); }
     mbar_init(res_full, 1);
     fence_barrier_init();
   }
@@ -80,98 +95,118 @@ __global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      if (p.b_resident) {
+    // ================= TMA producer (whole warp runs the loops; one elected lane issues) =================
+    if (p.b_resident) {
+      if (elect_one()) {
         mbar_expect_tx(&b_full[0], (uint32_t)(taps2 * p.b_bytes));
-        for (int t = 0; t < taps2; ++t) tma_load_2d(b_smem + (size_t)t * p.b_bytes, &tmB, &b_full[0], 0, t * p.NF);
+        for (int t = 0; t < taps2; ++t) tma_load_2d(b_smem + (size_t)t * p.b_bytes, &tmB, &b_full[0], 0, t * 2 * p.NF);
       }
-      uint32_t pa = 0, pb = 0;
-      for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        long t = tile;
-        const int xw = (int)(t % p.xwins); t /= p.xwins;
-        const int yb = (int)(t % p.yblks); t /= p.yblks;
-        const int z = (int)(t % p.D);
-        const int n = (int)(t / p.D);
-        for (int kd = 0; kd < p.K; ++kd) {
-          const uint32_t slot = pa % p.a_slots;
-          mbar_wait(&a_empty[slot], ((pa / p.a_slots) & 1u) ^ 1u);
-          mbar_expect_tx(&a_full[slot], (uint32_t)p.slab_bytes);
-          tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.pad, yb * 8 - p.pad,
-                      z + kd - p.pad, n);
-          ++pa;
-          if (!p.b_resident) {
-            for (int kh = 0; kh < p.K; ++kh) {
-              const uint32_t bs = pb % p.b_slots;
-              mbar_wait(&b_empty[bs], ((pb / p.b_slots) & 1u) ^ 1u);
-              mbar_expect_tx(&b_full[bs], (uint32_t)p.b_bytes);
-              tma_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, &b_full[bs], 0, (kd * p.K + kh) * p.NF);
-              ++pb;
-            }
+      __syncwarp();
+    }
+    uint32_t pa = 0, pb = 0;
+    const bool prof = p.prof != nullptr;
+    unsigned long long w_ae = 0, w_be = 0;
+    const long long tstart = clock64();
+    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+      long t = tile;
+      const int xw = (int)(t % p.xwins); t /= p.xwins;
+      const int yb = (int)(t % p.yblks); t /= p.yblks;
+      const int z = (int)(t % p.D);
+      const int n = (int)(t / p.D);
+      for (int kd = 0; kd < p.K; ++kd) {
+        const uint32_t slot = pa % p.a_slots;
+        mbar_wait_prof(&a_empty[slot], ((pa / p.a_slots) & 1u) ^ 1u, w_ae, prof);
+        if (elect_one()) {
+          if (p.dbg == 3 && pa >= (uint32_t)p.a_slots) {
+            mbar_arrive(&a_full[slot]);          // debug: reuse stale slab contents, no TMA traffic
+          } else {
+            mbar_expect_tx(&a_full[slot], (uint32_t)p.slab_bytes);
+            tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.pad, yb * 8 - p.pad,
+                        z + kd - p.pad, n);
           }
         }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.NF);
-      if (p.b_resident) { mbar_wait(&b_full[0], 0); }
-      uint32_t pa = 0, pb = 0, it = 0;
-      for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it & 1u;
-        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d1 = tmem_base + as * 2u * (uint32_t)p.NF;
-        const uint32_t d2 = d1 + (uint32_t)p.NF;
-        uint32_t acc1 = 0, acc2 = 0;
-        for (int kd = 0; kd < p.K; ++kd) {
-          const uint32_t slot = pa % p.a_slots;
-          mbar_wait(&a_full[slot], (pa / p.a_slots) & 1u);
-          tc_fence_after();
-          const uint32_t slab = smem_u32(a_smem + (size_t)slot * p.slab_bytes);
+        __syncwarp();
+        ++pa;
+        if (!p.b_resident) {
           for (int kh = 0; kh < p.K; ++kh) {
-            uint32_t b_addr;
-            uint32_t bs = 0;
-            if (p.b_resident) {
-              b_addr = smem_u32(b_smem + (size_t)(kd * p.K + kh) * p.b_bytes);
-            } else {
-              bs = pb % p.b_slots;
-              mbar_wait(&b_full[bs], (pb / p.b_slots) & 1u);
-              tc_fence_after();
-              b_addr = smem_u32(b_smem + (size_t)bs * p.b_bytes);
+            const uint32_t bs = pb % p.b_slots;
+            mbar_wait_prof(&b_empty[bs], ((pb / p.b_slots) & 1u) ^ 1u, w_be, prof);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[bs], (uint32_t)p.b_bytes);
+              tma_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, &b_full[bs], 0, (kd * p.K + kh) * 2 * p.NF);
             }
-            const uint64_t ad = make_sw128_desc(slab + (uint32_t)kh * 2048u);   // line kh of the slab: 16 rows x 128 B
-            const uint64_t bd = make_sw128_desc(b_addr);
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-              const uint64_t ah = ad + (uint64_t)(sl * 2), al = ad + (uint64_t)(4 + sl * 2);
-              const uint64_t bh = bd + (uint64_t)(sl * 2), bl = bd + (uint64_t)(4 + sl * 2);
-              umma_f16(d1, ah, bh, idesc, acc1);
-              acc1 = 1;
-              umma_f16(d2, ah, bl, idesc, acc2);
-              acc2 = 1;
-              umma_f16(d2, al, bh, idesc, 1);
-            }
-            if (!p.b_resident) { umma_commit(&b_empty[bs]); ++pb; }
+            __syncwarp();
+            ++pb;
           }
-          umma_commit(&a_empty[slot]);
-          ++pa;
         }
-        umma_commit(&acc_full[as]);
       }
     }
+    if (prof && lane == 0) { atomicAdd(&p.prof[0], w_ae); atomicAdd(&p.prof[1], w_be); atomicAdd(&p.prof[2], (unsigned long long)(clock64() - tstart)); }
+  } else if (warp == 1) {
+    // ================= MMA issuer (whole warp runs the loops; one elected lane issues) =================
+    const uint32_t idesc = make_idesc_f16(p.NF), idesc2 = make_idesc_f16(2 * p.NF);
+    if (p.b_resident) { mbar_wait(&b_full[0], 0); }
+    uint32_t pa = 0, pb = 0, it = 0;
+    const bool prof = p.prof != nullptr;
+    unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
+    const long long tstart = clock64();
+    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1u;
+      mbar_wait_prof(&acc_empty[as], ((it >> 1) & 1u) ^ 1u, w_acc, prof);
+      tc_fence_after();
+      const uint32_t d1 = tmem_base + as * 2u * (uint32_t)p.NF;
+      const uint32_t d2 = d1 + (uint32_t)p.NF;
+      for (int kd = 0; kd < p.K; ++kd) {
+        const uint32_t slot = pa % p.a_slots;
+        mbar_wait_prof(&a_full[slot], (pa / p.a_slots) & 1u, w_af, prof);
+        tc_fence_after();
+        const uint32_t slab = smem_u32(a_smem + (size_t)slot * p.slab_bytes);
+        for (int kh = 0; kh < p.K; ++kh) {
+          uint32_t b_addr;
+          uint32_t bs = 0;
+          if (p.b_resident) {
+            b_addr = smem_u32(b_smem + (size_t)(kd * p.K + kh) * p.b_bytes);
+          } else {
+            bs = pb % p.b_slots;
+            mbar_wait_prof(&b_full[bs], (pb / p.b_slots) & 1u, w_bf, prof);
+            tc_fence_after();
+            b_addr = smem_u32(b_smem + (size_t)bs * p.b_bytes);
+          }
+          const uint64_t ad = make_sw128_desc(slab + (uint32_t)kh * 2048u);   // line kh of the slab: 16 rows x 128 B
+          const uint64_t bd = make_sw64_desc(b_addr);                          // 2*NF rows x 64 B: [hi rows ; lo rows]
+          const uint32_t first = (kd | kh) ? 1u : 0u;
+          if (elect_one()) {
+            // A: hi slices at +0,+32 B, lo slices at +64,+96 B of each 128-byte row; B: slices at +0,+32 B of each 64-byte row
+            umma_f16(d1, ad, bd, idesc2, first);          // A_hi(s0) x [B_hi;B_lo](s0) -> [D1|D2]
+            umma_f16(d2, ad + 4, bd, idesc, 1);           // A_lo(s0) x B_hi(s0)        -> D2
+            umma_f16(d1, ad + 2, bd + 2, idesc2, 1);      // slice 1
+            umma_f16(d2, ad + 6, bd + 2, idesc, 1);
+            if (!p.b_resident) umma_commit(&b_empty[bs]);
+            if (kh == p.K - 1) umma_commit(&a_empty[slot]);
+            if (kh == p.K - 1 && kd == p.K - 1) umma_commit(&acc_full[as]);
+          }
+          __syncwarp();
+          if (!p.b_resident) ++pb;
+        }
+        ++pa;
+      }
+    }
+    if (prof && lane == 0) { atomicAdd(&p.prof[3], w_acc); atomicAdd(&p.prof[4], w_af); atomicAdd(&p.prof[5], w_bf); atomicAdd(&p.prof[6], (unsigned long long)(clock64() - tstart)); }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9: two per TMEM lane quadrant, 16 output channels each) =================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int line = row >> 4, xi = row & 15;
     const bool keep = xi < p.OWt;
     const int srow = line * p.OWt + xi;        // compacted staging row
     const bool leader = threadIdx.x == 64;
-    const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
+    const bool has_cols = half * 16 < p.NC;    // NC = 16: the upper half only writes the zero padding channels
     const uint32_t stage_bytes = (uint32_t)p.stage_rows * 128u;
     uint32_t it = 0;
+    const bool prof = p.prof != nullptr;
+    unsigned long long w_accf = 0, w_res = 0;
+    const long long tstart = clock64();
     for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       long t = tile;
       const int xw = (int)(t % p.xwins); t /= p.xwins;
@@ -184,105 +219,46 @@ __global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant
         mbar_expect_tx(res_full, stage_bytes);
         tma_load_5d(res_stage, &tmRes, res_full, 0, xw * p.OWt, yb * 8, z, n);
       }
-      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      mbar_wait_prof(&acc_full[as], (it >> 1) & 1u, w_accf, prof);
       tc_fence_after();
-      float v[32];
+      float v[16], r[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-      const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 2u * (uint32_t)p.NF;
-      for (int kw = 0; kw < p.K; ++kw) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h * 16 >= p.NC) break;
+      for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      if (has_cols) {
+        const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 2u * (uint32_t)p.NF + (uint32_t)(half * 16);
+        for (int kw = 0; kw < p.K; ++kw) {
           uint32_t t1[16], t2[16];
-          tmem_ld16(tb + (uint32_t)(kw * p.NC + h * 16), t1);
-          tmem_ld16(tb + (uint32_t)(p.NF + kw * p.NC + h * 16), t2);
+          tmem_ld16_nowait(tb + (uint32_t)(kw * p.NC), t1);
+          tmem_ld16_nowait(tb + (uint32_t)(p.NF + kw * p.NC), t2);
+          tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float d = fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j]));
-            v[h * 16 + j] += __shfl_down_sync(0xffffffffu, d, kw);    // row (line, xi + kw) -> output (line, xi)
+            v[j] += __shfl_down_sync(0xffffffffu, d, kw);    // row (line, xi + kw) -> output (line, xi)
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);              // accumulator stage drained: the MMA warp may start tile it+2
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + j));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + j));
-        v[j] = fmaf(v[j], sc.x, sh.x); v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
-        v[j + 2] = fmaf(v[j + 2], sc.z, sh.z); v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
-      }
-      float r[32];
+      if (p.dbg == 2) continue;
+      epi_affine16(v, p.scale, p.shift, half * 16);
       if (p.residual != LT_RES_NONE) {
-        mbar_wait(res_full, it & 1u);
-        const uint32_t rb = smem_u32(res_stage);
-        if (keep) {
-          if (p.out_format == LT_FMT_F32) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 q = lds128(rb + sw128_off(srow, c));
-              r[c * 4] = __uint_as_float(q.x); r[c * 4 + 1] = __uint_as_float(q.y);
-              r[c * 4 + 2] = __uint_as_float(q.z); r[c * 4 + 3] = __uint_as_float(q.w);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 qh = lds128(rb + sw128_off(srow, c)), ql = lds128(rb + sw128_off(srow, c + 4));
-              const sh_t* hh = reinterpret_cast<const sh_t*>(&qh);
-              const sh_t* ll = reinterpret_cast<const sh_t*>(&ql);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) r[c * 8 + e] = join_s32(hh[e], ll[e]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0.0f;
-        }
+        mbar_wait_prof(res_full, it & 1u, w_res, prof);
+        if (keep) epi_load16(smem_u32(res_stage), srow, half, p.out_format, r);
       }
-      if (p.residual == LT_RES_BEFORE_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += r[j];
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.residual == LT_RES_AFTER_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += r[j];
-      }
-      if (leader) bulk_wait_read<0>();          // previous tile's store has finished reading out_stage
+      epi_activate16(v, r, p.residual, p.relu);
+      if (leader) bulk_wait_read<0>();          // previous tile's store has finished reading the staging buffer
       epi_bar_sync();
-      if (keep) {
-        const uint32_t ob = smem_u32(out_stage);
-        if (p.out_format == LT_FMT_F32) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts128(ob + sw128_off(srow, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
-                                                        __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 qh, ql;
-            sh_t* hh = reinterpret_cast<sh_t*>(&qh);
-            sh_t* ll = reinterpret_cast<sh_t*>(&ql);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split_s32(v[c * 8 + e], hh[e], ll[e]);
-            sts128(ob + sw128_off(srow, c), qh);
-            sts128(ob + sw128_off(srow, c + 4), ql);
-          }
-        }
-      }
+      if (keep) epi_store16(smem_u32(out_stage), srow, half, p.out_format, v);
       fence_proxy_async();
       epi_bar_sync();
       if (leader) {
         tma_store_5d(&tmOut, out_stage, 0, xw * p.OWt, yb * 8, z, n);
         bulk_commit();
       }
-      (void)esz;
     }
     if (leader) bulk_wait<0>();
+    if (prof && threadIdx.x == 64) { atomicAdd(&p.prof[7], w_accf); atomicAdd(&p.prof[8], w_res); atomicAdd(&p.prof[9], (unsigned long long)(clock64() - tstart)); }
   }
 
   tc_fence_before();
@@ -293,7 +269,7 @@ __global__ void __launch_bounds__(192, 1) conv_fold_kernel(const __grid_constant
   }
 }
 
-// fp32 [K^3 taps (kd,kh,kw)][32][Cout] -> split-fp16 [kd][kh][kw*NC + co][64]
+// fp32 [K^3 taps (kd,kh,kw)][32][Cout] -> fp16 [kd][kh][2][kw*NC + co][32]: hi rows then lo rows, 64 bytes per row
 __global__ void __launch_bounds__(256) pack_fold_weights_kernel(const float* __restrict__ w, sh_t* __restrict__ out, int K, int Cout, int NC) {
   const int NF = K * NC;
   const long total = (long)K * K * NF * 32;
@@ -307,9 +283,9 @@ __global__ void __launch_bounds__(256) pack_fold_weights_kernel(const float* __r
     const float v = (co < Cout) ? w[((((long)kd * K + kh) * K + kw) * 32 + ci) * Cout + co] : 0.0f;
     sh_t hi, lo;
     split_s32(v, hi, lo);
-    sh_t* row = out + (((long)kd * K + kh) * NF + col) * 64;
-    row[ci] = hi;
-    row[32 + ci] = lo;
+    sh_t* tile = out + ((long)kd * K + kh) * 2 * NF * 32;
+    tile[(long)col * 32 + ci] = hi;
+    tile[((long)NF + col) * 32 + ci] = lo;
   }
 }
 
@@ -317,7 +293,7 @@ int conv_fold_supported(const lt_conv_desc* d) {
   const bool cubic = d->KD == d->KH && d->KH == d->KW && (d->KW == 3 || d->KW == 7);
   const int p = d->KW / 2;
   const int NC = (d->Cout + 15) & ~15;
-  return cubic && d->Cin == 32 && NC <= 32 && d->KW * NC <= 128 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == p &&
+  return cubic && d->Cin == 32 && NC <= 32 && d->KW * NC <= 128 && 2 * d->KW * NC <= 256 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == p &&
          d->ph == p && d->pw == p && d->OD == d->ID && d->OH == d->IH && d->OW == d->IW && d->osd == 1 && d->osh == 1 &&
          d->osw == 1 && d->ood == 0 && d->ooh == 0 && d->oow == 0 && d->FD == d->OD && d->FH == d->OH && d->FW == d->OW &&
          d->FC == 32 && d->in_format == LT_FMT_S32 && d->IW >= 16;
@@ -346,6 +322,12 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.stage_rows = 8 * p.OWt;
   p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
   p.scale = scale; p.shift = shift;
+  p.dbg = getenv("LT_FOLD_DBG") ? atoi(getenv("LT_FOLD_DBG")) : 0;
+  static unsigned long long* prof_buf = nullptr;
+  static const bool want_prof = getenv("LT_FOLD_PROF") != nullptr;
+  if (want_prof && !prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long));
+  p.prof = want_prof ? prof_buf : nullptr;
+  if (want_prof) cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
   const int b_region = p.b_resident ? p.K * p.K * p.b_bytes : p.b_slots * p.b_bytes;
   p.off_b = 0;
   p.off_a = up1024(b_region);
@@ -365,10 +347,10 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {64, (uint64_t)p.K * p.K * p.NF};
-    const uint64_t str[1] = {128};
-    const uint32_t bx[2] = {64, (uint32_t)p.NF};
-    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
+    const uint64_t dims[2] = {32, (uint64_t)p.K * p.K * 2 * p.NF};
+    const uint64_t str[1] = {64};
+    const uint32_t bx[2] = {32, (uint32_t)(2 * p.NF)};
+    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 2);   // 64-byte rows, 64B swizzle
     if (rc) return rc;
   }
   {
@@ -392,9 +374,16 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
     configured = true;
   }
   long grid = p.tiles < sm_count() ? p.tiles : sm_count();
-  conv_fold_kernel<<<(unsigned)grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, tmOut, tmRes, p);
+  conv_fold_kernel<<<(unsigned)grid, 320, smem, (cudaStream_t)stream>>>(tmA, tmB, tmOut, tmRes, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold_kernel: %s", cudaGetErrorString(e));
+  if (want_prof) {   // debug only: synchronises
+    unsigned long long h[16];
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const double g = (double)grid;
+    fprintf(stderr, "[fold prof K=%d tiles/cta=%.0f] producer: total %.0f wait a_empty %.0f b_empty %.0f | mma: total %.0f wait acc_empty %.0f a_full %.0f b_full %.0f | epi: total %.0f wait acc_full %.0f res %.0f (cycles per CTA)\n",
+            p.K, (double)p.tiles / g, h[2] / g, h[0] / g, h[1] / g, h[6] / g, h[3] / g, h[4] / g, h[5] / g, h[9] / g, h[7] / g, h[8] / g);
+  }
   return LT_OK;
 }
 

@@ -10,6 +10,15 @@ namespace lt {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a CONVERGED warp (elect.sync): keeps the surrounding control flow warp-uniform so that the compiler
+// keeps descriptors / loop state in uniform registers instead of serialising through divergence waterfalls
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -60,7 +69,8 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quadrant, each taking 16 of a block's 32 channels
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // byte offset of 16-byte chunk c16 of row `row` inside a [rows][128 B] tile with the 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128_off(int row, int c16) { return (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4)); }
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -105,10 +115,100 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// two floats -> packed split-fp16 (hi pair, lo pair); element `a` lands in the low half-word (lower address)
+__device__ __forceinline__ void split_s32x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  const float ra = (a - hf.x) * kLoScale, rb = (b - hf.y) * kLoScale;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(rb), "f"(ra));
+}
+
+// 16 channels (half `half` of a 32-channel block) of staged row `srow`: [rows][128 B] tile, 128B swizzle.
+// split-fp16: hi halves in chunks 0..3, lo halves in chunks 4..7 (8 channels per chunk); fp32: 4 channels per chunk.
+__device__ __forceinline__ void epi_load16(uint32_t base, int srow, int half, int out_format, float (&r)[16]) {
+  if (out_format == LT_FMT_F32) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 q = lds128(base + sw128_off(srow, half * 4 + c));
+      r[c * 4] = __uint_as_float(q.x); r[c * 4 + 1] = __uint_as_float(q.y);
+      r[c * 4 + 2] = __uint_as_float(q.z); r[c * 4 + 3] = __uint_as_float(q.w);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint4 qh = lds128(base + sw128_off(srow, half * 2 + c)), ql = lds128(base + sw128_off(srow, 4 + half * 2 + c));
+      const __half2* hh = reinterpret_cast<const __half2*>(&qh);
+      const __half2* ll = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(hh[e]), b = __half22float2(ll[e]);
+        r[c * 8 + e * 2] = fmaf(b.x, kLoInv, a.x);
+        r[c * 8 + e * 2 + 1] = fmaf(b.y, kLoInv, a.y);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void epi_store16(uint32_t base, int srow, int half, int out_format, const float (&v)[16]) {
+  if (out_format == LT_FMT_F32) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      sts128(base + sw128_off(srow, half * 4 + c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
+                                                               __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
+  } else {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint4 qh, ql;
+      split_s32x2(v[c * 8], v[c * 8 + 1], qh.x, ql.x);
+      split_s32x2(v[c * 8 + 2], v[c * 8 + 3], qh.y, ql.y);
+      split_s32x2(v[c * 8 + 4], v[c * 8 + 5], qh.z, ql.z);
+      split_s32x2(v[c * 8 + 6], v[c * 8 + 7], qh.w, ql.w);
+      sts128(base + sw128_off(srow, half * 2 + c), qh);
+      sts128(base + sw128_off(srow, 4 + half * 2 + c), ql);
+    }
+  }
+}
+// scale/shift, residual, ReLU on 16 channels starting at channel index co
+__device__ __forceinline__ void epi_affine16(float (&v)[16], const float* __restrict__ scale, const float* __restrict__ shift, int co) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + co + j));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + co + j));
+    v[j] = fmaf(v[j], sc.x, sh.x); v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z); v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+  }
+}
+__device__ __forceinline__ void epi_activate16(float (&v)[16], const float (&r)[16], int residual, int relu) {
+  if (residual == LT_RES_BEFORE_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += r[j];
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (residual == LT_RES_AFTER_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += r[j];
+  }
+}
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 bytes, 8-row atoms
 // 1024 bytes apart): start address >> 4 | LBO=1 | SBO=1024>>4 | version=1 | layout=SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// K-major, 64-byte-swizzled descriptor (rows of 64 bytes, 8-row atoms 512 bytes apart): layout = SWIZZLE_64B (4)
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=fp16 (format 0), both K-major, M=128, N=n
 __host__ __device__ inline uint32_t make_idesc_f16(int n) {
@@ -118,6 +218,6 @@ __host__ __device__ inline uint32_t make_idesc_f16(int n) {
 
 // ---- host helpers (conv_tc.cu) ----
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box, const uint32_t* estrides, int swizzle128, int f32 = 0);
+             const uint32_t* box, const uint32_t* estrides, int swizzle128, int f32 = 0);   // swizzle128: 1 = 128B, 2 = 64B, 0 = none
 
 }  // namespace lt
