@@ -97,7 +97,9 @@ def cpu_oracle_rate(args, steps, warmup):
     from oracle import vol_oracle as O
     import lt_b200
     from lt_b200 import testing
-    torch.set_num_threads(os.cpu_count())
+    # all host threads the reference can use productively: intra-op scaling of fp32 convs flattens (and on shared,
+    # oversubscribed hosts reverses) beyond ~32 threads; LT_BENCH_CPU_THREADS overrides
+    torch.set_num_threads(int(os.environ.get("LT_BENCH_CPU_THREADS", min(os.cpu_count(), 32))))
     cfg = testing.make_config(num_layers=args.layers, volume_size=args.volume)
     model = lt_b200.VolumetricTriangulationNet(cfg, device="cpu", backend="torch")   # parameter holder only
     sd = model.state_dict()
@@ -116,7 +118,7 @@ def cpu_oracle_rate(args, steps, warmup):
 def main_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 2)), max(1, min(args.warmup, 1))
     rate, dt, threads = cpu_oracle_rate(args, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
@@ -255,30 +257,43 @@ def main_native(args, rank, world, local_rank):
     pk = peaks()
     roof = None
     extra = {}
-    conv_key = "conv_tc" if "conv_tc" in agg else "conv_ffma"
-    if conv_key in agg:
-        ms, fl, _, cnt = agg[conv_key]
+    tensor_kernels = [k for k in ("conv_tc", "conv_fold", "conv_ffma") if k in agg]
+    conv_key = max(tensor_kernels, key=lambda k: agg[k][0]) if tensor_kernels else None
+
+    def tensor_roof(key):
+        ms, fl, _, cnt = agg[key]
         ach = fl / (ms / 1e3) / 1e12
-        peak = pk["bf16_tflops"] if conv_key == "conv_tc" else 75.0
-        roof = {"kernel": conv_key + "_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "launches": cnt, "ms_per_step": ms,
-                "peak_source": pk["src"] + (" sustained dense bf16 (cuBLAS)" if conv_key == "conv_tc" else " nominal fp32 FFMA")}
-    for key in ("unproject", "softargmax", "conv_ffma"):
-        if key in agg and key != conv_key:
+        tc = key != "conv_ffma"
+        peak = pk["bf16_tflops"] if tc else 75.0
+        r = {"kernel": {"conv_tc": "conv_tc_kernel", "conv_fold": "conv_fold_kernel", "conv_ffma": "conv_simt_kernel"}[key],
+             "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+             "launches": cnt, "ms_per_step": ms,
+             "peak_source": pk["src"] + (" sustained dense bf16/fp16 (cuBLAS)" if tc else " nominal fp32 FFMA")}
+        if tc and args.mode == "tc":
+            # fp32-grade results cost three fp16 products per term (hi*hi, hi*lo, lo*hi): tensor-pipe work actually issued
+            r["issued_mma_tflops"] = 3.0 * ach
+            r["issued_frac"] = 3.0 * ach / peak
+        return r
+
+    if conv_key:
+        roof = tensor_roof(conv_key)
+    for key in tensor_kernels:
+        if key != conv_key:
+            extra["roofline_" + key] = tensor_roof(key)
+    for key in ("unproject", "softargmax"):
+        if key in agg:
             ms, fl, nb, cnt = agg[key]
-            if nb > 0:
-                ach = nb / (ms / 1e3) / 1e9
-                extra["roofline_" + key] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                            "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt}
-            else:
-                extra["time_" + key] = {"ms_per_step": ms, "tflops": fl / (ms / 1e3) / 1e12, "launches": cnt}
+            ach = nb / (ms / 1e3) / 1e9
+            extra["roofline_" + key] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                        "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt,
+                                        "peak_source": pk["src"] + " copy bandwidth"}
     extra["step_breakdown_ms"] = {k: round(v[0], 3) for k, v in agg.items()}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, dt, threads = cpu_oracle_rate(args, 2, 1)
+        rate, dt, threads = cpu_oracle_rate(args, 1, 1)
         cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "2 timed forwards of one %d-view sample (same config), CPU oracle port, %d threads" % (V, threads)}
+               "sample": "1 warm-up + 1 timed forward of one %d-view sample (same config), CPU oracle port, %d of %d host threads" % (V, threads, os.cpu_count())}
 
     if rank == 0:
         line = {

@@ -44,35 +44,6 @@ __device__ __forceinline__ void st_push(SoftState& s, float l, float x, float y,
     s.sz = fmaf(e, z, s.sz);
   }
 }
-// four elements at once: one rescale of the running sums per batch (1.25 exp per element instead of 2)
-__device__ __forceinline__ void st_push4(SoftState& s, const float (&l)[4], const float (&x)[4], const float (&y)[4],
-                                         const float (&z)[4], const bool (&ok)[4], bool softmax) {
-  if (softmax) {
-    float mn = s.m;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (ok[u]) mn = fmaxf(mn, l[u]);
-    if (mn == -INFINITY) return;
-    const float r = __expf(s.m - mn);
-    s.d *= r; s.sx *= r; s.sy *= r; s.sz *= r;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float e = ok[u] ? __expf(l[u] - mn) : 0.0f;
-      s.d += e;
-      s.sx = fmaf(e, x[u], s.sx);
-      s.sy = fmaf(e, y[u], s.sy);
-      s.sz = fmaf(e, z[u], s.sz);
-    }
-    s.m = mn;
-  } else {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float e = ok[u] ? fmaxf(l[u], 0.0f) : 0.0f;
-      s.sx = fmaf(e, x[u], s.sx);
-      s.sy = fmaf(e, y[u], s.sy);
-      s.sz = fmaf(e, z[u], s.sz);
-    }
-  }
-}
 __device__ __forceinline__ void st_merge(SoftState& a, const SoftState& b, bool softmax) {
   if (softmax) {
     const float mn = fmaxf(a.m, b.m);
@@ -126,17 +97,18 @@ __global__ void __launch_bounds__(256) softargmax_partial_cl(const SoftParams p)
   // 4 voxels in flight per warp iteration
   for (long v = v0 + warp * 4; v < v1; v += 32) {
     float l[4], x[4], y[4], z[4];
-    bool ok[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long vv = v + u;
-      ok[u] = vv < v1;
-      l[u] = (ok[u] && active) ? __ldg(lg + vv * p.vs) * p.mult : 0.0f;
-      x[u] = ok[u] ? __ldg(cd + vv * 3) : 0.0f;
-      y[u] = ok[u] ? __ldg(cd + vv * 3 + 1) : 0.0f;
-      z[u] = ok[u] ? __ldg(cd + vv * 3 + 2) : 0.0f;
+      const bool ok = vv < v1;
+      l[u] = (ok && active) ? __ldg(lg + vv * p.vs) : 0.0f;
+      x[u] = ok ? __ldg(cd + vv * 3) : 0.0f;
+      y[u] = ok ? __ldg(cd + vv * 3 + 1) : 0.0f;
+      z[u] = ok ? __ldg(cd + vv * 3 + 2) : 0.0f;
     }
-    st_push4(s, l, x, y, z, ok, sm);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u < v1) st_push(s, l[u] * p.mult, x[u], y[u], z[u], sm);
   }
   __shared__ SoftState sh[8][32];
   sh[warp][lane] = s;

@@ -299,7 +299,8 @@ class NativeEngine:
         if (pk.w_fold is not None and x.W >= 16 and out.C == 32 and out_scale == (1, 1, 1) and (od, oh, ow) == (x.D, x.H, x.W)):
             impl, weight = CONV_TC_FOLD, pk.w_fold
             d.Cout = pk.cout
-        with self._timed("conv_tc" if pk.impl != CONV_SIMT else "conv_ffma", flops=2.0 * x.N * od * oh * ow * pk.kmacs,
+        label = "conv_fold" if impl == CONV_TC_FOLD else ("conv_tc" if impl != CONV_SIMT else "conv_ffma")
+        with self._timed(label, flops=2.0 * x.N * od * oh * ow * pk.kmacs,
                          desc="N%d %dx%dx%d Cin%d Cout%d k%d%d%d s%d" % (x.N, od, oh, ow, pk.cin, pk.cout, kd, kh, kw, sw)):
             capi.conv_nd(d, x.data, weight, pk.scale, pk.shift, None if residual is None else residual.data, out.data, impl)
         self.launches += 1
