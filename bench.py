@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--image", type=int, default=384)
     ap.add_argument("--volume", type=int, default=64)
     ap.add_argument("--layers", type=int, default=152)
-    ap.add_argument("--collective", default="all_reduce", choices=["all_reduce", "reduce_scatter"])
+    ap.add_argument("--collective", default="all_reduce", choices=["all_reduce", "reduce_scatter", "p2p"],
+                    help="view-group exchange: one NCCL all-reduce (contract), reduce-scatter, or the fused P2P-store kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-calibrate", action="store_true", help="keep PyTorch default init (faster start, degenerate signal)")
     return ap.parse_args()
@@ -188,8 +189,10 @@ def main_native(args, rank, world, local_rank):
         proj, base, position, stepv, rots, _ = model._host_geometry(batch, Bg, (S, S), (S // 4, S // 4))
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
         geo = (up(proj[:, views]), up(position), up(base), up(stepv), up(rots.reshape(Bg, 9)))
-        parallelism = "view-sharded: %d group(s) x %d ranks, %d view(s)/rank, packed num/den %s over NCCL, V2V batch-sharded" % (
-            plan.n_groups, plan.group_size, len(views), args.collective)
+        parallelism = "view-sharded: %d group(s) x %d ranks, %d view(s)/rank, packed num/den %s, V2V batch-sharded" % (
+            plan.n_groups, plan.group_size, len(views),
+            "stored into the owner rank by the unprojection kernel over NVLink peer memory" if args.collective == "p2p"
+            else args.collective + " over NCCL")
 
         def step(img):
             return eng.forward_view_sharded(img, geo[0], geo[1], geo[2], geo[3], geo[4], plan, pg, args.collective)[0]

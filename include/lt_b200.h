@@ -96,6 +96,18 @@ int lt_unproject_partial_fwd(const float* features, const float* proj, const flo
 int lt_unproject_finalize_fwd(const float* partial, void* out, int out_format, int B, int C, long nvox,
                               int agg, void* stream);
 
+/* Fused unprojection + exchange over NVLink peer memory (no NCCL on the data path).  peer_buffers[r] is rank r's
+ * reduction buffer [n_peers slots][B/n_peers][P][nvox][C] float32, mapped into this process (CUDA IPC / symmetric
+ * memory).  The kernel computes this rank's partials for all B samples and STORES sample b's partial directly into
+ * peer_buffers[b / (B/n_peers)] at slot src_rank, so the transfer overlaps the gather/softmax math voxel by voxel.
+ * After a cross-rank barrier, lt_unproject_reduce_finalize_fwd on each owner sums its n_peers slots (max for
+ * LT_AGG_MAX), divides (softmax) and converts.  C = 4*2^k <= 128, V_local <= 8. */
+int lt_unproject_push_fwd(const float* features, const float* proj, const float* coord, const float* conf,
+                          float* const* peer_buffers /* HOST array of n_peers device pointers */, int n_peers, int src_rank,
+                          int B, int V_local, int C, int h, int w, long nvox, int agg, void* stream);
+int lt_unproject_reduce_finalize_fwd(const float* slots, int nslots, void* out, int out_format, int B, int C, long nvox,
+                                     int agg, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Volumetric soft-argmax.  Replaces op.integrate_tensor_3d_with_coordinates (op.py:84-96).
  *   logits: element (b, j, vox) at logits[b*batch_stride + vox*voxel_stride + j*chan_stride]

@@ -45,6 +45,8 @@ SIGNATURES = {
     "lt_unproject_aggregate_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_long, c_int, c_void_p]),
     "lt_unproject_partial_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_long, c_int, c_void_p]),
     "lt_unproject_finalize_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
+    "lt_unproject_push_fwd": (c_int, [c_void_p] * 4 + [ctypes.POINTER(c_void_p), c_int, c_int] + [c_int] * 5 + [c_long, c_int, c_void_p]),
+    "lt_unproject_reduce_finalize_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
     "lt_softargmax3d_workspace_bytes": (c_size_t, [c_int, c_int, c_long]),
     "lt_softargmax3d_fwd": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                     c_int, c_int, c_long, c_float, c_int, c_void_p]),
@@ -132,6 +134,20 @@ def unproject_partial(features_cl, proj, coord, conf, partial, agg):
 def unproject_finalize(partial, out, out_format, B, C, nvox, agg):
     _check(lib().lt_unproject_finalize_fwd(_ptr(partial), _ptr(out), out_format, B, C, nvox, agg, _stream()),
            "lt_unproject_finalize_fwd")
+
+
+def unproject_push(features_cl, proj, coord, conf, peer_ptrs, src_rank, agg):
+    """peer_ptrs: list of int device pointers (one reduction buffer per rank of the view group)."""
+    B, V, h, w, C = features_cl.shape
+    nvox = coord.shape[1]
+    arr = (c_void_p * len(peer_ptrs))(*peer_ptrs)
+    _check(lib().lt_unproject_push_fwd(_ptr(features_cl), _ptr(proj), _ptr(coord), _ptr(conf), arr, len(peer_ptrs), src_rank,
+                                       B, V, C, h, w, nvox, agg, _stream()), "lt_unproject_push_fwd")
+
+
+def unproject_reduce_finalize(slots, nslots, out, out_format, B, C, nvox, agg):
+    _check(lib().lt_unproject_reduce_finalize_fwd(_ptr(slots), nslots, _ptr(out), out_format, B, C, nvox, agg, _stream()),
+           "lt_unproject_reduce_finalize_fwd")
 
 
 def softargmax3d(logits, batch_stride, voxel_stride, chan_stride, coord, volumes_out, keypoints_out, workspace,

@@ -30,6 +30,9 @@ struct UnprojParams {
   int B, V, C, h, w;
   long nvox;
   int agg, out_format, G, partial;
+  // partial == 2 ("push"): sample b's partial goes to peer[b / samples_per_owner] (P2P store over NVLink) at slot src_rank
+  float* peer[8];
+  int samples_per_owner, src_rank;
 };
 
 struct Taps {
@@ -378,7 +381,13 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
     if (!live) continue;
     if (p.partial) {
       const int planes = (p.agg == LT_AGG_SOFTMAX) ? 2 : 1;
-      float* d0 = reinterpret_cast<float*>(p.out) + (((long)b * planes) * p.nvox + vox) * C + c0;
+      float* d0;
+      if (p.partial == 2) {   // fused exchange: write straight into the owner rank's reduction buffer (peer memory)
+        const int owner = b / p.samples_per_owner, bl = b % p.samples_per_owner;
+        d0 = p.peer[owner] + ((((long)p.src_rank * p.samples_per_owner + bl) * planes) * p.nvox + vox) * C + c0;
+      } else {
+        d0 = reinterpret_cast<float*>(p.out) + (((long)b * planes) * p.nvox + vox) * C + c0;
+      }
       *reinterpret_cast<float4*>(d0) = make_float4(o[0], o[1], o[2], o[3]);
       if (planes == 2) *reinterpret_cast<float4*>(d0 + p.nvox * C) = make_float4(o2[0], o2[1], o2[2], o2[3]);
     } else {
@@ -388,18 +397,29 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
 }
 
 // partial[B][P][nvox][C] -> out[B][nvox][C] (divide numerator by denominator for softmax)
+// nslots > 1: partial is [slot][B][P][nvox][C] (one slot per source rank, filled by P2P stores) and is reduced here.
 __global__ void __launch_bounds__(256) unproject_finalize_kernel(const float* __restrict__ partial, void* out, int out_format,
-                                                                 int B, int C, long nvox, int agg) {
+                                                                 int B, int C, long nvox, int agg, int nslots) {
   const long per_b = nvox * C;
   const long total4 = (long)B * per_b / 4;
   const int planes = (agg == LT_AGG_SOFTMAX) ? 2 : 1;
+  const long slot_stride = (long)B * planes * per_b;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
     const long e = i * 4;
     const long b = e / per_b, r = e % per_b;
-    const float4 n = *reinterpret_cast<const float4*>(partial + (b * planes) * per_b + r);
+    float4 n = *reinterpret_cast<const float4*>(partial + (b * planes) * per_b + r);
+    for (int s = 1; s < nslots; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(partial + s * slot_stride + (b * planes) * per_b + r);
+      if (agg == LT_AGG_MAX) { n.x = fmaxf(n.x, t.x); n.y = fmaxf(n.y, t.y); n.z = fmaxf(n.z, t.z); n.w = fmaxf(n.w, t.w); }
+      else { n.x += t.x; n.y += t.y; n.z += t.z; n.w += t.w; }
+    }
     float4 o = n;
     if (planes == 2) {
-      const float4 d = *reinterpret_cast<const float4*>(partial + (b * planes + 1) * per_b + r);
+      float4 d = *reinterpret_cast<const float4*>(partial + (b * planes + 1) * per_b + r);
+      for (int s = 1; s < nslots; ++s) {
+        const float4 t = *reinterpret_cast<const float4*>(partial + s * slot_stride + (b * planes + 1) * per_b + r);
+        d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+      }
       o = make_float4(n.x / d.x, n.y / d.y, n.z / d.z, n.w / d.w);
     }
     if (out_format == LT_FMT_F32) {
@@ -414,7 +434,7 @@ __global__ void __launch_bounds__(256) unproject_finalize_kernel(const float* __
 
 static int launch_unproject(const float* features, const float* proj, const float* coord, const float* conf, void* out,
                             int out_format, int B, int V, int C, int h, int w, long nvox, int agg, int partial,
-                            void* stream) {
+                            void* stream, float* const* peers = nullptr, int n_peers = 0, int src_rank = 0) {
   LT_REQUIRE(features && proj && coord && out, "unproject: null pointer");
   LT_REQUIRE(B > 0 && V > 0 && C > 0 && h > 0 && w > 0 && nvox > 0, "unproject: non-positive size");
   LT_REQUIRE(agg >= LT_AGG_SUM && agg <= LT_AGG_CONF, "unproject: unknown aggregation %d", agg);
@@ -423,6 +443,13 @@ static int launch_unproject(const float* features, const float* proj, const floa
              "unproject: split-fp16 output needs C %% 32 == 0 (C=%d)", C);
   LT_REQUIRE(B <= 65535, "unproject: batch too large");
   UnprojParams p{features, proj, coord, conf, out, B, V, C, h, w, nvox, agg, out_format, 1, partial};
+  p.samples_per_owner = 1; p.src_rank = src_rank;
+  for (int i = 0; i < 8; ++i) p.peer[i] = (peers && i < n_peers) ? peers[i] : nullptr;
+  if (partial == 2) {
+    LT_REQUIRE(peers && n_peers >= 1 && n_peers <= 8 && B % n_peers == 0, "unproject_push: need 1..8 peers dividing the batch");
+    LT_REQUIRE(C % 4 == 0 && C / 4 <= 32 && ((C / 4) & (C / 4 - 1)) == 0 && V <= kMaxStoredViews, "unproject_push: unsupported shape");
+    p.samples_per_owner = B / n_peers;
+  }
   const bool vec4 = (C % 4 == 0);
   const int units = vec4 ? C / 4 : C;   // lanes wanted per voxel
   int G = 1;
@@ -474,6 +501,27 @@ extern "C" int lt_unproject_partial_fwd(const float* features, const float* proj
   return lt::launch_unproject(features, proj, coord, conf, partial, LT_FMT_F32, B, V_local, C, h, w, nvox, agg, 1, stream);
 }
 
+extern "C" int lt_unproject_push_fwd(const float* features, const float* proj, const float* coord, const float* conf,
+                                     float* const* peer_buffers, int n_peers, int src_rank, int B, int V_local, int C, int h,
+                                     int w, long nvox, int agg, void* stream) {
+  return lt::launch_unproject(features, proj, coord, conf, (void*)peer_buffers[src_rank], LT_FMT_F32, B, V_local, C, h, w, nvox, agg, 2,
+                              stream, peer_buffers, n_peers, src_rank);
+}
+
+extern "C" int lt_unproject_reduce_finalize_fwd(const float* slots, int nslots, void* out, int out_format, int B, int C, long nvox,
+                                                int agg, void* stream) {
+  using namespace lt;
+  LT_REQUIRE(slots && out && nslots >= 1 && C % 4 == 0, "unproject_reduce_finalize: bad arguments");
+  LT_REQUIRE(out_format == LT_FMT_F32 || C % 32 == 0, "unproject_reduce_finalize: split-fp16 output needs C %% 32 == 0");
+  const long total4 = (long)B * nvox * C / 4;
+  long blocks = (total4 + 255) / 256;
+  const long cap = (long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  unproject_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(slots, out, out_format, B, C, nvox, agg, nslots);
+  LT_CHECK_LAUNCH("unproject_finalize_kernel");
+  return LT_OK;
+}
+
 extern "C" int lt_unproject_finalize_fwd(const float* partial, void* out, int out_format, int B, int C, long nvox, int agg,
                                          void* stream) {
   using namespace lt;
@@ -484,7 +532,7 @@ extern "C" int lt_unproject_finalize_fwd(const float* partial, void* out, int ou
   long blocks = (total4 + 255) / 256;
   const long cap = (long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  unproject_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partial, out, out_format, B, C, nvox, agg);
+  unproject_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partial, out, out_format, B, C, nvox, agg, 1);
   LT_CHECK_LAUNCH("unproject_finalize_kernel");
   return LT_OK;
 }

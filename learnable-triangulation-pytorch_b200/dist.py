@@ -82,6 +82,26 @@ def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum
     return partial[plan.view_rank * per:(plan.view_rank + 1) * per]
 
 
+class PeerExchange:
+    """Per-rank reduction buffers of a view group mapped into every member (torch symmetric memory = CUDA IPC /
+    fabric handles over NVLink): the fused unprojection kernel stores its partials straight into the owner's buffer
+    (`lt_unproject_push_fwd`), a group barrier orders the stores, the owner reduces its slots (`lt_unproject_reduce_
+    finalize_fwd`).  No NCCL collective on the data path.
+    """
+
+    def __init__(self, plan, pg, batch, planes, nvox, channels, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.plan, self.pg = plan, pg
+        per = batch // plan.group_size
+        self.shape = (plan.group_size, per, planes, nvox, channels)
+        self.buf = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def barrier(self):
+        self.handle.barrier()
+
+
 def gather_keypoints(kp_local, plan, pg):
     """[B/G][J][3] on each rank -> [B][J][3] on every rank of the group."""
     import torch.distributed as dist

@@ -458,12 +458,27 @@ class NativeEngine:
         feats = self.backbone_features(images_local.reshape(B * Vl, *images_local.shape[2:]))
         agg = capi.AGG[m.volume_aggregation_method]
         planes = 2 if m.volume_aggregation_method == "softmax" else 1
-        partial = torch.empty((B, planes, nvox, feats.C), dtype=torch.float32, device=dev)
-        capi.unproject_partial(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None, partial, agg)
-        mine = lt_dist.complete_partials(partial, plan, pg, collective, "max" if m.volume_aggregation_method == "max" else "sum")
-        Bl = mine.shape[0]
-        vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
-        capi.unproject_finalize(mine.contiguous(), vol.data, vol.fmt, Bl, feats.C, nvox, agg)
+        if collective == "p2p" and plan.group_size > 1:
+            # fused unprojection + exchange: partials are stored straight into the owner's buffer over NVLink
+            key = (B, planes, nvox, feats.C)
+            if getattr(self, "_peer_key", None) != key:
+                self._peer = lt_dist.PeerExchange(plan, pg, B, planes, nvox, feats.C, dev)
+                self._peer_key = key
+            px = self._peer
+            px.barrier()      # every owner has finished reducing the previous step's slots
+            capi.unproject_push(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None,
+                                px.peer_ptrs, plan.view_rank, agg)
+            px.barrier()      # all pushes of the group have landed
+            Bl = B // plan.group_size
+            vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
+            capi.unproject_reduce_finalize(px.buf, plan.group_size, vol.data, vol.fmt, Bl, feats.C, nvox, agg)
+        else:
+            partial = torch.empty((B, planes, nvox, feats.C), dtype=torch.float32, device=dev)
+            capi.unproject_partial(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None, partial, agg)
+            mine = lt_dist.complete_partials(partial, plan, pg, collective, "max" if m.volume_aggregation_method == "max" else "sum")
+            Bl = mine.shape[0]
+            vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
+            capi.unproject_finalize(mine.contiguous(), vol.data, vol.fmt, Bl, feats.C, nvox, agg)
         self.launches += 3
         logits = self.v2v(vol)
         own = plan.owned_samples(B)
