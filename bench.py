@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--image", type=int, default=384)
     ap.add_argument("--volume", type=int, default=64)
     ap.add_argument("--layers", type=int, default=152)
-    ap.add_argument("--collective", default="all_reduce", choices=["all_reduce", "reduce_scatter", "p2p"],
+    ap.add_argument("--collective", default="features", choices=["all_reduce", "reduce_scatter", "p2p", "features"],
                     help="view-group exchange: one NCCL all-reduce (contract), reduce-scatter, or the fused P2P-store kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-calibrate", action="store_true", help="keep PyTorch default init (faster start, degenerate signal)")
@@ -188,14 +188,15 @@ def main_native(args, rank, world, local_rank):
         images_dev = images.to(dev)
         proj, base, position, stepv, rots, _ = model._host_geometry(batch, Bg, (S, S), (S // 4, S // 4))
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-        geo = (up(proj[:, views]), up(position), up(base), up(stepv), up(rots.reshape(Bg, 9)))
+        geo = (up(proj[:, views]), up(position), up(base), up(stepv), up(rots.reshape(Bg, 9)), up(proj))
         parallelism = "view-sharded: %d group(s) x %d ranks, %d view(s)/rank, packed num/den %s, V2V batch-sharded" % (
             plan.n_groups, plan.group_size, len(views),
             "stored into the owner rank by the unprojection kernel over NVLink peer memory" if args.collective == "p2p"
-            else args.collective + " over NCCL")
+            else ("replaced by a feature-map exchange over NVLink peer memory (unprojection on the owner)" if args.collective == "features"
+                  else args.collective + " over NCCL"))
 
         def step(img):
-            return eng.forward_view_sharded(img, geo[0], geo[1], geo[2], geo[3], geo[4], plan, pg, args.collective)[0]
+            return eng.forward_view_sharded(img, geo[0], geo[1], geo[2], geo[3], geo[4], plan, pg, args.collective, proj_all=geo[5])[0]
     h2d = images.numel() * 4
 
     with torch.no_grad():

@@ -438,7 +438,8 @@ class NativeEngine:
         features = feats.data.view(B, V, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
         return keypoints, features, volumes, coord
 
-    def forward_view_sharded(self, images_local, proj_local, position, center, step, rot, plan, pg, collective="all_reduce"):
+    def forward_view_sharded(self, images_local, proj_local, position, center, step, rot, plan, pg, collective="all_reduce",
+                             proj_all=None):
         """Multi-GPU step of one rank (see dist.py): this rank's views of the group's batch in, all keypoints out.
 
         images_local (B, V_local, 3, H, W), proj_local (B, V_local, 3, 4); the other inputs cover all B samples.
@@ -458,7 +459,24 @@ class NativeEngine:
         feats = self.backbone_features(images_local.reshape(B * Vl, *images_local.shape[2:]))
         agg = capi.AGG[m.volume_aggregation_method]
         planes = 2 if m.volume_aggregation_method == "softmax" else 1
-        if collective == "p2p" and plan.group_size > 1:
+        if collective == "features" and plan.group_size > 1:
+            # exchange feature maps (14x fewer bytes than voxel partials), then unproject all views of the owned samples
+            assert proj_all is not None, "collective='features' needs the projection matrices of all views"
+            V = plan.n_views
+            key = ("feat", B, V, feats.H, feats.W, feats.C)
+            if getattr(self, "_peer_key", None) != key:
+                self._peer = lt_dist.FeatureExchange(plan, pg, B, V, feats.H, feats.W, feats.C, dev)
+                self._peer_key = key
+            fx = self._peer
+            fx.barrier()
+            fx.scatter(feats.data.view(B, Vl, feats.H, feats.W, feats.C))
+            fx.barrier()
+            own = plan.owned_samples(B)
+            Bl = len(own)
+            vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
+            capi.unproject_aggregate(fx.buf, proj_all[own[0]:own[-1] + 1].contiguous(),
+                                     coord[own[0]:own[-1] + 1].reshape(Bl, nvox, 3), None, vol.data, vol.fmt, agg)
+        elif collective == "p2p" and plan.group_size > 1:
             # fused unprojection + exchange: partials are stored straight into the owner's buffer over NVLink
             key = (B, planes, nvox, feats.C)
             if getattr(self, "_peer_key", None) != key:

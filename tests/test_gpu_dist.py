@@ -42,10 +42,10 @@ def _worker(rank, world, port, ret):
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
             vs = plan.views
             errs = {}
-            for coll in ("all_reduce", "reduce_scatter", "p2p"):
+            for coll in ("all_reduce", "reduce_scatter", "p2p", "features"):
                 try:
                     kp = model.engine().forward_view_sharded(images[:, vs].contiguous().to(dev), up(proj[:, vs]), up(position), up(base),
-                                                             up(step), up(rots.reshape(B, 9)), plan, pg, coll)[0]
+                                                             up(step), up(rots.reshape(B, 9)), plan, pg, coll, proj_all=up(proj))[0]
                     torch.cuda.synchronize()
                     errs[coll] = float((kp - kp_single).abs().max())
                 except Exception as e:   # report, do not hang the other rank
