@@ -15,6 +15,7 @@
 // Algorithmic bytes per sample (V=4, C=32, 96x96 maps, 64^3 voxels, fp32 out):
 //   33.55 MB volume write + 4.72 MB feature read (compulsory) + 3.15 MB coordinate read = 41.42 MB.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace lt {
 
@@ -265,20 +266,21 @@ __global__ void __launch_bounds__(256) unproject_kernel(const UnprojParams p) {
 // (lane j builds the taps of view j and the group shares them with width-G shuffles), per-view samples
 // stay in registers and the view softmax is one pass (max, then exp once: num = sum s*e, den = sum e).
 // ------------------------------------------------------------------------------------------------
-template <int G, int MAXV>
+template <int G, int MAXV, int CPL>   // CPL channels per lane (4 or 8): C = CPL * G
 __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams p) {
   __shared__ float sP[kMaxStoredViews * 12];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < p.V * 12; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
   __syncthreads();
 
-  constexpr int C = 4 * G;
+  constexpr int C = CPL * G;
+  constexpr int NQ = CPL / 4;
   const int sub = threadIdx.x % G;
   const int slot = threadIdx.x / G;
   constexpr int VPB = 256 / G;
   const long map_elems = (long)p.h * p.w * C;
-  const float* fbase = p.features + (long)b * p.V * map_elems + sub * 4;
-  const int c0 = sub * 4;
+  const float* fbase = p.features + (long)b * p.V * map_elems + sub * CPL;
+  const int c0 = sub * CPL;
   const int wm = p.w - 1, hm = p.h - 1;
 
   // block-uniform trip count: the width-G shuffles below need every lane of the warp present
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
     const long vox = live ? vbase + slot : p.nvox - 1;
     const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
     const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
-    float s[MAXV][4];
+    float s[MAXV][CPL];
 #pragma unroll
     for (int v0 = 0; v0 < MAXV; v0 += G) {
       if (v0 >= p.V) break;
@@ -308,73 +310,82 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
           const float fx = __shfl_sync(0xffffffffu, fx_m, j, G);
           const float fy = __shfl_sync(0xffffffffu, fy_m, j, G);
           const unsigned mask = __shfl_sync(0xffffffffu, mask_m, j, G);
-          // unconditional, clamped loads (independent -> all 4 taps of all views in flight); invalid taps get weight 0
+          // unconditional, clamped loads (independent -> all taps of all views in flight); invalid taps get weight 0
           const int x0 = min(max(xi, 0), wm), x1 = min(max(xi + 1, 0), wm);
           const int y0 = min(max(yi, 0), hm), y1 = min(max(yi + 1, 0), hm);
           const float* f = fbase + (long)v * map_elems;
-          const float4 q00 = __ldg(reinterpret_cast<const float4*>(f + (long)(y0 * p.w + x0) * C));
-          const float4 q01 = __ldg(reinterpret_cast<const float4*>(f + (long)(y0 * p.w + x1) * C));
-          const float4 q10 = __ldg(reinterpret_cast<const float4*>(f + (long)(y1 * p.w + x0) * C));
-          const float4 q11 = __ldg(reinterpret_cast<const float4*>(f + (long)(y1 * p.w + x1) * C));
+          const float* f00 = f + (long)(y0 * p.w + x0) * C;
+          const float* f01 = f + (long)(y0 * p.w + x1) * C;
+          const float* f10 = f + (long)(y1 * p.w + x0) * C;
+          const float* f11 = f + (long)(y1 * p.w + x1) * C;
+          float4 q00[NQ], q01[NQ], q10[NQ], q11[NQ];
+#pragma unroll
+          for (int qd = 0; qd < NQ; ++qd) {
+            q00[qd] = __ldg(reinterpret_cast<const float4*>(f00) + qd);
+            q01[qd] = __ldg(reinterpret_cast<const float4*>(f01) + qd);
+            q10[qd] = __ldg(reinterpret_cast<const float4*>(f10) + qd);
+            q11[qd] = __ldg(reinterpret_cast<const float4*>(f11) + qd);
+          }
           const float gx = 1.0f - fx, gy = 1.0f - fy;
           const float w00 = (mask & 1u) ? gx * gy : 0.0f, w01 = (mask & 2u) ? fx * gy : 0.0f;
           const float w10 = (mask & 4u) ? gx * fy : 0.0f, w11 = (mask & 8u) ? fx * fy : 0.0f;
-          s[v][0] = fmaf(q11.x, w11, fmaf(q10.x, w10, fmaf(q01.x, w01, q00.x * w00)));
-          s[v][1] = fmaf(q11.y, w11, fmaf(q10.y, w10, fmaf(q01.y, w01, q00.y * w00)));
-          s[v][2] = fmaf(q11.z, w11, fmaf(q10.z, w10, fmaf(q01.z, w01, q00.z * w00)));
-          s[v][3] = fmaf(q11.w, w11, fmaf(q10.w, w10, fmaf(q01.w, w01, q00.w * w00)));
+#pragma unroll
+          for (int qd = 0; qd < NQ; ++qd) {
+            s[v][qd * 4 + 0] = fmaf(q11[qd].x, w11, fmaf(q10[qd].x, w10, fmaf(q01[qd].x, w01, q00[qd].x * w00)));
+            s[v][qd * 4 + 1] = fmaf(q11[qd].y, w11, fmaf(q10[qd].y, w10, fmaf(q01[qd].y, w01, q00[qd].y * w00)));
+            s[v][qd * 4 + 2] = fmaf(q11[qd].z, w11, fmaf(q10[qd].z, w10, fmaf(q01[qd].z, w01, q00[qd].z * w00)));
+            s[v][qd * 4 + 3] = fmaf(q11[qd].w, w11, fmaf(q10[qd].w, w10, fmaf(q01[qd].w, w01, q00[qd].w * w00)));
+          }
         }
       }
     }
 
-    float o[4], o2[4];
+    float o[CPL], o2[CPL];
     if (p.agg == LT_AGG_SOFTMAX) {
       if (p.partial) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { o[i] = 0.f; o2[i] = 0.f; }
+        for (int i = 0; i < CPL; ++i) { o[i] = 0.f; o2[i] = 0.f; }
 #pragma unroll
         for (int v = 0; v < MAXV; ++v)
           if (v < p.V) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float e = __expf(s[v][i]); o[i] = fmaf(s[v][i], e, o[i]); o2[i] += e; }
+            for (int i = 0; i < CPL; ++i) { const float e = __expf(s[v][i]); o[i] = fmaf(s[v][i], e, o[i]); o2[i] += e; }
           }
       } else {
-        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int v = 0; v < MAXV; ++v)
-          if (v < p.V) {
+        for (int i = 0; i < CPL; ++i) {
+          float m = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) m[i] = fmaxf(m[i], s[v][i]);
-          }
-        float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int v = 0; v < MAXV; ++v) if (v < p.V) m = fmaxf(m, s[v][i]);
+          float num = 0.f, den = 0.f;
 #pragma unroll
-        for (int v = 0; v < MAXV; ++v)
-          if (v < p.V) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const float e = __expf(s[v][i] - m[i]); num[i] = fmaf(s[v][i], e, num[i]); den[i] += e; }
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = num[i] / den[i];
+          for (int v = 0; v < MAXV; ++v)
+            if (v < p.V) { const float e = __expf(s[v][i] - m); num = fmaf(s[v][i], e, num); den += e; }
+          o[i] = num / den;
+        }
       }
     } else if (p.agg == LT_AGG_MAX) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = -INFINITY;
+      for (int i = 0; i < CPL; ++i) o[i] = -INFINITY;
 #pragma unroll
       for (int v = 0; v < MAXV; ++v)
         if (v < p.V) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], s[v][i]);
+          for (int i = 0; i < CPL; ++i) o[i] = fmaxf(o[i], s[v][i]);
         }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = 0.f;
+      for (int i = 0; i < CPL; ++i) o[i] = 0.f;
 #pragma unroll
       for (int v = 0; v < MAXV; ++v)
         if (v < p.V) {
-          float cf[4] = {1.f, 1.f, 1.f, 1.f};
-          if (p.agg == LT_AGG_CONF) load_vec<4>(p.conf + ((long)b * p.V + v) * C + c0, cf);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = fmaf(s[v][i], cf[i], o[i]);
+          for (int qd = 0; qd < NQ; ++qd) {
+            float cf[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.agg == LT_AGG_CONF) load_vec<4>(p.conf + ((long)b * p.V + v) * C + c0 + qd * 4, cf);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[qd * 4 + i] = fmaf(s[v][qd * 4 + i], cf[i], o[qd * 4 + i]);
+          }
         }
     }
 
@@ -388,10 +399,17 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
       } else {
         d0 = reinterpret_cast<float*>(p.out) + (((long)b * planes) * p.nvox + vox) * C + c0;
       }
-      *reinterpret_cast<float4*>(d0) = make_float4(o[0], o[1], o[2], o[3]);
-      if (planes == 2) *reinterpret_cast<float4*>(d0 + p.nvox * C) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+#pragma unroll
+      for (int qd = 0; qd < NQ; ++qd) {
+        reinterpret_cast<float4*>(d0)[qd] = make_float4(o[qd * 4], o[qd * 4 + 1], o[qd * 4 + 2], o[qd * 4 + 3]);
+        if (planes == 2) reinterpret_cast<float4*>(d0 + p.nvox * C)[qd] = make_float4(o2[qd * 4], o2[qd * 4 + 1], o2[qd * 4 + 2], o2[qd * 4 + 3]);
+      }
     } else {
-      store_out<4>(p, b, vox, c0, o);
+#pragma unroll
+      for (int qd = 0; qd < NQ; ++qd) {
+        const float oq[4] = {o[qd * 4], o[qd * 4 + 1], o[qd * 4 + 2], o[qd * 4 + 3]};
+        store_out<4>(p, b, vox, c0 + qd * 4, oq);
+      }
     }
   }
 }
@@ -447,7 +465,7 @@ static int launch_unproject(const float* features, const float* proj, const floa
   for (int i = 0; i < 8; ++i) p.peer[i] = (peers && i < n_peers) ? peers[i] : nullptr;
   if (partial == 2) {
     LT_REQUIRE(peers && n_peers >= 1 && n_peers <= 8 && B % n_peers == 0, "unproject_push: need 1..8 peers dividing the batch");
-    LT_REQUIRE(C % 4 == 0 && C / 4 <= 32 && ((C / 4) & (C / 4 - 1)) == 0 && V <= kMaxStoredViews, "unproject_push: unsupported shape");
+    LT_REQUIRE(C % 4 == 0 && C <= 128 && ((C / 4) & (C / 4 - 1)) == 0 && V <= kMaxStoredViews, "unproject_push: unsupported shape");
     p.samples_per_owner = B / n_peers;
   }
   const bool vec4 = (C % 4 == 0);
@@ -462,18 +480,38 @@ static int launch_unproject(const float* features, const float* proj, const floa
   dim3 grid((unsigned)blocks, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool stored = V <= kMaxStoredViews;
-  if (vec4 && stored && units == G && C <= 128) {   // C = 4*G exactly: one float4 per lane per tap
-#define LT_UNPROJ_FAST(GG)                                                              \
-    if (V <= 2) unproject_fast_kernel<GG, 2><<<grid, 256, 0, st>>>(p);                  \
-    else if (V <= 4) unproject_fast_kernel<GG, 4><<<grid, 256, 0, st>>>(p);             \
-    else unproject_fast_kernel<GG, 8><<<grid, 256, 0, st>>>(p)
-    switch (G) {
-      case 1: LT_UNPROJ_FAST(1); break;
-      case 2: LT_UNPROJ_FAST(2); break;
-      case 4: LT_UNPROJ_FAST(4); break;
-      case 8: LT_UNPROJ_FAST(8); break;
-      case 16: LT_UNPROJ_FAST(16); break;
-      default: LT_UNPROJ_FAST(32); break;
+  const bool pow2q = (units & (units - 1)) == 0;
+  if (vec4 && stored && pow2q && C <= 128) {
+    // C = 8*G' (two float4 per lane per tap: half the per-lane ray/weight overhead) when possible, else C = 4*G
+#define LT_UNPROJ_FAST(GG, CPL)                                                             \
+    if (V <= 2) unproject_fast_kernel<GG, 2, CPL><<<grid, 256, 0, st>>>(p);                 \
+    else if (V <= 4) unproject_fast_kernel<GG, 4, CPL><<<grid, 256, 0, st>>>(p);            \
+    else unproject_fast_kernel<GG, 8, CPL><<<grid, 256, 0, st>>>(p)
+    // (measured on B200: the 8-channel-per-lane variant halves the per-lane ray/weight overhead but drops occupancy to
+    //  2 CTAs/SM and is 45 % slower at C = 32, so it is only used on request)
+    static const bool wide_lanes = getenv("LT_UNPROJECT_CPL8") != nullptr;
+    if (wide_lanes && C % 8 == 0) {
+      p.G = C / 8;
+      const int vpb8 = 256 / p.G;
+      long blocks8 = (nvox + vpb8 - 1) / vpb8;
+      if (blocks8 > (long)sm_count() * 8) blocks8 = (long)sm_count() * 8;
+      grid.x = (unsigned)blocks8;
+      switch (p.G) {
+        case 1: LT_UNPROJ_FAST(1, 8); break;
+        case 2: LT_UNPROJ_FAST(2, 8); break;
+        case 4: LT_UNPROJ_FAST(4, 8); break;
+        case 8: LT_UNPROJ_FAST(8, 8); break;
+        default: LT_UNPROJ_FAST(16, 8); break;
+      }
+    } else {
+      switch (G) {
+        case 1: LT_UNPROJ_FAST(1, 4); break;
+        case 2: LT_UNPROJ_FAST(2, 4); break;
+        case 4: LT_UNPROJ_FAST(4, 4); break;
+        case 8: LT_UNPROJ_FAST(8, 4); break;
+        case 16: LT_UNPROJ_FAST(16, 4); break;
+        default: LT_UNPROJ_FAST(32, 4); break;
+      }
     }
 #undef LT_UNPROJ_FAST
   } else if (vec4) {
