@@ -171,6 +171,21 @@ int lt_maxpool_fwd(const void* in, void* out, int format, int N, int ID, int IH,
                    int OD, int OH, int OW, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Algebraic-triangulation path and confidence heads (config #5).
+ * ---------------------------------------------------------------------------------------- */
+/* tail of GlobalAveragePoolingHead (pose_resnet.py:163-174): mean over the P positions of a channels-last map
+ * [N][P][C0] (either format), Linear(C0,H1)+ReLU, Linear(H1,H2)+ReLU, Linear(H2,NO)+Sigmoid; nn.Linear weight layout. */
+int lt_gap_mlp3_fwd(const void* in, int format, int N, int P, int C0, int H1, int H2, int NO, const float* w1,
+                    const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, float* out,
+                    void* stream);
+/* conf[B][V][C] <- conf / sum_v conf + eps   (triangulation.py:173-174 with eps = 1e-5; :268-269 with eps = 0) */
+int lt_view_normalize_fwd(float* conf, int B, int V, int C, float eps, void* stream);
+/* confidence-weighted DLT (multiview.py:141-183): proj [B][V][3][4], keypoints_2d [B][V][J][2], confidences [B][V][J] or
+ * NULL -> out [B][J][3]; float64 A^T A + Jacobi eigen-solve per (sample, joint). */
+int lt_triangulate_dlt_fwd(const float* proj, const float* keypoints_2d, const float* confidences, float* out, int B,
+                           int V, int J, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layout / format helpers.
  * ---------------------------------------------------------------------------------------- */
 /* images [N][C][H][W] float32 -> [N][H][W][Cp] float32, channels >= C zero filled */

@@ -56,6 +56,9 @@ SIGNATURES = {
     "lt_conv_fold_weight_bytes": (c_size_t, [c_int, c_int]),
     "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
+    "lt_gap_mlp3_fwd": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p] * 7 + [c_void_p]),
+    "lt_view_normalize_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "lt_triangulate_dlt_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "lt_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "lt_stem_s2d_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "lt_f32_to_s32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
@@ -185,6 +188,21 @@ def conv_fold_pack_weights(w_tap_ci_co, packed, k, cout):
 def maxpool(inp, out, fmt, N, ID, IH, IW, C, k, s, p, OD, OH, OW):
     _check(lib().lt_maxpool_fwd(_ptr(inp), _ptr(out), fmt, N, ID, IH, IW, C, k[0], k[1], k[2], s[0], s[1], s[2],
                                 p[0], p[1], p[2], OD, OH, OW, _stream()), "lt_maxpool_fwd")
+
+
+def gap_mlp3(inp, fmt, N, P, C0, lin1, lin2, lin3, out):
+    """lin*: (weight [out][in], bias) float32 CUDA tensors."""
+    _check(lib().lt_gap_mlp3_fwd(_ptr(inp), fmt, N, P, C0, lin1[0].shape[0], lin2[0].shape[0], lin3[0].shape[0], _ptr(lin1[0]), _ptr(lin1[1]),
+                                 _ptr(lin2[0]), _ptr(lin2[1]), _ptr(lin3[0]), _ptr(lin3[1]), _ptr(out), _stream()), "lt_gap_mlp3_fwd")
+
+
+def view_normalize(conf, B, V, C, eps):
+    _check(lib().lt_view_normalize_fwd(_ptr(conf), B, V, C, float(eps), _stream()), "lt_view_normalize_fwd")
+
+
+def triangulate_dlt(proj, kp2d, conf, out):
+    B, V, J = kp2d.shape[:3]
+    _check(lib().lt_triangulate_dlt_fwd(_ptr(proj), _ptr(kp2d), _ptr(conf), _ptr(out), B, V, J, _stream()), "lt_triangulate_dlt_fwd")
 
 
 def nchw_to_nhwc(inp, out, N, C, H, W, Cp):

@@ -231,6 +231,19 @@ class NativeEngine:
                         P[key + ".ds"] = self._pack_conv(unit.downsample[0], unit.downsample[1])
             for i in (0, 3, 6):
                 P["deconv%d" % i] = self._pack_deconv2d_k4s2(bb.deconv_layers[i], bb.deconv_layers[i + 1])
+            # 17-channel heatmap head: only the algebraic model evaluates it (the volumetric forward uses its shape only)
+            P["final"] = self._pack_conv(bb.final_layer, None, out_fmt=FMT_F32)
+            for head_name in ("alg_confidences", "vol_confidences"):
+                if hasattr(bb, head_name):
+                    head = getattr(bb, head_name)
+                    P[head_name + ".c0"] = self._pack_conv(head.features[0], head.features[1])
+                    P[head_name + ".c1"] = self._pack_conv(head.features[4], head.features[5])
+                    P[head_name + ".mlp"] = [(head.head[i].weight.detach().float().contiguous(), head.head[i].bias.detach().float().contiguous())
+                                             for i in (0, 2, 4)]
+            if not hasattr(m, "volume_net"):
+                self._packs, self._packs_version = P, ver
+                self._graphs = {}
+                return
             P["process_features"] = self._pack_conv(m.process_features[0], None, out_fmt=FMT_F32)
             v = m.volume_net
             pad16 = 32 if self.mode != "simt" else None   # the 16-channel tensor is stored 32 wide in split-fp16
@@ -340,13 +353,41 @@ class NativeEngine:
         return self._conv(y, P[name + ".b"], relu=True, residual=skip, res_mode=RES_BEFORE_RELU)
 
     # ------------------------------------------------------------------ network stages
-    def backbone_features(self, images_nchw):
+    def backbone_features(self, images_nchw, return_trunk=False):
         """(BV, 3, H, W) float32 -> processed features, channels-last float32 Act (BV, 1, h, w, 32).
 
         = backbone trunk + deconvs (pose_resnet.py:293-313) + process_features (triangulation.py:344-346).
         The 17-channel heatmap head (final_layer) is not evaluated: the volumetric forward uses it
         only for its shape (triangulation.py:257,264-265).
         """
+        trunk = self.backbone_trunk(images_nchw)
+        feats = self._conv(self.backbone_upsample(trunk), self._packs["process_features"], relu=False, out_fmt=FMT_F32)
+        return (feats, trunk) if return_trunk else feats
+
+    def backbone_upsample(self, x):
+        """trunk output -> 256-channel features at 1/4 resolution (three k4 s2 transposed convs + BN + ReLU)."""
+        for i in (0, 3, 6):
+            x = self._deconv2d(x, self._packs["deconv%d" % i])
+        return x
+
+    def confidence_head(self, trunk, name):
+        """GlobalAveragePoolingHead (pose_resnet.py:140-174) on the trunk output -> float32 (BV, n_classes).
+
+        conv3x3+BN, MaxPool2, ReLU, twice (ReLU and max commute, so ReLU is fused into the conv epilogue), then the
+        global-average-pool + 3-layer MLP + sigmoid tail in one small kernel."""
+        P = self._packs
+        x = self._conv(trunk, P[name + ".c0"], relu=True)
+        x = self._maxpool(x, (1, 2, 2), (1, 2, 2), (0, 0, 0))
+        x = self._conv(x, P[name + ".c1"], relu=True)
+        x = self._maxpool(x, (1, 2, 2), (1, 2, 2), (0, 0, 0))
+        lin = P[name + ".mlp"]
+        out = torch.empty((x.N, lin[2][0].shape[0]), dtype=torch.float32, device=x.data.device)
+        capi.gap_mlp3(x.data, x.fmt, x.N, x.D * x.H * x.W, x.C, lin[0], lin[1], lin[2], out)
+        self.launches += 1
+        return out
+
+    def backbone_trunk(self, images_nchw):
+        """(BV, 3, H, W) float32 -> trunk output Act (BV, 1, H/32, W/32, 512*expansion) (pose_resnet.py:293-302)."""
         P = self._packs
         bv, c, H, W = images_nchw.shape
         dev = images_nchw.device
@@ -371,9 +412,7 @@ class NativeEngine:
                 for si in range(n_st - 1):
                     y = self._conv(y, P["%s.c%d" % (key, si)], relu=True)
                 x = self._conv(y, P["%s.c%d" % (key, n_st - 1)], relu=True, residual=identity, res_mode=RES_BEFORE_RELU)
-        for i in (0, 3, 6):
-            x = self._deconv2d(x, P["deconv%d" % i])
-        return self._conv(x, P["process_features"], relu=False, out_fmt=FMT_F32)
+        return x
 
     def unproject(self, feats, B, V, proj, coord, agg, conf=None):
         """feats: Act (B*V, 1, h, w, C) float32 -> volume Act (B, n, n, n, C) in the conv operand format."""
@@ -429,7 +468,14 @@ class NativeEngine:
         coord = torch.empty((B, n, n, n, 3), dtype=torch.float32, device=dev)
         capi.coord_volume(position, center, step, rot, coord, m.transfer_cmu_to_human36m)
         self.launches += 1
-        feats = self.backbone_features(images.reshape(B * V, *images.shape[2:]))
+        need_conf = m.volume_aggregation_method.startswith("conf")
+        feats, trunk = self.backbone_features(images.reshape(B * V, *images.shape[2:]), return_trunk=True)
+        if need_conf:
+            conf = self.confidence_head(trunk, "vol_confidences").view(B, V, -1)          # triangulation.py:253-261
+            if m.volume_aggregation_method == "conf_norm":
+                capi.view_normalize(conf, B, V, conf.shape[2], 0.0)                        # :268-269
+                self.launches += 1
+        del trunk
         agg = capi.AGG[m.volume_aggregation_method]
         vol = self.unproject(feats, B, V, proj, coord, agg, conf)
         logits = self.v2v(vol)

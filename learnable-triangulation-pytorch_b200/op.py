@@ -63,3 +63,19 @@ def integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax=True, b
     ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=volumes.device)
     capi.softargmax3d(logits, J * nvox, 1, nvox, coord, out, keypoints, ws, B, J, nvox, 1.0, softmax)
     return keypoints, out
+
+
+def integrate_tensor_2d(heatmaps, softmax=True, backend=None):
+    """Drop-in for reference op.py:11-47: (B, J, h, w) -> coordinates (B, J, 2) [x, y in pixels], normalised heatmaps."""
+    if _resolve_backend(backend, heatmaps) == "torch" or not softmax:
+        return torch_ops.integrate_tensor_2d(heatmaps, softmax)
+    B, J, h, w = heatmaps.shape
+    dev = heatmaps.device
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+    grid = torch.stack([xs, ys, torch.zeros_like(xs)], dim=-1).reshape(1, h * w, 3).expand(B, h * w, 3).contiguous()
+    logits = heatmaps.float().contiguous()
+    out = torch.empty_like(logits)
+    kp = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, h * w) // 4 + 1, dtype=torch.float32, device=dev)
+    capi.softargmax3d(logits, J * h * w, 1, h * w, grid, out, kp, ws, B, J, h * w, 1.0, True)
+    return kp[:, :, :2].contiguous(), out

@@ -146,3 +146,60 @@ def randomize_weights(model, seed=0, calib_size=64, calib_views=2, feat_gain=4.0
     model_cpu.volume_net.output_layer.weight.mul_(2.5 / float(logits.std()))
     model_cpu.eval()
     return model_cpu.to(dev)
+
+
+def make_alg_config(num_layers=152, use_confidences=True, heatmap_multiplier=100.0, num_joints=17):
+    """The `model:` section of experiments/human36m/*/human36m_alg.yaml with init_weights off."""
+    return AttrDict({
+        "image_shape": [384, 384],
+        "model": {"name": "alg", "init_weights": False, "use_confidences": use_confidences,
+                  "heatmap_multiplier": heatmap_multiplier, "heatmap_softmax": True,
+                  "backbone": {"name": "resnet%d" % num_layers, "style": "simple", "init_weights": False,
+                               "num_joints": num_joints, "num_layers": num_layers}},
+    })
+
+
+def image_projections(batch):
+    """(B, V, 3, 4) float32 image-space projection matrices of a make_batch() dict (datasets/utils.py:61-63)."""
+    from .multiview import stack_projections
+    return stack_projections(batch["cameras"])
+
+
+@torch.no_grad()
+def randomize_backbone_weights(model, seed=0, calib_size=128, calib_images=4, branch_gain=0.2, heat_spread=3.0):
+    """Seeded well-conditioned weights for a model that only has `.backbone` (algebraic model): same recipe as
+    randomize_weights; the heatmap head is rescaled so that heatmaps * heatmap_multiplier has a spread of ~3."""
+    g = torch.Generator().manual_seed(seed)
+    dev = next(model.parameters()).device
+    m = model.to("cpu")
+    bb = m.backbone
+    for mod in bb.modules():
+        if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+            fan_in = mod.weight[0].numel() if isinstance(mod, nn.Conv2d) else mod.weight.shape[0] * mod.weight[0, 0].numel() / 4
+            mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
+            if mod.bias is not None:
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.05)
+        if isinstance(mod, nn.Linear):
+            mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * (1.0 / mod.weight.shape[1]) ** 0.5)
+            mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.3)
+    last = {u.stages()[-1][1] for u in bb.modules() if hasattr(u, "stages")}
+    bns = [x for x in bb.modules() if isinstance(x, nn.BatchNorm2d)]
+    for x in bns:
+        lo, hi = (branch_gain * 0.5, branch_gain * 1.5) if x in last else (0.75, 1.25)
+        x.weight.copy_(torch.rand(x.weight.shape, generator=g) * (hi - lo) + lo)
+        x.bias.copy_(torch.randn(x.bias.shape, generator=g) * 0.2)
+        x.momentum = 1.0
+        x.train()
+    heat, _, _, _ = bb(torch.randn(calib_images, 3, calib_size, calib_size, generator=g))
+    for x in bns:
+        x.momentum = BN_MOMENTUM
+        x.eval()
+        x.running_var.clamp_(min=1e-3)
+    scale = heat_spread / (float(heat.std()) * float(m.heatmap_multiplier))
+    bb.final_layer.weight.mul_(scale)
+    bb.final_layer.bias.mul_(scale)
+    m.eval()
+    return m.to(dev)
+
+
+BN_MOMENTUM = 0.1

@@ -70,3 +70,32 @@ def integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax=True):
     flat = torch.softmax(flat, dim=2) if softmax else F.relu(flat)
     coords = flat @ coord_volumes.reshape(B, -1, 3)
     return coords, flat.reshape(volumes.shape)
+
+
+def integrate_tensor_2d(heatmaps, softmax=True):
+    """Same contract as reference op.py:11-47."""
+    B, J, h, w = heatmaps.shape
+    flat = heatmaps.reshape(B, J, -1)
+    flat = torch.softmax(flat, dim=2) if softmax else F.relu(flat)
+    hm = flat.reshape(B, J, h, w)
+    mass_x, mass_y = hm.sum(dim=2), hm.sum(dim=3)
+    x = (mass_x * torch.arange(w, device=hm.device, dtype=hm.dtype)).sum(dim=2, keepdim=True)
+    y = (mass_y * torch.arange(h, device=hm.device, dtype=hm.dtype)).sum(dim=2, keepdim=True)
+    if not softmax:
+        x = x / mass_x.sum(dim=2, keepdim=True)
+        y = y / mass_y.sum(dim=2, keepdim=True)
+    return torch.cat((x, y), dim=2), hm
+
+
+def triangulate_batch_of_points(proj_matricies_batch, points_batch, confidences_batch=None):
+    """Weighted DLT, batched (reference multiview.py:141-183 loops over samples and joints and calls torch.svd each time)."""
+    B, V, J = points_batch.shape[:3]
+    if confidences_batch is None:
+        confidences_batch = torch.ones(B, V, J, dtype=points_batch.dtype, device=points_batch.device)
+    P = proj_matricies_batch.unsqueeze(2)                                     # (B, V, 1, 3, 4)
+    A = P[..., 2:3, :] * points_batch.unsqueeze(-1) - P[..., :2, :]          # (B, V, J, 2, 4)
+    A = A * confidences_batch.unsqueeze(-1).unsqueeze(-1)
+    A = A.permute(0, 2, 1, 3, 4).reshape(B, J, 2 * V, 4)
+    _, _, vh = torch.linalg.svd(A.double(), full_matrices=False)
+    X = vh[..., 3, :]
+    return (X[..., :3] / X[..., 3:4]).to(points_batch.dtype)

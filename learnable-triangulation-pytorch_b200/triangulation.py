@@ -101,9 +101,6 @@ class VolumetricTriangulationNet(nn.Module):
         if self.training or torch.is_grad_enabled():
             raise RuntimeError("lt_b200 native backend is inference-only: call model.eval() under torch.no_grad(), "
                                "or construct the model with backend='torch' (LT_B200_BACKEND=torch) for training")
-        if self.volume_aggregation_method.startswith("conf"):
-            raise NotImplementedError("conf/conf_norm aggregation needs the vol_confidences head: use backend='torch'")
-
         B, V = images.shape[:2]
         H, W = images.shape[3:]
         hm_shape = (H // 4, W // 4)   # stem /2, maxpool /2, three stride-2 stages, three x2 deconvs
@@ -113,12 +110,14 @@ class VolumetricTriangulationNet(nn.Module):
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=True)
 
-        kp, features, volumes, coord = self.engine().forward(
+        outs = self.engine().forward(
             images.float().contiguous(), up(proj), up(position), up(base), up(step), up(rots.reshape(B, 9)))
         base_points = up(base)
         if self.clone_outputs and self.use_cuda_graph:
-            kp, features, volumes, coord = kp.clone(), features.clone(), volumes.clone(), coord.clone()
-        return kp, features, volumes, None, cuboids, coord, base_points
+            outs = tuple(o.clone() for o in outs)
+        kp, features, volumes, coord = outs[:4]
+        vol_conf = outs[4] if len(outs) > 4 else None
+        return kp, features, volumes, vol_conf, cuboids, coord, base_points
 
     def _forward_torch(self, images, batch):
         dev = images.device
@@ -150,3 +149,57 @@ class VolumetricTriangulationNet(nn.Module):
         volumes = self.volume_net(volumes)
         kp, volumes = torch_ops.integrate_tensor_3d_with_coordinates(volumes * self.volume_multiplier, coord, self.volume_softmax)
         return kp, features, volumes, vol_conf, cuboids, coord, cen_t
+
+
+class AlgebraicTriangulationNet(nn.Module):
+    """Drop-in for reference mvn/models/triangulation.py:131-200 (BASELINE config #5): backbone heatmaps -> 2-D
+    soft-argmax -> confidence-weighted DLT.  Same ctor keys (`config.model.use_confidences`, `heatmap_softmax`,
+    `heatmap_multiplier`, `backbone.*`), same config side effects, same 4-tuple."""
+
+    def __init__(self, config, device="cuda:0", backend=None, conv_mode=None):
+        super().__init__()
+        self.use_confidences = config.model.use_confidences
+        config.model.backbone.alg_confidences = False
+        config.model.backbone.vol_confidences = False
+        if self.use_confidences:
+            config.model.backbone.alg_confidences = True
+        self.backbone = pose_resnet.get_pose_net(config.model.backbone, device=device)
+        self.heatmap_softmax = config.model.heatmap_softmax
+        self.heatmap_multiplier = config.model.heatmap_multiplier
+        self.backend = backend or os.environ.get("LT_B200_BACKEND", "native")
+        self.conv_mode = conv_mode or os.environ.get("LT_B200_CONV", "tc")
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import NativeEngine
+            self._engine = NativeEngine(self, mode=self.conv_mode, use_graph=False)
+        return self._engine
+
+    def forward(self, images, proj_matricies, batch):
+        if self.backend == "torch":
+            return self._forward_torch(images, proj_matricies)
+        if not images.is_cuda:
+            raise RuntimeError("lt_b200 native backend needs CUDA tensors; construct the model with backend='torch' for CPU/autograd")
+        if self.training or torch.is_grad_enabled():
+            raise RuntimeError("lt_b200 native backend is inference-only: use model.eval() under torch.no_grad(), or backend='torch'")
+        if not self.heatmap_softmax:
+            raise NotImplementedError("heatmap_softmax=False (ReLU mass normalisation) is only available with backend='torch'")
+        return self.engine().algebraic_forward(images.float().contiguous(), proj_matricies.float().contiguous(),
+                                               self.heatmap_multiplier, self.use_confidences)
+
+    def _forward_torch(self, images, proj_matricies):
+        B, V = images.shape[:2]
+        heatmaps, _, alg_conf, _ = self.backbone(images.reshape(-1, *images.shape[2:]))
+        if not self.use_confidences:
+            alg_conf = torch.ones(B * V, heatmaps.shape[1], dtype=torch.float, device=images.device)
+        kp2d, heatmaps = op.integrate_tensor_2d(heatmaps * self.heatmap_multiplier, self.heatmap_softmax, backend="torch")
+        heatmaps = heatmaps.view(B, V, *heatmaps.shape[1:])
+        kp2d = kp2d.view(B, V, *kp2d.shape[1:])
+        alg_conf = alg_conf.view(B, V, -1)
+        alg_conf = alg_conf / alg_conf.sum(dim=1, keepdim=True) + 1e-5
+        h, w = heatmaps.shape[3:]
+        H, W = images.shape[3:]
+        kp2d = kp2d * torch.tensor([W / w, H / h], device=images.device, dtype=kp2d.dtype)
+        kp3d = multiview.triangulate_batch_of_points(proj_matricies, kp2d, confidences_batch=alg_conf, backend="torch")
+        return kp3d, kp2d, heatmaps, alg_conf

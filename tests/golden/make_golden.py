@@ -105,6 +105,27 @@ def gen_forward():
     print("forward_r50: max prob", float(flat.max()), "uniform", 1.0 / n ** 3, "kp spread", kp.std(dim=1))
 
 
+def gen_algebraic():
+    """AlgebraicTriangulationNet (config #5 flavour): B=2, V=4, 128x128, ResNet-50, with confidences."""
+    from mvn.models.triangulation import AlgebraicTriangulationNet as RefAlg
+    B, V, S = 2, 4, 128
+    mine = lt_b200.AlgebraicTriangulationNet(testing.make_alg_config(num_layers=50), device="cpu", backend="torch")
+    testing.randomize_backbone_weights(mine, seed=5, calib_size=S)
+    sd = mine.state_dict()
+    ref = RefAlg(testing.make_alg_config(num_layers=50), device="cpu")
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    images, batch = testing.make_batch(B, V, image_size=S, seed=9, camera_cls=ref_multiview.Camera)
+    proj = torch.from_numpy(testing.image_projections(batch))
+    with torch.no_grad():
+        kp3d, kp2d, heat, conf = ref(images, proj, batch)
+    out = {"sd_checksum": np.array([float(sum(v.double().abs().sum() for v in sd.values()))]),
+           "proj": proj.numpy(), "keypoints_3d": kp3d.numpy(), "keypoints_2d": kp2d.numpy(), "confidences": conf.numpy(),
+           "heatmaps_sub": heat[:, :, :, ::2, ::2].numpy(), "heatmaps_argmax": heat.reshape(B, V, 17, -1).argmax(-1).numpy()}
+    np.savez_compressed(os.path.join(HERE, "algebraic_r50.npz"), **out)
+    print("algebraic_r50: heat max", float(heat.max()), "kp3d", kp3d[0, :3])
+
+
 def gen_state_dict_keys():
     """Key -> shape table of the reference ResNet-152 volumetric model (1311 tensors)."""
     import json
@@ -118,5 +139,6 @@ if __name__ == "__main__":
     gen_unproject()
     gen_softargmax()
     gen_forward()
+    gen_algebraic()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
