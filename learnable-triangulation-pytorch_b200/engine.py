@@ -482,6 +482,8 @@ class NativeEngine:
         keypoints, volumes = self.softargmax(logits, coord, m.num_joints, m.volume_multiplier, m.volume_softmax)
         # (B, V, 32, h, w) view of the channels-last features (values identical, strides permuted)
         features = feats.data.view(B, V, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
+        if need_conf:
+            return keypoints, features, volumes, coord, conf
         return keypoints, features, volumes, coord
 
     def forward_view_sharded(self, images_local, proj_local, position, center, step, rot, plan, pg, collective="all_reduce",
@@ -550,6 +552,46 @@ class NativeEngine:
         kp_all = lt_dist.gather_keypoints(kp, plan, pg)
         features = feats.data.view(B, Vl, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
         return kp_all, features, volumes, coord
+
+    # ------------------------------------------------------------------ algebraic model (config #5)
+    def algebraic_forward(self, images, proj, heatmap_multiplier, use_confidences):
+        """AlgebraicTriangulationNet.forward (triangulation.py:149-200), device side.
+
+        images (B, V, 3, H, W), proj (B, V, 3, 4) image-space projection matrices.
+        -> keypoints_3d (B, J, 3), keypoints_2d (B, V, J, 2) in image pixels, heatmaps (B, V, J, h, w) softmaxed,
+           confidences (B, V, J)."""
+        self.prepare()
+        self.launches = 0
+        m = self.model
+        B, V = images.shape[:2]
+        H, W = images.shape[3:]
+        dev = images.device
+        J = m.backbone.num_joints
+        trunk = self.backbone_trunk(images.reshape(B * V, *images.shape[2:]))
+        logits = self._conv(self.backbone_upsample(trunk), self._packs["final"], relu=False, out_fmt=FMT_F32)   # (BV,1,h,w,32)
+        h, w = logits.H, logits.W
+        # 2-D soft-argmax (op.py:11-47) = the 3-D kernels with pixel-index coordinates (x, y, 0)
+        key = ("grid2d", h, w, B * V)
+        if getattr(self, "_grid_key", None) != key:
+            ys, xs = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+            g = torch.stack([xs, ys, torch.zeros_like(xs)], dim=-1).reshape(1, h * w, 3)
+            self._grid2d, self._grid_key = g.expand(B * V, h * w, 3).contiguous(), key
+        heat = torch.empty((B * V, J, h, w), dtype=torch.float32, device=dev)
+        kp = torch.empty((B * V, J, 3), dtype=torch.float32, device=dev)
+        ws = torch.empty(capi.softargmax3d_workspace_bytes(B * V, J, h * w) // 4 + 1, dtype=torch.float32, device=dev)
+        capi.softargmax3d(logits.data, h * w * logits.C, logits.C, 1, self._grid2d, heat, kp, ws, B * V, J, h * w, heatmap_multiplier, True)
+        self.launches += 3
+        kp2d = kp[:, :, :2].reshape(B, V, J, 2) * torch.tensor([W / w, H / h], device=dev, dtype=torch.float32)   # :181-184
+        kp2d = kp2d.contiguous()
+        if use_confidences:
+            conf = self.confidence_head(trunk, "alg_confidences").view(B, V, J)
+        else:
+            conf = torch.ones((B, V, J), dtype=torch.float32, device=dev)
+        capi.view_normalize(conf, B, V, J, 1e-5)                                                                 # :173-174
+        kp3d = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+        capi.triangulate_dlt(proj.contiguous(), kp2d, conf, kp3d)
+        self.launches += 2
+        return kp3d, kp2d, heat.view(B, V, J, h, w), conf
 
     def forward(self, images, proj, position, center, step, rot):
         """All inputs are CUDA float32 tensors. Returns (keypoints, features, volumes, coord_volumes)."""
