@@ -250,6 +250,198 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over (M tile, N tile) pairs.  Two TMEM accumulator stages let the
+// epilogue of tile i (8 warps) overlap the MMAs of tile i+1, the operand ring runs continuously across tiles,
+// and the residual tiles of the NEXT epilogue are prefetched by TMA into dedicated staging while the main loop
+// of the current tile is still running (the non-persistent kernel exposes that DRAM latency in every CTA).
+// ------------------------------------------------------------------------------------------------
+struct TcPersistExtra {
+  int n_tiles;        // N tiles
+  long total_tiles;   // M tiles * N tiles
+  int off_out, off_res, off_bar;   // smem offsets
+};
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const __grid_constant__ CUtensorMap tmOut,
+                                                                 const __grid_constant__ CUtensorMap tmRes, const TcParams p,
+                                                                 const TcPersistExtra x) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.Nt * 128;
+  const int stage_bytes = kATileBytes + b_bytes;
+  uint8_t* out_stage = smem + x.off_out;   // 2 x 16 KB
+  uint8_t* res_stage = smem + x.off_res;   // 2 x 16 KB
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + x.off_bar);
+  uint64_t* empty = full + p.stages;
+  uint64_t* acc_full = empty + p.stages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* res_full = acc_empty + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int nchunks = p.KD * p.KH * p.KW * p.CB;
+  const int acc_cols = (p.terms == 3 ? 2 : 1) * p.Nt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads); mbar_init(&res_full[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> coordinates (N tile fastest: CTAs running side by side share the A tile in L2)
+  auto decode = [&](long tile, int& ow0, int& oh0, int& od0, int& nb0, int& n0) {
+    n0 = (int)(tile % x.n_tiles) * p.Nt;
+    long t = tile / x.n_tiles;
+    ow0 = (int)(t % p.tw) * p.bw; t /= p.tw;
+    oh0 = (int)(t % p.th) * p.bh; t /= p.th;
+    od0 = (int)(t % p.td) * p.bd; t /= p.td;
+    nb0 = (int)t * p.bn;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    uint32_t g = 0;   // global chunk counter (ring position)
+    for (long tile = blockIdx.x; tile < x.total_tiles; tile += gridDim.x) {
+      int ow0, oh0, od0, nb0, n0;
+      decode(tile, ow0, oh0, od0, nb0, n0);
+      for (int q = 0; q < nchunks; ++q, ++g) {
+        const uint32_t s = g % (uint32_t)p.stages;
+        mbar_wait(&empty[s], ((g / (uint32_t)p.stages) & 1u) ^ 1u);
+        const int tap = q / p.CB, cb = q % p.CB;
+        const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+        if (elect_one()) {
+          mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+          tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 * p.sw - p.pw + kw, oh0 * p.sh - p.ph + kh, od0 * p.sd - p.pd + kd, nb0);
+          tma_load_2d(a_dst + kATileBytes, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0 * p.b_nmul);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_f16(p.Nt), idesc2 = make_idesc_f16(2 * p.Nt);
+    uint32_t g = 0, it = 0;
+    for (long tile = blockIdx.x; tile < x.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1u;
+      mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d1 = tmem_base + as * (uint32_t)acc_cols, d2 = d1 + (uint32_t)p.Nt;
+      for (int q = 0; q < nchunks; ++q, ++g) {
+        const uint32_t s = g % (uint32_t)p.stages;
+        mbar_wait(&full[s], (g / (uint32_t)p.stages) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw64_desc(a_addr + kATileBytes);
+        const uint32_t first = (q == 0) ? 0u : 1u;
+        if (elect_one()) {
+          if (p.terms == 3) {
+            umma_f16(d1, ad, bd, idesc2, first);
+            umma_f16(d2, ad + 4, bd, idesc, 1);
+            umma_f16(d1, ad + 2, bd + 2, idesc2, 1);
+            umma_f16(d2, ad + 6, bd + 2, idesc, 1);
+          } else {
+            umma_f16(d1, ad, bd, idesc, first);
+            umma_f16(d1, ad + 2, bd + 2, idesc, 1);
+          }
+          umma_commit(&empty[s]);
+          if (q == nchunks - 1) umma_commit(&acc_full[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..9) =================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const bool leader = threadIdx.x == 64;
+    const int nblk = p.Nt >> 5;
+    const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
+    const bool has_res = p.residual != LT_RES_NONE;
+    // Residual tiles stream through two 16 KB buffers indexed by a block counter that runs across tiles: global block
+    // c = (k-th tile of this CTA, block c % nblk) lives in buffer c & 1 and is requested two blocks ahead, so the blocks of
+    // the NEXT tile are already in flight while the main loop of that tile runs.
+    const long my_tiles = (x.total_tiles > (long)blockIdx.x) ? (x.total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const long total_blocks = my_tiles * nblk;
+    auto issue_res = [&](long c) {   // leader only
+      const long tile_c = (long)blockIdx.x + (c / nblk) * (long)gridDim.x;
+      const int blk = (int)(c % nblk);
+      int a0, a1, a2, a3, an;
+      decode(tile_c, a0, a1, a2, a3, an);
+      const int buf = (int)(c & 1);
+      mbar_expect_tx(&res_full[buf], 16384u);
+      tma_load_5d(res_stage + buf * 16384, &tmRes, &res_full[buf], an * esz + blk * 32 * esz, a0, a1, a2, a3);
+    };
+    if (leader && has_res)
+      for (long c = 0; c < 2 && c < total_blocks; ++c) issue_res(c);
+    uint32_t it = 0;
+    long c = 0;   // global block counter
+    for (long tile = blockIdx.x; tile < x.total_tiles; tile += gridDim.x, ++it) {
+      int ow0, oh0, od0, nb0, n0;
+      decode(tile, ow0, oh0, od0, nb0, n0);
+      const uint32_t as = it & 1u;
+      const int cbase = n0 * esz;
+      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)acc_cols;
+      for (int i = 0; i < nblk; ++i, ++c) {
+        const int buf = (int)(c & 1);
+        float v[16], r[16];
+        {
+          uint32_t t1[16], t2[16];
+          tmem_ld16_nowait(tlane + (uint32_t)(i * 32 + half * 16), t1);
+          if (p.terms == 3) tmem_ld16_nowait(tlane + (uint32_t)(p.Nt + i * 32 + half * 16), t2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = (p.terms == 3) ? fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j])) : __uint_as_float(t1[j]);
+        }
+        if (i == nblk - 1) {               // accumulator stage fully read: release it to the MMA warp
+          tc_fence_before();
+          mbar_arrive_cta(&acc_empty[as]);
+        }
+        epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
+        if (has_res) {
+          mbar_wait(&res_full[buf], (uint32_t)((c >> 1) & 1));
+          epi_load16(smem_u32(res_stage + buf * 16384), row, half, p.out_format, r);
+        }
+        epi_activate16(v, r, p.residual, p.relu);
+        if (leader) bulk_wait_read<1>();      // the store that last read out_stage[buf] (two blocks ago) is done with it
+        epi_bar_sync();                       // also: every thread has finished reading res_stage[buf]
+        epi_store16(smem_u32(out_stage + buf * 16384), row, half, p.out_format, v);
+        fence_proxy_async();
+        epi_bar_sync();
+        if (leader) {
+          tma_store_5d(&tmOut, out_stage + buf * 16384, cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+          bulk_commit();
+          if (has_res && c + 2 < total_blocks) issue_res(c + 2);
+        }
+      }
+    }
+    if (leader) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -335,6 +527,37 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     configured = 227 * 1024;
   }
   const long m_tiles = (long)p.tw * p.th * p.td * p.tn;
+  static const int persist_mode = getenv("LT_TC_PERSIST") ? atoi(getenv("LT_TC_PERSIST")) : 1;
+  // Measured on B200 (profiles/): two co-resident non-persistent CTAs already overlap epilogue and main loop for the
+  // MMA-heavy layers and win there; the persistent variant wins when a tile carries almost no work (1x1x1 convs at 64^3:
+  // 0.73 -> 0.41 ms for three launches), where CTA setup (TMEM alloc, barrier init, descriptor fetch) dominates.
+  const int nchunks_total = p.KD * p.KH * p.KW * p.CB;
+  const bool tiny_tiles = nchunks_total * (p.Nt / 32) <= 2 && m_tiles * n_tiles > 4L * sm_count();
+  if ((persist_mode == 2 || (persist_mode == 1 && tiny_tiles)) && p.tma_epi && p.terms != 0 && m_tiles * n_tiles > (long)sm_count()) {
+    // persistent variant: one CTA per SM, deep operand ring + dedicated epilogue staging, two TMEM accumulator stages
+    TcPersistExtra x;
+    x.n_tiles = n_tiles;
+    x.total_tiles = m_tiles * n_tiles;
+    int pst = (128 * 1024) / stage_bytes;
+    if (pst > 8) pst = 8;
+    if (pst < 2) pst = 2;
+    p.stages = pst;
+    const int ring = pst * stage_bytes;
+    x.off_out = (ring + 1023) & ~1023;
+    x.off_res = x.off_out + 32768;
+    x.off_bar = x.off_res + 32768;
+    const size_t psmem = (size_t)x.off_bar + (2 * pst + 6) * 8 + 16 + 1024;
+    static bool pconf = false;
+    if (!pconf) {
+      cudaError_t e2 = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+      if (e2 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+      pconf = true;
+    }
+    conv_tc_persist_kernel<<<(unsigned)sm_count(), 320, psmem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
+    cudaError_t e3 = cudaGetLastError();
+    if (e3 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist_kernel: %s", cudaGetErrorString(e3));
+    return LT_OK;
+  }
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
   conv_tc_kernel<<<grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p);
   cudaError_t e = cudaGetLastError();
