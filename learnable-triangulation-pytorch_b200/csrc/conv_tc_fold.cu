@@ -32,11 +32,12 @@ struct FoldParams {
   int N, D, H, W;
   int K, pad;
   int NC, NF, OWt;
+  int WX, LINES, wx_shift;   // x window of the M tile (16 or 32 rows per line) and lines per tile (128 / WX)
   int xwins, yblks;
   long tiles;
   int slab_bytes, a_slots;
   int b_resident, b_slots, b_bytes;
-  int stage_rows;        // 8 * OWt
+  int stage_rows;        // LINES * OWt
   int out_format, relu, residual;
   const float* scale;
   const float* shift;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
             mbar_arrive(&a_full[slot]);          // debug: reuse stale slab contents, no TMA traffic
           } else {
             mbar_expect_tx(&a_full[slot], (uint32_t)p.slab_bytes);
-            tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.pad, yb * 8 - p.pad,
+            tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.pad, yb * p.LINES - p.pad,
                         z + kd - p.pad, n);
           }
         }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
             tc_fence_after();
             b_addr = smem_u32(b_smem + (size_t)bs * p.b_bytes);
           }
-          const uint64_t ad = make_sw128_desc(slab + (uint32_t)kh * 2048u);   // line kh of the slab: 16 rows x 128 B
+          const uint64_t ad = make_sw128_desc(slab + (uint32_t)(kh * p.WX) * 128u);   // line kh of the slab: WX rows x 128 B
           const uint64_t bd = make_sw64_desc(b_addr);                          // 2*NF rows x 64 B: [hi rows ; lo rows]
           const uint32_t first = (kd | kh) ? 1u : 0u;
           if (elect_one()) {
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    const int line = row >> 4, xi = row & 15;
+    const int line = row >> p.wx_shift, xi = row & (p.WX - 1);
     const bool keep = xi < p.OWt;
     const int srow = line * p.OWt + xi;        // compacted staging row
     const bool leader = threadIdx.x == 64;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       if (leader && p.residual != LT_RES_NONE) {
         bulk_wait_read<0>();                    // staging buffer is shared: the previous tile's store must have drained it
         mbar_expect_tx(res_full, stage_bytes);
-        tma_load_5d(res_stage, &tmRes, res_full, 0, xw * p.OWt, yb * 8, z, n);
+        tma_load_5d(res_stage, &tmRes, res_full, 0, xw * p.OWt, yb * p.LINES, z, n);
       }
       mbar_wait_prof(&acc_full[as], (it >> 1) & 1u, w_accf, prof);
       tc_fence_after();
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       fence_proxy_async();
       epi_bar_sync();
       if (leader) {
-        tma_store_5d(&tmOut, out_stage, 0, xw * p.OWt, yb * 8, z, n);
+        tma_store_5d(&tmOut, out_stage, 0, xw * p.OWt, yb * p.LINES, z, n);
         bulk_commit();
       }
     }
@@ -309,17 +310,25 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.K = d->KW; p.pad = d->KW / 2;
   p.NC = (d->Cout + 15) & ~15;
   p.NF = p.K * p.NC;
-  p.OWt = 16 - p.K + 1;
+  // x window: 16 rows keep 16-K+1 outputs per line, 32 rows keep 32-K+1; pick whichever computes fewer wasted rows
+  // (64-wide volumes: K=3 -> 16 (80 rows per line vs 96), K=7 -> 32 (96 vs 112))
+  static const int wx_env = getenv("LT_FOLD_WX") ? atoi(getenv("LT_FOLD_WX")) : 0;
+  p.WX = 16;
+  if (p.W >= 32 && ceil_div(p.W, 32 - p.K + 1) * 32 < ceil_div(p.W, 16 - p.K + 1) * 16) p.WX = 32;
+  if ((wx_env == 16 || wx_env == 32) && p.W >= wx_env) p.WX = wx_env;
+  p.wx_shift = p.WX == 32 ? 5 : 4;
+  p.LINES = 128 / p.WX;
+  p.OWt = p.WX - p.K + 1;
   p.xwins = ceil_div(p.W, p.OWt);
-  p.yblks = ceil_div(p.H, 8);
+  p.yblks = ceil_div(p.H, p.LINES);
   p.tiles = (long)p.N * p.D * p.yblks * p.xwins;
-  const int slab_lines = 8 + p.K - 1;
-  p.slab_bytes = 16 * slab_lines * 128;
+  const int slab_lines = p.LINES + p.K - 1;
+  p.slab_bytes = p.WX * slab_lines * 128;
   p.b_bytes = p.NF * 128;
   p.b_resident = (p.K * p.K * p.b_bytes <= 112 * 1024) ? 1 : 0;
-  p.b_slots = p.b_resident ? 1 : 8;     // streamed weights: 8 x 14 KB in flight hide the L2 latency of a (kd,kh) step
-  p.a_slots = p.b_resident ? 5 : 3;     // slabs in flight
-  p.stage_rows = 8 * p.OWt;
+  p.b_slots = p.b_resident ? 1 : (p.WX == 32 ? 6 : 8);   // streamed weights: 14 KB tiles in flight hide the L2 latency of a (kd,kh) step
+  p.a_slots = p.b_resident ? (p.WX == 32 ? 3 : 5) : 3;    // slabs in flight
+  p.stage_rows = p.LINES * p.OWt;
   p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
   p.scale = scale; p.shift = shift;
   p.dbg = getenv("LT_FOLD_DBG") ? atoi(getenv("LT_FOLD_DBG")) : 0;
@@ -342,7 +351,7 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
     const uint64_t rowb = 128;  // 32 channels split-fp16
     const uint64_t dims[5] = {64, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N};
     const uint64_t str[4] = {rowb, rowb * p.W, rowb * p.W * p.H, rowb * p.W * p.H * p.D};
-    const uint32_t bx[5] = {64, 16, (uint32_t)slab_lines, 1, 1};
+    const uint32_t bx[5] = {64, (uint32_t)p.WX, (uint32_t)slab_lines, 1, 1};
     int rc = make_map(&tmA, in, 5, dims, str, bx, nullptr, 1);
     if (rc) return rc;
   }
@@ -358,7 +367,7 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
     const uint64_t rowb = 128;
     const uint64_t dims[5] = {(uint64_t)(f32 ? 32 : 64), (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N};
     const uint64_t str[4] = {rowb, rowb * p.W, rowb * p.W * p.H, rowb * p.W * p.H * p.D};
-    const uint32_t bx[5] = {(uint32_t)(f32 ? 32 : 64), (uint32_t)p.OWt, 8, 1, 1};
+    const uint32_t bx[5] = {(uint32_t)(f32 ? 32 : 64), (uint32_t)p.OWt, (uint32_t)p.LINES, 1, 1};
     int rc = make_map(&tmOut, out, 5, dims, str, bx, nullptr, 1, f32);
     if (rc) return rc;
     tmRes = tmOut;

@@ -127,6 +127,8 @@ FOLD_CASES = [
     (32, 16, 7, (8, 8, 16), 1),       # 7^3, weights streamed
     (32, 16, 7, (7, 13, 25), 2),
     (32, 32, 3, (32, 32, 32), 2),     # many tiles per persistent CTA
+    (32, 16, 7, (5, 10, 64), 1),      # 7^3 on a 64-wide volume: 32-row x window (26 outputs per line), partial y block
+    (32, 16, 7, (4, 7, 71), 2),       # 32-row window with a partial last window (71 = 2*26 + 19)
 ]
 
 
