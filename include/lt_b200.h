@@ -146,6 +146,9 @@ typedef struct lt_conv_desc {
   int relu;                  /* apply max(x,0) */
   int residual;              /* lt_residual; residual tensor has the output tensor's shape/format */
   int in_format, out_format; /* lt_format */
+  void* workspace;           /* optional device scratch for split-K (layers with fewer M x N tiles than half the SMs:
+                                the K loop is spread over more CTAs and summed in a fixed order); NULL = never split */
+  size_t workspace_bytes;    /* size of workspace; a split is only used when its partial tiles fit */
 } lt_conv_desc;
 
 /* SIMT weights: float32 [KD*KH*KW][Cin][CoutW], CoutW = round_up(Cout, 4), zero padded.
@@ -190,6 +193,14 @@ int lt_triangulate_dlt_fwd(const float* proj, const float* keypoints_2d, const f
  * ---------------------------------------------------------------------------------------- */
 /* images [N][C][H][W] float32 -> [N][H][W][Cp] float32, channels >= C zero filled */
 int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, int Cp, void* stream);
+/* Batch image ingest.  Replaces image_batch_to_torch (mvn/utils/img.py:96-99, called from prepare_batch,
+ * mvn/datasets/utils.py:45-52) and, for uint8 input with a table, normalize_image (img.py:102-110):
+ *   in  [N][H][W][C] as collated by the dataset (datasets/utils.py:24), dtype lt_image_dtype, C <= 4
+ *   lut NULL, or float32 [C][256] applied to uint8 input (out = lut[c][in]); NULL = plain cast
+ *   out [N][C][H][W] float32 */
+enum lt_image_dtype { LT_IMG_U8 = 0, LT_IMG_F32 = 1, LT_IMG_F64 = 2 };
+int lt_images_hwc_to_nchw_fwd(const void* in, int in_dtype, const float* lut, float* out, int N, int C, int H, int W,
+                              void* stream);
 /* stem input packing: images [N][C<=8][H][W] float32 -> 2x2 space-to-depth split-fp16 [N][H/2][W/2][32],
  * channel (r*2+s)*C + c = in[c][2y+r][2x+s]; turns the 7x7 stride-2 stem conv (pose_resnet.py:205) into a 4x4 stride-1 conv */
 int lt_stem_s2d_fwd(const float* in, void* out, int N, int C, int H, int W, void* stream);

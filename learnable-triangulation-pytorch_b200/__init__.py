@@ -8,7 +8,7 @@ Python identifier; `lt_b200.py` at the repo root is the import shim).
     from lt_b200 import op                                   # drop-in for mvn.utils.op (two ops)
     lt_b200.install()                                        # or: patch an imported reference `mvn` in place
 """
-from . import multiview, op, pose_resnet, v2v, volumetric  # noqa: F401
+from . import multiview, op, pipeline, pose_resnet, v2v, volumetric  # noqa: F401
 from .multiview import Camera  # noqa: F401
 from .triangulation import AlgebraicTriangulationNet, VolumetricTriangulationNet  # noqa: F401
 from .v2v import V2VModel  # noqa: F401

@@ -33,7 +33,7 @@ class ConvDesc(ctypes.Structure):
         "FD", "FH", "FW", "FC",
         "osd", "osh", "osw",
         "ood", "ooh", "oow",
-        "relu", "residual", "in_format", "out_format")]
+        "relu", "residual", "in_format", "out_format")] + [("workspace", c_void_p), ("workspace_bytes", c_size_t)]
 
 
 # every symbol include/lt_b200.h declares: name -> (restype, argtypes)
@@ -60,6 +60,7 @@ SIGNATURES = {
     "lt_view_normalize_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "lt_triangulate_dlt_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "lt_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "lt_images_hwc_to_nchw_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "lt_stem_s2d_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "lt_f32_to_s32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
     "lt_s32_to_f32": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
@@ -207,6 +208,15 @@ def triangulate_dlt(proj, kp2d, conf, out):
 
 def nchw_to_nhwc(inp, out, N, C, H, W, Cp):
     _check(lib().lt_nchw_to_nhwc_f32(_ptr(inp), _ptr(out), N, C, H, W, Cp, _stream()), "lt_nchw_to_nhwc_f32")
+
+
+IMG_DTYPE = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}
+
+
+def images_hwc_to_nchw(inp, lut, out, N, C, H, W):
+    """inp: device tensor [N][H][W][C] uint8/float32/float64; lut: None or float32 [C][256]; out: float32 [N][C][H][W]."""
+    _check(lib().lt_images_hwc_to_nchw_fwd(_ptr(inp), IMG_DTYPE[inp.dtype], None if lut is None else _ptr(lut), _ptr(out),
+                                           N, C, H, W, _stream()), "lt_images_hwc_to_nchw_fwd")
 
 
 def stem_s2d(inp, out, N, C, H, W):

@@ -42,6 +42,10 @@ struct TcParams {
   const float* shift;
   const void* res;
   void* out;
+  // split-K (latency-bound layers with fewer CTAs than SMs): blockIdx.z owns a contiguous range of the K chunks and
+  // writes its raw fp32 accumulator tile to ws[z][m tile][128][ws_ld]; splitk_reduce_kernel sums and applies the epilogue
+  int splits, ws_ld;
+  float* ws;
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
@@ -70,7 +74,9 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
   const int tni = t;
   const int ow0 = twi * p.bw, oh0 = thi * p.bh, od0 = tdi * p.bd, nb0 = tni * p.bn;
   const int n0 = blockIdx.y * p.Nt;
-  const int nchunks = p.KD * p.KH * p.KW * p.CB;
+  const int nchunks_all = p.KD * p.KH * p.KW * p.CB;
+  const int q_begin = (int)(((long)blockIdx.z * nchunks_all) / p.splits);
+  const int nchunks = (int)(((long)(blockIdx.z + 1) * nchunks_all) / p.splits) - q_begin;   // chunks of this split
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -92,14 +98,15 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
       const int s = q % p.stages;
       const uint32_t ph = (uint32_t)((q / p.stages) & 1);
       mbar_wait(&empty[s], ph ^ 1u);
-      const int tap = q / p.CB, cb = q % p.CB;
+      const int qa = q_begin + q;
+      const int tap = qa / p.CB, cb = qa % p.CB;
       const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
       uint8_t* a_dst = smem + (size_t)s * stage_bytes;
       uint8_t* b_dst = a_dst + kATileBytes;
       if (elect_one()) {
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
         tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 * p.sw - p.pw + kw, oh0 * p.sh - p.ph + kh, od0 * p.sd - p.pd + kd, nb0);
-        tma_load_2d(b_dst, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0 * p.b_nmul);
+        tma_load_2d(b_dst, &tmB, &full[s], qa * p.b_step0, qa * p.b_step1 + n0 * p.b_nmul);
       }
       __syncwarp();
     }
@@ -159,7 +166,26 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    if (p.tma_epi) {
+    if (p.splits > 1) {
+      // ---- split-K: raw accumulators to the workspace, epilogue deferred to splitk_reduce_kernel ----
+      float* wrow = p.ws + (((size_t)blockIdx.z * gridDim.x + blockIdx.x) * 128 + row) * p.ws_ld + n0;
+      for (int c0 = half * 16; c0 < p.Nt; c0 += 32) {
+        uint32_t v[16], v2[16];
+        tmem_ld16_nowait(tlane + (uint32_t)c0, v);
+        if (p.terms == 3) tmem_ld16_nowait(tlane + (uint32_t)(p.Nt + c0), v2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 o;
+          if (p.terms == 3)
+            o = make_float4(fmaf(__uint_as_float(v2[j]), kLoInv, __uint_as_float(v[j])), fmaf(__uint_as_float(v2[j + 1]), kLoInv, __uint_as_float(v[j + 1])),
+                            fmaf(__uint_as_float(v2[j + 2]), kLoInv, __uint_as_float(v[j + 2])), fmaf(__uint_as_float(v2[j + 3]), kLoInv, __uint_as_float(v[j + 3])));
+          else
+            o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          *reinterpret_cast<float4*>(wrow + c0 + j) = o;
+        }
+      }
+    } else if (p.tma_epi) {
       // ---- staged epilogue: 32-channel blocks -> swizzled smem tile -> TMA store; residual tiles arrive by TMA ----
       // All MMAs have completed (tmem_full), so the operand ring is free: reuse its first 64 KB.
       uint8_t* out_stage = smem;              // 2 x 16 KB
@@ -493,6 +519,48 @@ static void pick_box(int OW, int OH, int OD, int N, int* box) {
   if (best == 1e300) { box[0] = pow2_ceil(OW) > 128 ? 128 : pow2_ceil(OW); box[1] = box[2] = 1; box[3] = 128 / box[0]; }
 }
 
+// Split-K second pass: sums the per-split accumulator tiles in a fixed order (deterministic) and applies the fused
+// epilogue (scale/shift, residual, ReLU, output format).  One thread per (tile row, 4 channels).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, long m_tiles, int coutp) {
+  const int c4 = coutp >> 2;
+  const long total = m_tiles * 128 * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % c4) * 4;
+    const long tr = i / c4;
+    const int row = (int)(tr % 128);
+    long t = tr / 128;
+    const int twi = (int)(t % p.tw); t /= p.tw;
+    const int thi = (int)(t % p.th); t /= p.th;
+    const int tdi = (int)(t % p.td); t /= p.td;
+    const int tni = (int)t;
+    int r_ = row;
+    const int dw = r_ % p.bw; r_ /= p.bw;
+    const int dh = r_ % p.bh; r_ /= p.bh;
+    const int dd = r_ % p.bd; r_ /= p.bd;
+    const int ow = twi * p.bw + dw, oh = thi * p.bh + dh, od = tdi * p.bd + dd, nb = tni * p.bn + r_;
+    if (!(ow < p.OW && oh < p.OH && od < p.OD && nb < p.N) || co >= p.FC) continue;
+    const long opix = (((long)nb * p.FD + (od * p.osd + p.ood)) * p.FH + (oh * p.osh + p.ooh)) * p.FW + (ow * p.osw + p.oow);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < p.splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(p.ws + ((size_t)z * m_tiles * 128 + tr) * p.ws_ld + co);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + co));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + co));
+    float4 o = make_float4(fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w));
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.residual != LT_RES_NONE) {
+      if (p.out_format == LT_FMT_F32) rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + opix * p.FC + co);
+      else rr = load_s32x4(reinterpret_cast<const sh_t*>(p.res) + opix * 2 * p.FC, co);
+    }
+    if (p.residual == LT_RES_BEFORE_RELU) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (p.residual == LT_RES_AFTER_RELU) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+    if (p.out_format == LT_FMT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.FC + co) = o;
+    else store_s32x4(reinterpret_cast<sh_t*>(p.out) + opix * 2 * p.FC, co, o);
+  }
+}
+
 // Tensor map over the output (or residual) tensor as seen by this launch: the stride-phase mapping
 // (out coordinate = o * os + oo) becomes a base offset plus scaled strides; box = one 32-channel block of an M tile.
 static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* d, const TcParams& p) {
@@ -507,7 +575,8 @@ static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* 
 }
 
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
-                     TcParams& p, int n_tiles, cudaStream_t st) {
+                     TcParams& p, int n_tiles, cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0) {
+  p.splits = 1; p.ws = nullptr; p.ws_ld = 0;
   const int stage_bytes = kATileBytes + p.Nt * 128;
   const long ctas = (long)p.tw * p.th * p.td * p.tn * n_tiles;
   // two resident CTAs per SM when the grid fills the chip; small grids (deep V2V levels) are latency-bound on the
@@ -558,10 +627,33 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if (e3 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist_kernel: %s", cudaGetErrorString(e3));
     return LT_OK;
   }
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
+  // split-K: a grid that cannot fill half the SMs is bound by the serial K loop of each CTA (27 taps x Cin/32 chunks of
+  // weights streamed from HBM by ONE SM); spread the chunks over blockIdx.z instead
+  static const int splitk_mode = getenv("LT_TC_SPLITK") ? atoi(getenv("LT_TC_SPLITK")) : 1;
+  int splits = 1;
+  const long grid_ctas = m_tiles * n_tiles;
+  if (splitk_mode && ws && p.terms != 0 && grid_ctas * 2 <= (long)sm_count() && nchunks_total >= 16) {
+    splits = (int)((long)sm_count() / grid_ctas);
+    if (splits > nchunks_total / 4) splits = nchunks_total / 4;
+    const size_t per_split = (size_t)m_tiles * 128 * (size_t)n_tiles * p.Nt * sizeof(float);
+    if ((size_t)splits * per_split > ws_bytes) splits = (int)(ws_bytes / per_split);
+    if (splits < 2) splits = 1;
+  }
+  p.splits = splits;
+  p.ws = reinterpret_cast<float*>(ws);
+  p.ws_ld = n_tiles * p.Nt;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
   conv_tc_kernel<<<grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_kernel: %s", cudaGetErrorString(e));
+  if (splits > 1) {
+    const long total = m_tiles * 128 * (p.ws_ld / 4);
+    long blocks = (total + 255) / 256;
+    if (blocks > 4L * sm_count()) blocks = 4L * sm_count();
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, m_tiles, p.ws_ld);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "splitk_reduce_kernel: %s", cudaGetErrorString(e));
+  }
   return LT_OK;
 }
 
@@ -624,7 +716,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
       if (rc) return rc;
     }
   }
-  return launch_tc(tmA, tmB, tmOut, tmRes, p, CoutP / Nt, (cudaStream_t)stream);
+  return launch_tc(tmA, tmB, tmOut, tmRes, p, CoutP / Nt, (cudaStream_t)stream, d->workspace, d->workspace_bytes);
 }
 
 int conv_tc_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,

@@ -75,6 +75,39 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolParams p) {
   }
 }
 
+
+// ---- batch image ingest ---------------------------------------------------------------------------
+// Host batches arrive as the dataset leaves them: [N][H][W][C] (HWC) uint8 / float32 / float64 (datasets/utils.py:24).
+// The reference transposes to CHW and casts on the CPU (image_batch_to_torch, img.py:96-99) after normalising per image
+// on the CPU as well (normalize_image, img.py:102-110).  Here the raw HWC buffer is uploaded once and this kernel does
+// transpose + cast (+ per-channel 256-entry table for uint8: the table is built on the host in float64 with the
+// reference's formula and rounded once, so the result equals normalize_image(...).astype(float32) bit for bit).
+template <typename T>
+__global__ void __launch_bounds__(256) images_hwc_to_nchw_kernel(const T* __restrict__ in, const float* __restrict__ lut,
+                                                                 float* __restrict__ out, long N, int C, long hw) {
+  __shared__ float s_lut[4 * 256];
+  const bool use_lut = lut != nullptr && sizeof(T) == 1;
+  if (use_lut) {
+    for (int i = threadIdx.x; i < C * 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+  }
+  const long total = N * hw;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / hw, r = i % hw;
+    const T* src = in + i * C;
+    for (int c = 0; c < C; ++c) {
+      float v;
+      if (sizeof(T) == 1) {
+        const unsigned u = (unsigned)src[c];
+        v = use_lut ? s_lut[c * 256 + u] : (float)u;
+      } else {
+        v = (float)src[c];     // float64 -> float32 round-to-nearest, as ndarray.astype / Tensor.float()
+      }
+      out[(n * C + c) * hw + r] = v;
+    }
+  }
+}
+
 // ---- layout / format conversion -------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            int N, int C, int H, int W, int Cp) {
@@ -190,6 +223,21 @@ extern "C" int lt_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, in
   LT_REQUIRE(in && out && Cp >= C, "nchw_to_nhwc: bad arguments");
   nchw_to_nhwc_kernel<<<grid_for((long)N * H * W), 256, 0, (cudaStream_t)stream>>>(in, out, N, C, H, W, Cp);
   LT_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return LT_OK;
+}
+
+extern "C" int lt_images_hwc_to_nchw_fwd(const void* in, int in_dtype, const float* lut, float* out, int N, int C, int H, int W,
+                                         void* stream) {
+  LT_REQUIRE(in && out && N > 0 && C > 0 && C <= 4 && H > 0 && W > 0, "images_hwc_to_nchw: bad arguments");
+  LT_REQUIRE(in_dtype >= LT_IMG_U8 && in_dtype <= LT_IMG_F64, "images_hwc_to_nchw: unknown input dtype %d", in_dtype);
+  LT_REQUIRE(lut == nullptr || in_dtype == LT_IMG_U8, "images_hwc_to_nchw: the table applies to uint8 input only");
+  const long hw = (long)H * W;
+  const unsigned grid = grid_for((long)N * hw);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == LT_IMG_U8) images_hwc_to_nchw_kernel<unsigned char><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(in), lut, out, N, C, hw);
+  else if (in_dtype == LT_IMG_F32) images_hwc_to_nchw_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), nullptr, out, N, C, hw);
+  else images_hwc_to_nchw_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(in), nullptr, out, N, C, hw);
+  LT_CHECK_LAUNCH("images_hwc_to_nchw_kernel");
   return LT_OK;
 }
 

@@ -308,6 +308,8 @@ class NativeEngine:
                           relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt)
         if residual is not None:
             assert residual.fmt == out.fmt and residual.C == out.C
+        ws = self._splitk_workspace(x.data.device)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         impl, weight = pk.impl, pk.w
         if (pk.w_fold is not None and x.W >= 16 and out.C == 32 and out_scale == (1, 1, 1) and (od, oh, ow) == (x.D, x.H, x.W)):
             impl, weight = CONV_TC_FOLD, pk.w_fold
@@ -318,6 +320,15 @@ class NativeEngine:
             capi.conv_nd(d, x.data, weight, pk.scale, pk.shift, None if residual is None else residual.data, out.data, impl)
         self.launches += 1
         return out
+
+    def _splitk_workspace(self, device):
+        """Scratch for the split-K path of lt_conv_nd_fwd (deep V2V levels: 1-32 M tiles); one buffer shared by all layers
+        (launches on one stream are ordered).  Allocated before any CUDA-graph capture by the eager warm-up forward."""
+        ws = getattr(self, "_splitk_ws", None)
+        if ws is None or ws.device != device:
+            ws = torch.empty(int(os.environ.get("LT_SPLITK_WS_MB", "32")) << 20, dtype=torch.uint8, device=device)
+            self._splitk_ws = ws
+        return ws
 
     def _timed(self, label, flops=0.0, nbytes=0.0, desc=""):
         return _Timed(self.timeline, label, flops, nbytes, desc)

@@ -78,6 +78,36 @@ def test_conv_tc_vs_torch(case, mode):
         assert float(full[:, cout:].abs().max()) == 0.0, "padding channels must be written as zeros"
 
 
+@pytest.mark.parametrize("case", [(128, 128, 3, (2, 2, 2), 8), (128, 128, 3, (4, 4, 4), 8), (128, 128, 3, (8, 8, 8), 8), (64, 128, 3, (5, 3, 4), 2),
+                                  (256, 96, 1, (4, 4, 4), 2)])
+@pytest.mark.parametrize("res_mode", ["none", "before", "after"])
+def test_conv_tc_splitk_matches_single_pass(case, res_mode):
+    """Deep V2V levels (v2v.py:75-101: 2^3..8^3 volumes) have fewer M tiles than SMs: the K loop is split over blockIdx.z
+    and summed by splitk_reduce_kernel.  Same result as the single-pass kernel up to fp32 summation order."""
+    cin, cout, k, spatial, N = case
+    torch.manual_seed(cin + cout + spatial[0])
+    conv = torch.nn.Conv3d(cin, cout, k, 1, k // 2, bias=True).eval()
+    bn = _bn_for(conv, 3)
+    x = torch.randn(N, cin, *spatial)
+    mode = {"none": capi.RES_NONE, "before": capi.RES_BEFORE_RELU, "after": capi.RES_AFTER_RELU}[res_mode]
+    with torch.no_grad():
+        y0 = bn(conv(x))
+        res = torch.randn_like(y0)
+        want = {"none": F.relu(y0), "before": F.relu(y0 + res), "after": F.relu(y0) + res}[res_mode]
+    e = _engine("tc")
+    pk = e._pack_conv(conv.to(DEV), bn.to(DEV))
+    xa = act_from_nchw(x, capi.FMT_S32)
+    ra = act_from_nchw(res, capi.FMT_S32) if res_mode != "none" else None
+    y_split = act_to_nchw(e._conv(xa, pk, relu=True, residual=ra, res_mode=mode), cout).cpu()
+    e._splitk_ws = torch.empty(0, dtype=torch.uint8, device=DEV)      # no workspace -> single pass
+    y_single = act_to_nchw(e._conv(xa, pk, relu=True, residual=ra, res_mode=mode), cout).cpu()
+    torch.cuda.synchronize()
+    err = rel_err(y_split.numpy(), want.numpy())
+    diff = rel_err(y_split.numpy(), y_single.numpy())
+    print("splitk %s res=%s rel err %.2e, vs single pass %.2e" % (case, res_mode, err, diff))
+    assert err < TOL["tc"] and diff < 5e-6
+
+
 @pytest.mark.parametrize("case", [(64, 64, 3, 2, 1, (12, 12), 2), (64, 128, 1, 2, 0, (12, 12), 2), (128, 128, 3, 2, 1, (48, 48), 4),
                                   (256, 512, 1, 2, 0, (48, 48), 4)])
 def test_conv_tc_stride2_vs_torch(case):

@@ -31,10 +31,11 @@ def test_conv_desc_layout_matches_header():
     fields = []
     for line in body.splitlines()[1:]:
         line = line.split("/*")[0].strip()
-        if line.startswith("int "):
-            fields += [f.strip() for f in line[4:].rstrip(";").split(",")]
-    assert fields == [f[0] for f in capi.ConvDesc._fields_]
-    assert ctypes.sizeof(capi.ConvDesc) == 4 * len(fields)
+        for ctype, c in (("int ", ctypes.c_int), ("void* ", ctypes.c_void_p), ("size_t ", ctypes.c_size_t)):
+            if line.startswith(ctype):
+                fields += [(f.strip(), c) for f in line[len(ctype):].rstrip(";").split(",")]
+    assert fields == [(f[0], f[1]) for f in capi.ConvDesc._fields_]
+    assert ctypes.sizeof(capi.ConvDesc) == sum(ctypes.sizeof(c) for _, c in fields)   # 32 ints, then 8-byte aligned
 
 
 def test_stack_projections_equals_per_camera_path():
