@@ -200,6 +200,22 @@ def main_native(args, rank, world, local_rank):
     h2d = images.numel() * 4
 
     with torch.no_grad():
+        if sharded and args.collective != "all_reduce":
+            # the peer-memory exchanges need CUDA IPC / symmetric memory between all ranks of a view group; if any rank
+            # cannot set them up, every rank falls back to the NCCL all-reduce contract path (reported in config)
+            failed = 0
+            try:
+                step(images_dev)
+                torch.cuda.synchronize()
+            except Exception as exc:   # noqa: BLE001 - reported, then the contract path is used
+                failed = 1
+                print("rank %d: collective %r unavailable (%s: %s); using all_reduce" % (rank, args.collective, type(exc).__name__, exc),
+                      file=sys.stderr, flush=True)
+            flag = torch.tensor([failed], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                parallelism += " [requested %s exchange unavailable on this box -> all_reduce over NCCL]" % args.collective
+                args.collective = "all_reduce"
         # ---- device-resident arm: CUDA events, L2 flushed between iterations ----
         for _ in range(max(args.warmup, 3)):
             step(images_dev)

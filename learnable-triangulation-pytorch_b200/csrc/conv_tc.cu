@@ -707,7 +707,10 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
   }
   CUtensorMap tmOut = tmA, tmRes = tmA;
   static const int direct_epi = getenv("LT_TC_EPILOGUE") && !strcmp(getenv("LT_TC_EPILOGUE"), "direct");
-  p.tma_epi = (!direct_epi && d->FC % 32 == 0 && Nt % 32 == 0 && CoutP <= d->FC) ? 1 : 0;
+  // float32 outputs may be narrower than the (single) padded N tile: the tensor map then has FC channels and the TMA
+  // store clips the box at the tensor bound (80-byte voxel rows for the 17-joint logits instead of 128)
+  const bool clipped_f32 = d->out_format == LT_FMT_F32 && d->residual == LT_RES_NONE && CoutP == Nt && d->FC % 4 == 0 && d->FC < CoutP;
+  p.tma_epi = (!direct_epi && Nt % 32 == 0 && ((d->FC % 32 == 0 && CoutP <= d->FC) || clipped_f32)) ? 1 : 0;
   if (p.tma_epi) {
     int rc = make_out_map(&tmOut, out, d, p);
     if (rc) return rc;

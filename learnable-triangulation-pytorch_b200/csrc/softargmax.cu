@@ -12,7 +12,8 @@
 //
 // Algorithmic bytes per sample (J=17, 64^3): 17.83 MB logits + 3.15 MB coords (+17.83 MB volume
 // write) = 20.97 MB keypoints-only / 38.80 MB with volumes.
-#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace lt {
 
@@ -211,12 +212,278 @@ __global__ void __launch_bounds__(256) softargmax_normalize_generic(const SoftPa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused streaming path (channels-last logits with a compact voxel stride: vs % 4 == 0, J <= vs <= 32).
+//
+// One persistent launch; every CTA owns the tiles t = g, g + G, ... of every sample.  A producer warp streams
+// 16 KB logit tiles (+ the matching coordinate rows) into a 4-stage shared-memory ring with 1-D TMA bulk copies
+// (cp.async.bulk -> mbarrier complete_tx), so each SM keeps up to 128 KB of HBM reads in flight; 8 consumer warps
+// read the tile as a flat float4 array (conflict-free: thread = (row, 4-joint chunk)) and carry an online softmax
+// state (max, sum, 3 coordinate sums) per joint.
+//
+// Phases per CTA:  A(0), then for b = 0..B-1:  A(b+1), C(b).
+//   A(b): statistics pass over sample b; the CTA's partial goes to global memory, a per-sample arrival counter finds the
+//         last CTA, which merges all partials, writes the keypoints and the (max, sum) of every joint and raises flag[b].
+//   C(b): normalisation pass: the logits of sample b are read again -- they were streamed one phase ago and are still in
+//         the 126 MB L2, so HBM sees them once -- and exp(l - max)/sum is written in NCDHW through a shared-memory
+//         transpose (coalesced 128-byte streaming stores).
+// While the last CTA finalises sample b everybody else is already streaming A(b+1); C(b) only waits on flag[b].
+// All CTAs are co-resident (grid <= occupancy x SMs), waits are bounded (trap instead of hang).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedConsumers = 256;
+constexpr int kFusedThreads = kFusedConsumers + 32;   // + producer warp
+constexpr int kFusedStages = 4;
+constexpr int kFusedLogitBytes = 16384;
+constexpr int kFusedCoordBytes = 2560;
+constexpr int kFusedStageBytes = kFusedLogitBytes + kFusedCoordBytes;
+constexpr int kFusedScratchBytes = 20480;             // CTA merge scratch [256][20] floats, aliased with the transpose staging
+constexpr int kFusedSmemBytes = kFusedStages * kFusedStageBytes + kFusedScratchBytes + 128 + 128;
+constexpr int kMaxFusedCtas = 640;
+constexpr long kFusedMinVoxels = 16384;
+
+struct FusedParams {
+  const float* logits;    // [B][nvox][vs]
+  const float* coord;     // [B][nvox][3]
+  float* volumes;         // [B][J][nvox] or null
+  float* keypoints;       // [B][J][3]
+  float* partial;         // [B][G][J][5]
+  float* stats;           // [B][J][2]
+  int* counters;          // [B] arrivals of A(b)
+  int* flags;             // [B] stats of sample b are final
+  long bs, nvox;
+  int vs, B, J, Q, RPI, T, tiles, LD;
+  float mult;
+  int softmax;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kFusedThreads, 2) softargmax_fused_kernel(const FusedParams p) {
+  extern __shared__ uint8_t fsm_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fsm_raw) + 127) & ~(uintptr_t)127);
+  float* scratch = reinterpret_cast<float*>(smem + kFusedStages * kFusedStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFusedStages * kFusedStageBytes + kFusedScratchBytes);
+  uint64_t* empty = full + kFusedStages;
+  __shared__ int s_last;
+
+  const int g = blockIdx.x, G = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool sm = p.softmax != 0;
+  const bool want_vol = p.volumes != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFusedStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kFusedConsumers / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kFusedConsumers / 32) {
+    // ===================== producer warp =====================
+    uint32_t it = 0;
+    auto stream = [&](int b, bool with_coord) {
+      for (int t = g; t < p.tiles; t += G, ++it) {
+        const uint32_t s = it % kFusedStages;
+        mbar_wait(&empty[s], ((it / kFusedStages) & 1u) ^ 1u);
+        if (lane == 0) {
+          const long v0 = (long)t * p.T;
+          const int rows = (int)min((long)p.T, p.nvox - v0);
+          const uint32_t lb = (uint32_t)rows * (uint32_t)p.vs * 4u, cb = with_coord ? (uint32_t)rows * 12u : 0u;
+          uint8_t* dst = smem + (size_t)s * kFusedStageBytes;
+          mbar_expect_tx(&full[s], lb + cb);
+          bulk_load_1d(dst, p.logits + (long)b * p.bs + v0 * p.vs, lb, &full[s]);
+          if (with_coord) bulk_load_1d(dst + kFusedLogitBytes, p.coord + ((long)b * p.nvox + v0) * 3, cb, &full[s]);
+        }
+        __syncwarp();
+      }
+    };
+    stream(0, true);
+    for (int b = 0; b < p.B; ++b) {
+      if (b + 1 < p.B) stream(b + 1, true);
+      if (want_vol) stream(b, false);
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  const int tid = threadIdx.x;
+  const int row_l = tid / p.Q, c = tid % p.Q;
+  const bool active = (tid < p.RPI * p.Q) && (4 * c < p.J);
+  uint32_t it = 0;
+  SoftState st[4];
+
+  auto stats_phase = [&](int b) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st_init(st[i], sm);
+    for (int t = g; t < p.tiles; t += G, ++it) {
+      const uint32_t s = it % kFusedStages;
+      const int rows = (int)min((long)p.T, p.nvox - (long)t * p.T);
+      mbar_wait(&full[s], (it / kFusedStages) & 1u);
+      const uint32_t lbase = smem_u32(smem + (size_t)s * kFusedStageBytes);
+      const float* cd = reinterpret_cast<const float*>(smem + (size_t)s * kFusedStageBytes + kFusedLogitBytes);
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = k * p.RPI + row_l;
+          if (row < rows) {
+            const uint4 q = lds128(lbase + (uint32_t)(row * p.Q + c) * 16u);
+            const float x = cd[row * 3], y = cd[row * 3 + 1], z = cd[row * 3 + 2];
+            st_push(st[0], __uint_as_float(q.x) * p.mult, x, y, z, sm);
+            st_push(st[1], __uint_as_float(q.y) * p.mult, x, y, z, sm);
+            st_push(st[2], __uint_as_float(q.z) * p.mult, x, y, z, sm);
+            st_push(st[3], __uint_as_float(q.w) * p.mult, x, y, z, sm);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[s]);
+    }
+    // ---- CTA merge: scratch[tid][i*5 + k] ----
+    consumer_bar();   // previous users of the scratch region (transpose staging) are done
+    {
+      float* my = scratch + tid * 20;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        SoftState z;
+        st_init(z, sm);
+        const SoftState& a = active ? st[i] : z;
+        my[i * 5] = a.m; my[i * 5 + 1] = a.d; my[i * 5 + 2] = a.sx; my[i * 5 + 3] = a.sy; my[i * 5 + 4] = a.sz;
+      }
+    }
+    consumer_bar();
+    for (int j = warp; j < p.J; j += kFusedConsumers / 32) {
+      const int cj = j >> 2, ij = j & 3;
+      SoftState a;
+      st_init(a, sm);
+      for (int r = lane; r < p.RPI; r += 32) {
+        const float* src = scratch + (r * p.Q + cj) * 20 + ij * 5;
+        SoftState t{src[0], src[1], src[2], src[3], src[4]};
+        st_merge(a, t, sm);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(a, o); st_merge(a, t, sm); }
+      if (lane == 0) {
+        float* dst = p.partial + (((long)b * G + g) * p.J + j) * 5;
+        __stcg(dst, a.m); __stcg(dst + 1, a.d); __stcg(dst + 2, a.sx); __stcg(dst + 3, a.sy); __stcg(dst + 4, a.sz);
+        __threadfence();
+      }
+    }
+    consumer_bar();
+    if (tid == 0) {
+      __threadfence();
+      s_last = (atomicAdd(&p.counters[b], 1) == G - 1) ? 1 : 0;
+    }
+    consumer_bar();
+    if (s_last) {
+      // ---- last CTA of sample b: merge the G partials, write keypoints + (max, sum), raise the flag ----
+      __threadfence();
+      for (int j = warp; j < p.J; j += kFusedConsumers / 32) {
+        SoftState a;
+        st_init(a, sm);
+        for (int gg = lane; gg < G; gg += 32) {
+          const float* src = p.partial + (((long)b * G + gg) * p.J + j) * 5;
+          SoftState t{__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3), __ldcg(src + 4)};
+          st_merge(a, t, sm);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(a, o); st_merge(a, t, sm); }
+        if (lane == 0) {
+          float* k = p.keypoints + ((long)b * p.J + j) * 3;
+          if (sm) { k[0] = a.sx / a.d; k[1] = a.sy / a.d; k[2] = a.sz / a.d; }
+          else { k[0] = a.sx; k[1] = a.sy; k[2] = a.sz; }
+          __stcg(p.stats + ((long)b * p.J + j) * 2, a.m);
+          __stcg(p.stats + ((long)b * p.J + j) * 2 + 1, a.d);
+          __threadfence();
+        }
+      }
+      consumer_bar();
+      if (tid == 0) st_release_gpu(&p.flags[b], 1);
+    }
+  };
+
+  auto normalize_phase = [&](int b) {
+    if (tid == 0) {
+      if (ld_acquire_gpu(&p.flags[b]) == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(&p.flags[b]) == 0) {
+          if (clock64() - t0 > 4000000000LL) __trap();
+          __nanosleep(64);
+        }
+      }
+    }
+    consumer_bar();
+    __threadfence();
+    float mx[4], dn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = min(4 * c + i, p.J - 1);
+      mx[i] = __ldcg(p.stats + ((long)b * p.J + j) * 2);
+      dn[i] = __ldcg(p.stats + ((long)b * p.J + j) * 2 + 1);
+    }
+    float* stag = scratch;   // [J][LD]
+    for (int t = g; t < p.tiles; t += G, ++it) {
+      const uint32_t s = it % kFusedStages;
+      const long v0 = (long)t * p.T;
+      const int rows = (int)min((long)p.T, p.nvox - v0);
+      mbar_wait(&full[s], (it / kFusedStages) & 1u);
+      const uint32_t lbase = smem_u32(smem + (size_t)s * kFusedStageBytes);
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = k * p.RPI + row_l;
+          if (row < rows) {
+            const uint4 q = lds128(lbase + (uint32_t)(row * p.Q + c) * 16u);
+            const float l[4] = {__uint_as_float(q.x) * p.mult, __uint_as_float(q.y) * p.mult,
+                                __uint_as_float(q.z) * p.mult, __uint_as_float(q.w) * p.mult};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (4 * c + i < p.J) stag[(4 * c + i) * p.LD + row] = sm ? __expf(l[i] - mx[i]) / dn[i] : fmaxf(l[i], 0.0f);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(&empty[s]);
+      consumer_bar();
+      for (int j = warp; j < p.J; j += kFusedConsumers / 32) {
+        float* dst = p.volumes + ((long)b * p.J + j) * p.nvox + v0;
+        const float* src = stag + j * p.LD;
+        for (int r = lane; r < rows; r += 32) __stcs(dst + r, src[r]);
+      }
+      consumer_bar();
+    }
+  };
+
+  stats_phase(0);
+  for (int b = 0; b < p.B; ++b) {
+    if (b + 1 < p.B) stats_phase(b + 1);
+    if (want_vol) normalize_phase(b);
+  }
+}
+
 static inline int n_chunks(long nvox) { return (int)((nvox + kChunk - 1) / kChunk); }
 
 }  // namespace lt
 
 extern "C" size_t lt_softargmax3d_workspace_bytes(int B, int J, long nvox) {
-  return (size_t)B * J * ((size_t)lt::n_chunks(nvox) * 5 + 2) * sizeof(float);
+  const size_t classic = (size_t)B * J * ((size_t)lt::n_chunks(nvox) * 5 + 2) * sizeof(float);
+  // fused path: partial [B][G <= kMaxFusedCtas][J][5] + stats [B][J][2] + counters [B] + flags [B]
+  const size_t fused = (size_t)B * ((size_t)lt::kMaxFusedCtas * J * 5 + (size_t)J * 2 + 2) * sizeof(float) + 64;
+  return classic > fused ? classic : fused;
 }
 
 extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long voxel_stride, long chan_stride,
@@ -237,6 +504,44 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
   p.B = B; p.J = J; p.nvox = nvox; p.mult = multiplier; p.softmax = softmax;
   cudaStream_t st = (cudaStream_t)stream;
   const bool cl = (chan_stride == 1 && J <= 32 && voxel_stride >= J);
+  // ---- fused streaming path ----
+  static const int fused_mode = getenv("LT_SOFTARGMAX_FUSED") ? atoi(getenv("LT_SOFTARGMAX_FUSED")) : 1;
+  if (fused_mode && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 4 == 0 && batch_stride % 4 == 0 &&
+      nvox >= kFusedMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0) {
+    FusedParams f;
+    f.logits = logits; f.coord = coord; f.volumes = volumes_out; f.keypoints = keypoints_out;
+    f.bs = batch_stride; f.nvox = nvox; f.vs = (int)voxel_stride; f.B = B; f.J = J;
+    f.Q = f.vs / 4;
+    f.RPI = kFusedConsumers / f.Q;
+    f.T = 4 * f.RPI;
+    f.LD = f.T + 1;
+    f.tiles = (int)((nvox + f.T - 1) / f.T);
+    f.mult = multiplier; f.softmax = softmax;
+    static int max_ctas = 0;
+    if (!max_ctas) {
+      cudaError_t e = cudaFuncSetAttribute(softargmax_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes);
+      if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, softargmax_fused_kernel, kFusedThreads, kFusedSmemBytes);
+      if (e != cudaSuccess || per_sm < 1) return fail(LT_ERR_CUDA, "softargmax_fused: occupancy query failed");
+      if (per_sm > 2) per_sm = 2;
+      max_ctas = per_sm * sm_count();
+      if (max_ctas > kMaxFusedCtas) max_ctas = kMaxFusedCtas;
+    }
+    const int G = f.tiles < max_ctas ? f.tiles : max_ctas;
+    LT_REQUIRE(f.T * f.vs * 4 <= kFusedLogitBytes && f.T * 12 <= kFusedCoordBytes && J * f.LD * 4 <= kFusedScratchBytes,
+               "softargmax_fused: tile does not fit (vs=%d J=%d)", f.vs, J);
+    float* w = reinterpret_cast<float*>(workspace);
+    f.partial = w;
+    f.stats = w + (size_t)B * G * J * 5;
+    f.counters = reinterpret_cast<int*>(f.stats + (size_t)B * J * 2);
+    f.flags = f.counters + B;
+    cudaError_t e = cudaMemsetAsync(f.counters, 0, (size_t)2 * B * sizeof(int), st);
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax_fused: memset: %s", cudaGetErrorString(e));
+    softargmax_fused_kernel<<<G, kFusedThreads, kFusedSmemBytes, st>>>(f);
+    LT_CHECK_LAUNCH("softargmax_fused_kernel");
+    return LT_OK;
+  }
   if (cl) softargmax_partial_cl<<<dim3(p.nch, B), 256, 0, st>>>(p);
   else softargmax_partial_generic<<<dim3(p.nch, J, B), 256, 0, st>>>(p);
   LT_CHECK_LAUNCH("softargmax_partial");

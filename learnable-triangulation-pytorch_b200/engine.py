@@ -99,6 +99,7 @@ class NativeEngine:
         self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
+        self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
         self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
 
@@ -283,8 +284,10 @@ class NativeEngine:
         return y
 
     def _conv(self, x, pk, relu, residual=None, res_mode=RES_NONE, out=None, out_scale=(1, 1, 1), out_off=(0, 0, 0),
-              out_dims=None, out_fmt=None):
-        """Launch one conv. `out` (with out_scale/out_off) lets transposed-conv phases share an output tensor."""
+              out_dims=None, out_fmt=None, out_c=None):
+        """Launch one conv. `out` (with out_scale/out_off) lets transposed-conv phases share an output tensor.
+
+        out_c: channel stride of a float32 output narrower than the padded N tile (the TMA store clips the padding)."""
         if pk.impl == CONV_SIMT:
             x = self._as_f32(x)
         assert x.fmt == pk.in_fmt and x.C == pk.cin, (x.fmt, pk.in_fmt, x.C, pk.cin)
@@ -300,6 +303,8 @@ class NativeEngine:
         if out is None:
             fmt = self.act_fmt if out_fmt is None else out_fmt
             c = _round_up(pk.cout, 32) if fmt == FMT_S32 else pk.cout_p
+            if out_c is not None and fmt == FMT_F32 and pk.cout <= out_c <= pk.cout_p:
+                c = out_c
             out = Act(x.N, od, oh, ow, c, fmt, x.data.device)
         d = capi.ConvDesc(N=x.N, ID=x.D, IH=x.H, IW=x.W, Cin=x.C, OD=od, OH=oh, OW=ow, Cout=pk.cout_p,
                           KD=kd, KH=kh, KW=kw, sd=sd, sh=sh, sw=sw, pd=pd, ph=ph, pw=pw,
@@ -455,7 +460,10 @@ class NativeEngine:
         x = self._res3d(x, "back0")
         x = self._conv(x, P["back1"], relu=True)
         x = self._conv(x, P["back2"], relu=True)
-        return self._conv(x, P["output"], relu=False, out_fmt=FMT_F32)
+        # compact logits: 17 joints stored 20 wide (80-byte voxel rows) instead of the 32-wide N tile -> the soft-argmax
+        # streams 37 % fewer bytes; the conv's TMA store clips the 12 padding channels
+        out_c = _round_up(P["output"].cout, 4) if self.compact_logits else None
+        return self._conv(x, P["output"], relu=False, out_fmt=FMT_F32, out_c=out_c)
 
     def softargmax(self, logits, coord, J, multiplier, softmax):
         B, n = logits.N, logits.D
@@ -466,7 +474,10 @@ class NativeEngine:
         ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=dev)
         with self._timed("softargmax", nbytes=B * (2 * J * nvox * 4 + nvox * 12)):
             capi.softargmax3d(logits.data, nvox * logits.C, logits.C, 1, coord, volumes, keypoints, ws, B, J, nvox, multiplier, softmax)
-        self.launches += 3
+        # one persistent streaming kernel when the fused path applies (csrc/softargmax.cu), else partial / finalize / normalize
+        fused = (os.environ.get("LT_SOFTARGMAX_FUSED", "1") != "0" and logits.C % 4 == 0 and 20 <= logits.C <= 32
+                 and nvox % 4 == 0 and nvox >= 16384)
+        self.launches += 1 if fused else 3
         return keypoints, volumes
 
     # ------------------------------------------------------------------ whole device-side forward

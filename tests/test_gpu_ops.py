@@ -108,6 +108,34 @@ def test_softargmax_vs_oracle(softmax, layout):
     assert np.array_equal(v.view(B, J, -1).argmax(-1).cpu().numpy(), v_w.reshape(B, J, -1).argmax(-1))
 
 
+@pytest.mark.parametrize("softmax", [True, False])
+@pytest.mark.parametrize("Cp,J,n,B", [(20, 17, 32, 3), (32, 17, 28, 2), (24, 21, 26, 1), (20, 17, 64, 2)])
+def test_softargmax_fused_stream(softmax, Cp, J, n, B):
+    """Fused streaming path (nvox >= 16384, voxel stride 20..32): partial tail tiles, more tiles than CTAs (64^3),
+    fewer tiles than CTAs, NaN in the padding channels (must never leak), keypoints-only call."""
+    rng = np.random.RandomState(Cp + n)
+    vols = (rng.randn(B, J, n, n, n) * 3).astype(np.float32)
+    vols[:, :, n // 3, n // 2, n // 5] += 9.0          # a clear peak per joint
+    coord = (rng.randn(B, n, n, n, 3) * 700).astype(np.float32)
+    mult = 1.3
+    kp_w, v_w = O.integrate_tensor_3d_with_coordinates(vols * np.float32(mult), coord, softmax)
+    nvox = n ** 3
+    cl = torch.full((B, nvox, Cp), float("nan"), dtype=torch.float32, device=DEV)
+    cl[:, :, :J] = cu(vols).view(B, J, nvox).permute(0, 2, 1)
+    v = torch.empty((B, J, n, n, n), dtype=torch.float32, device=DEV)
+    kp = torch.empty((B, J, 3), dtype=torch.float32, device=DEV)
+    ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=DEV)
+    for _ in range(2):   # twice: the per-sample counters/flags in the workspace must be re-armed by every call
+        v.fill_(-1.0)
+        capi.softargmax3d(cl, nvox * Cp, Cp, 1, cu(coord).view(B, nvox, 3), v, kp, ws, B, J, nvox, mult, softmax)
+        assert rel_err(kp.cpu().numpy(), kp_w) < 3e-5
+        assert rel_err(v.cpu().numpy(), v_w) < 3e-5
+        assert np.array_equal(v.view(B, J, -1).argmax(-1).cpu().numpy(), v_w.reshape(B, J, -1).argmax(-1))
+    kp2 = torch.empty_like(kp)
+    capi.softargmax3d(cl, nvox * Cp, Cp, 1, cu(coord).view(B, nvox, 3), None, kp2, ws, B, J, nvox, mult, softmax)
+    assert torch.equal(kp2, kp)
+
+
 # ------------------------------------------------------------------------------------------ coordinate volume
 @pytest.mark.parametrize("theta,transfer", [(0.0, False), (0.0, True), (1.1, False)])
 def test_coord_volume(theta, transfer):

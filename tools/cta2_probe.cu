@@ -1,0 +1,200 @@
+// Micro-probe: tcgen05.mma issue cost for cta_group::1 vs cta_group::2 (SS mode, kind::f16, K = 16 per instruction),
+// plus a semantic check of the 2-CTA operand split (which CTA supplies which B rows / D columns).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/cta2_probe tools/cta2_probe.cu && /tmp/cta2_probe
+//
+// Output: one line per (cta_group, N pattern, grid) with cycles per instruction measured by the issuing thread around a
+// chain of back-to-back MMAs that ends in a tcgen05.commit -> mbarrier wait.  The model being tested:
+//   cta_group::1:  T = (128 + N) / 2 cycles      (A rows + B rows fetched from shared memory at 64 B/clk, 32 B per row)
+//   cta_group::2:  T = (128 + N/2) / 2 cycles    (each SM fetches its 128 A rows and HALF of the B rows), floor N/2.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {   // bounded: false on timeout
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 2000000000LL) return false;
+  return true;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// kind::f16: D=f32 (bit 4), A=B=fp16, K-major both, M (>>4) at bit 24, N (>>3) at bit 17
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
+template <int CG>
+__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (CG == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Result {
+  long long cycles;      // issue -> completion of the whole chain (leader CTA)
+  int n_instr;
+  float d[2][4];         // semantic check: D[row 5][col 0], [col N/2 - 1], [col N/2], [col N - 1] for CTA rank 0 / 1
+  int timeout;
+};
+
+// pattern: 0 = chain of N=n1 MMAs; 1 = alternate N=n1 / N=n2 (the product's hi*[hi;lo] + lo*hi pair)
+template <int CG>
+__global__ void __launch_bounds__(128, 1) probe_kernel(int n1, int n2, int pattern, int chain, Result* res) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  __half* A = reinterpret_cast<__half*>(smem);              // 128 rows x 64 fp16 (128B swizzle) = 16 KB
+  __half* Bm = reinterpret_cast<__half*>(smem + 16384);     // 256 rows x 32 fp16 (64B swizzle)  = 16 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 32768 + 64);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // constant tiles (swizzle-invariant): A = 1 (rank 0) / 3 (rank 1); B = 1 (rank 0) / 2 (rank 1)
+  const __half av = __float2half(rank == 0 ? 1.0f : 3.0f), bv = __float2half(rank == 0 ? 1.0f : 2.0f);
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) { A[i] = av; Bm[i] = bv; }
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<CG>(slot, 512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+
+  long long t0 = 0, t1 = 0;
+  int timeout = 0;
+  if (rank == 0 && warp == 1) {
+    const uint64_t ad = make_sw128_desc(smem_u32(A)), bd = make_sw64_desc(smem_u32(Bm));
+    const uint32_t id1 = make_idesc(128 * CG, n1), id2 = make_idesc(128 * CG, n2);
+    if (lane == 0) {
+      t0 = clock64();
+      for (int i = 0; i < chain; ++i) {
+        if (pattern == 0) umma<CG>(tmem, ad, bd, id1, i > 0);
+        else { umma<CG>(tmem, ad, bd, id1, i > 0); umma<CG>(tmem + 256, ad + 4, bd, id2, i > 0); }
+      }
+      commit<CG>(bar);
+    }
+    __syncwarp();
+  }
+  // everyone (both CTAs) waits for the commit (multicast for CG == 2)
+  if (!mbar_wait(bar, 0)) timeout = 1;
+  if (rank == 0 && warp == 1 && lane == 0) t1 = clock64();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // semantic check (block 0 / cluster 0 only): row 5 of this CTA's accumulator, four columns
+  if (blockIdx.x < CG && warp == 0) {
+    const int cols[4] = {0, n1 / 2 - 1, n1 / 2, n1 - 1};
+    for (int k = 0; k < 4; ++k) {
+      uint32_t v;
+      tmem_ld1(tmem + (uint32_t)cols[k], v);   // warp 0 -> lanes 0..31; lane 5 = row 5
+      if (lane == 5) res->d[rank][k] = __uint_as_float(v);
+    }
+  }
+  if (blockIdx.x == 0 && warp == 1 && lane == 0) { res->cycles = t1 - t0; res->n_instr = chain * (pattern == 0 ? 1 : 2); }
+  if (timeout && threadIdx.x == 0) atomicExch(&res->timeout, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 0) tmem_dealloc<CG>(tmem, 512);
+}
+
+template <int CG>
+static void run(int n1, int n2, int pattern, int chain, int grid, Result* dres) {
+  CK(cudaMemset(dres, 0, sizeof(Result)));
+  const size_t smem = 32768 + 128 + 1024;
+  CK(cudaFuncSetAttribute(probe_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  for (int rep = 0; rep < 2; ++rep) {   // second run is warm
+    CK(cudaLaunchKernelEx(&cfg, probe_kernel<CG>, n1, n2, pattern, chain, dres));
+    CK(cudaDeviceSynchronize());
+  }
+  Result r;
+  CK(cudaMemcpy(&r, dres, sizeof(r), cudaMemcpyDeviceToHost));
+  const double per = (double)r.cycles / r.n_instr;
+  const double model = pattern == 0 ? (CG == 1 ? (128 + n1) / 2.0 : (128 + n1 / 2.0) / 2.0)
+                                    : (CG == 1 ? ((128 + n1) + (128 + n2)) / 4.0 : ((128 + n1 / 2.0) + (128 + n2 / 2.0)) / 4.0);
+  printf("cta_group=%d grid=%3d pattern=%d N=%3d/%3d chain=%d: %.1f cyc/instr (model %.1f, math floor %.1f)%s\n", CG, grid, pattern, n1,
+         pattern ? n2 : 0, chain, per, model, pattern == 0 ? n1 / 2.0 : (n1 + n2) / 4.0, r.timeout ? "  TIMEOUT" : "");
+  if (pattern == 0 && chain == 1)
+    printf("   semantic: cta0 D[5][0,N/2-1,N/2,N-1] = %.0f %.0f %.0f %.0f   cta1 = %.0f %.0f %.0f %.0f\n", r.d[0][0], r.d[0][1], r.d[0][2],
+           r.d[0][3], r.d[1][0], r.d[1][1], r.d[1][2], r.d[1][3]);
+}
+
+int main() {
+  Result* dres;
+  CK(cudaMalloc(&dres, sizeof(Result)));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  printf("SMs: %d\n", sms);
+  // semantic check: one K=16 MMA, N = 128.  Expected if "B rows [0, N/2) come from CTA 0 and [N/2, N) from CTA 1":
+  //   cta0 (A = 1): 16 16 32 32     cta1 (A = 3): 48 48 96 96        (cta_group::1: 16 16 16 16)
+  run<1>(128, 0, 0, 1, 1, dres);
+  run<2>(128, 0, 0, 1, 2, dres);
+  const int ns[] = {32, 64, 96, 128, 192, 256};
+  for (int n : ns) { run<1>(n, 0, 0, 256, 1, dres); run<2>(n, 0, 0, 256, 2, dres); }
+  for (int n : ns) { run<1>(n, 0, 0, 256, sms, dres); run<2>(n, 0, 0, 256, sms & ~1, dres); }
+  // product patterns: (2Nt, Nt) pairs
+  const int nts[] = {32, 64, 96, 128};
+  for (int nt : nts) { run<1>(2 * nt, nt, 1, 128, sms, dres); run<2>(2 * nt, nt, 1, 128, sms & ~1, dres); run<2>(2 * nt, 2 * nt, 1, 128, sms & ~1, dres); }
+  printf("done\n");
+  return 0;
+}
