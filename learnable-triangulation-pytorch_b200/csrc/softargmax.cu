@@ -214,45 +214,42 @@ __global__ void __launch_bounds__(256) softargmax_normalize_generic(const SoftPa
 
 
 // ------------------------------------------------------------------------------------------------
-// Fused streaming path (channels-last logits with a compact voxel stride: vs % 4 == 0, J <= vs <= 32).
+// Streaming path (channels-last logits with a compact voxel stride: vs % 4 == 0, 20 <= vs <= 32, J <= vs).
 //
-// One persistent launch; every CTA owns the tiles t = g, g + G, ... of every sample.  A producer warp streams
-// 16 KB logit tiles (+ the matching coordinate rows) into a 4-stage shared-memory ring with 1-D TMA bulk copies
-// (cp.async.bulk -> mbarrier complete_tx), so each SM keeps up to 128 KB of HBM reads in flight; 8 consumer warps
-// read the tile as a flat float4 array (conflict-free: thread = (row, 4-joint chunk)) and carry an online softmax
-// state (max, sum, 3 coordinate sums) per joint.
+// Two persistent kernels + a tiny merge, each CTA owning the flat tiles f = g, g + G, ... of the whole batch
+// (f -> sample f / tiles, tile f % tiles; ~35 tiles per CTA, balanced to 1 %).  In both kernels a producer warp
+// streams 16 KB logit tiles (stats pass: + the matching coordinate rows) into a 4-stage shared-memory ring with 1-D
+// TMA bulk copies (cp.async.bulk -> mbarrier complete_tx): up to 128 KB of reads in flight per SM, no register staging.
 //
-// Phases per CTA:  A(0), then for b = 0..B-1:  A(b+1), C(b).
-//   A(b): statistics pass over sample b; the CTA's partial goes to global memory, a per-sample arrival counter finds the
-//         last CTA, which merges all partials, writes the keypoints and the (max, sum) of every joint and raises flag[b].
-//   C(b): normalisation pass: the logits of sample b are read again -- they were streamed one phase ago and are still in
-//         the 126 MB L2, so HBM sees them once -- and exp(l - max)/sum is written in NCDHW through a shared-memory
-//         transpose (coalesced 128-byte streaming stores).
-// While the last CTA finalises sample b everybody else is already streaming A(b+1); C(b) only waits on flag[b].
-// All CTAs are co-resident (grid <= occupancy x SMs), waits are bounded (trap instead of hang).
+//   stream_stats_kernel      8 consumer warps read the tile as a flat float4 array (conflict-free: thread = (row, 4-joint
+//                            chunk)) and fold 4 rows x 4 joints per step into an online-softmax state (one rescale + four
+//                            ex2 per joint per step); per (sample, CTA) partials -> global memory.
+//   softargmax_stream_merge  one warp per (sample, joint): merges the G partials -> keypoints, (max, 1/sum).
+//   stream_normalize_kernel  same ring, samples in REVERSE order (the tail of the stats pass is still in the 126 MB L2);
+//                            a warp reads 8 rows x 4 joints per instruction (bank-conflict free for 80- and 112-byte rows) and
+//                            writes exp(l - max) / sum in NCDHW as four full 32-byte sectors (streaming stores).
 // ------------------------------------------------------------------------------------------------
-constexpr int kFusedConsumers = 256;
-constexpr int kFusedThreads = kFusedConsumers + 32;   // + producer warp
-constexpr int kFusedStages = 4;
-constexpr int kFusedLogitBytes = 16384;
-constexpr int kFusedCoordBytes = 2560;
-constexpr int kFusedStageBytes = kFusedLogitBytes + kFusedCoordBytes;
-constexpr int kFusedScratchBytes = 20480;             // CTA merge scratch [256][20] floats, aliased with the transpose staging
-constexpr int kFusedSmemBytes = kFusedStages * kFusedStageBytes + kFusedScratchBytes + 128 + 128;
-constexpr int kMaxFusedCtas = 640;
-constexpr long kFusedMinVoxels = 16384;
+constexpr int kStreamConsumers = 256;
+constexpr int kStreamThreads = kStreamConsumers + 32;   // + producer warp
+constexpr int kStreamStages = 4;
+constexpr int kStreamLogitBytes = 16384;
+constexpr int kStreamCoordBytes = 2560;
+constexpr int kStreamStageBytes = kStreamLogitBytes + kStreamCoordBytes;
+constexpr int kStreamScratchBytes = 20480;             // CTA merge scratch [256][20] floats (stats kernel)
+constexpr int kStreamSmemBytes = kStreamStages * kStreamStageBytes + kStreamScratchBytes + 128 + 128;
+constexpr int kMaxStreamCtas = 640;
+constexpr long kStreamMinVoxels = 16384;
+constexpr float kLog2e = 1.4426950408889634f;
 
-struct FusedParams {
+struct StreamParams {
   const float* logits;    // [B][nvox][vs]
   const float* coord;     // [B][nvox][3]
-  float* volumes;         // [B][J][nvox] or null
+  float* volumes;         // [B][J][nvox]
   float* keypoints;       // [B][J][3]
   float* partial;         // [B][G][J][5]
-  float* stats;           // [B][J][2]
-  int* counters;          // [B] arrivals of A(b)
-  int* flags;             // [B] stats of sample b are final
-  long bs, nvox;
-  int vs, B, J, Q, RPI, T, tiles, LD;
+  float* stats;           // [B][J][2] = (max, 1 / sum)
+  long bs, nvox, total_tiles;
+  int vs, B, J, Q, RPI, T, tiles, G;
   float mult;
   int softmax;
 };
@@ -264,214 +261,232 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
-__global__ void __launch_bounds__(kFusedThreads, 2) softargmax_fused_kernel(const FusedParams p) {
+// producer warp: stream the CTA's tiles in order; reverse = samples from last to first
+__device__ __forceinline__ void stream_producer(const StreamParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, bool with_coord,
+                                                bool reverse) {
+  const int lane = threadIdx.x & 31;
+  uint32_t it = 0;
+  for (long f = blockIdx.x; f < p.total_tiles; f += gridDim.x, ++it) {
+    const uint32_t s = it % kStreamStages;
+    mbar_wait(&empty[s], ((it / kStreamStages) & 1u) ^ 1u);
+    if (lane == 0) {
+      int b = (int)(f / p.tiles);
+      const int t = (int)(f % p.tiles);
+      if (reverse) b = p.B - 1 - b;
+      const long v0 = (long)t * p.T;
+      const int rows = (int)min((long)p.T, p.nvox - v0);
+      const uint32_t lb = (uint32_t)rows * (uint32_t)p.vs * 4u, cb = with_coord ? (uint32_t)rows * 12u : 0u;
+      uint8_t* dst = smem + (size_t)s * kStreamStageBytes;
+      mbar_expect_tx(&full[s], lb + cb);
+      bulk_load_1d(dst, p.logits + (long)b * p.bs + v0 * p.vs, lb, &full[s]);
+      if (with_coord) bulk_load_1d(dst + kStreamLogitBytes, p.coord + ((long)b * p.nvox + v0) * 3, cb, &full[s]);
+    }
+    __syncwarp();
+  }
+}
+
+// fold four (logit, coordinate) pairs into one online-softmax state: one rescale + four exponentials
+template <bool SM>
+__device__ __forceinline__ void st_push4(SoftState& s, const float (&l)[4], const float (&x)[4], const float (&y)[4], const float (&z)[4]) {
+  if (SM) {
+    const float mn = fmaxf(fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3])), s.m);
+    if (mn == -INFINITY) return;                 // nothing but padding so far
+    const float nb = -mn * kLog2e;
+    const float r = ex2f(fmaf(s.m, kLog2e, nb)); // exp(m_old - m_new); 0 for the first batch (m_old = -inf)
+    const float e0 = ex2f(fmaf(l[0], kLog2e, nb)), e1 = ex2f(fmaf(l[1], kLog2e, nb));
+    const float e2 = ex2f(fmaf(l[2], kLog2e, nb)), e3 = ex2f(fmaf(l[3], kLog2e, nb));
+    s.d = fmaf(s.d, r, (e0 + e1) + (e2 + e3));
+    s.sx = fmaf(s.sx, r, fmaf(e0, x[0], fmaf(e1, x[1], fmaf(e2, x[2], e3 * x[3]))));
+    s.sy = fmaf(s.sy, r, fmaf(e0, y[0], fmaf(e1, y[1], fmaf(e2, y[2], e3 * y[3]))));
+    s.sz = fmaf(s.sz, r, fmaf(e0, z[0], fmaf(e1, z[1], fmaf(e2, z[2], e3 * z[3]))));
+    s.m = mn;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = fmaxf(l[k], 0.0f);         // op.py:90-91: ReLU, no normalisation
+      s.sx = fmaf(e, x[k], s.sx); s.sy = fmaf(e, y[k], s.sy); s.sz = fmaf(e, z[k], s.sz);
+    }
+  }
+}
+
+template <bool SM>
+__global__ void __launch_bounds__(kStreamThreads, 2) stream_stats_kernel(const StreamParams p) {
   extern __shared__ uint8_t fsm_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fsm_raw) + 127) & ~(uintptr_t)127);
-  float* scratch = reinterpret_cast<float*>(smem + kFusedStages * kFusedStageBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFusedStages * kFusedStageBytes + kFusedScratchBytes);
-  uint64_t* empty = full + kFusedStages;
-  __shared__ int s_last;
-
+  float* scratch = reinterpret_cast<float*>(smem + kStreamStages * kStreamStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStreamStages * kStreamStageBytes + kStreamScratchBytes);
+  uint64_t* empty = full + kStreamStages;
   const int g = blockIdx.x, G = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool sm = p.softmax != 0;
-  const bool want_vol = p.volumes != nullptr;
-
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFusedStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kFusedConsumers / 32); }
+    for (int s = 0; s < kStreamStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStreamConsumers / 32); }
     fence_barrier_init();
   }
   __syncthreads();
+  if (warp == kStreamConsumers / 32) { stream_producer(p, smem, full, empty, true, false); return; }
 
-  if (warp == kFusedConsumers / 32) {
-    // ===================== producer warp =====================
-    uint32_t it = 0;
-    auto stream = [&](int b, bool with_coord) {
-      for (int t = g; t < p.tiles; t += G, ++it) {
-        const uint32_t s = it % kFusedStages;
-        mbar_wait(&empty[s], ((it / kFusedStages) & 1u) ^ 1u);
-        if (lane == 0) {
-          const long v0 = (long)t * p.T;
-          const int rows = (int)min((long)p.T, p.nvox - v0);
-          const uint32_t lb = (uint32_t)rows * (uint32_t)p.vs * 4u, cb = with_coord ? (uint32_t)rows * 12u : 0u;
-          uint8_t* dst = smem + (size_t)s * kFusedStageBytes;
-          mbar_expect_tx(&full[s], lb + cb);
-          bulk_load_1d(dst, p.logits + (long)b * p.bs + v0 * p.vs, lb, &full[s]);
-          if (with_coord) bulk_load_1d(dst + kFusedLogitBytes, p.coord + ((long)b * p.nvox + v0) * 3, cb, &full[s]);
-        }
-        __syncwarp();
-      }
-    };
-    stream(0, true);
-    for (int b = 0; b < p.B; ++b) {
-      if (b + 1 < p.B) stream(b + 1, true);
-      if (want_vol) stream(b, false);
-    }
-    return;
-  }
-
-  // ===================== consumer warps =====================
   const int tid = threadIdx.x;
   const int row_l = tid / p.Q, c = tid % p.Q;
   const bool active = (tid < p.RPI * p.Q) && (4 * c < p.J);
-  uint32_t it = 0;
   SoftState st[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st_init(st[i], SM);
 
-  auto stats_phase = [&](int b) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) st_init(st[i], sm);
-    for (int t = g; t < p.tiles; t += G, ++it) {
-      const uint32_t s = it % kFusedStages;
-      const int rows = (int)min((long)p.T, p.nvox - (long)t * p.T);
-      mbar_wait(&full[s], (it / kFusedStages) & 1u);
-      const uint32_t lbase = smem_u32(smem + (size_t)s * kFusedStageBytes);
-      const float* cd = reinterpret_cast<const float*>(smem + (size_t)s * kFusedStageBytes + kFusedLogitBytes);
-      if (active) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = k * p.RPI + row_l;
-          if (row < rows) {
-            const uint4 q = lds128(lbase + (uint32_t)(row * p.Q + c) * 16u);
-            const float x = cd[row * 3], y = cd[row * 3 + 1], z = cd[row * 3 + 2];
-            st_push(st[0], __uint_as_float(q.x) * p.mult, x, y, z, sm);
-            st_push(st[1], __uint_as_float(q.y) * p.mult, x, y, z, sm);
-            st_push(st[2], __uint_as_float(q.z) * p.mult, x, y, z, sm);
-            st_push(st[3], __uint_as_float(q.w) * p.mult, x, y, z, sm);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(&empty[s]);
+  // samples in which this CTA owns no tile still need an (identity) partial for the merge
+  for (int i = tid; i < p.B * p.J; i += kStreamConsumers) {
+    const int b = i / p.J, j = i % p.J;
+    const long lo = (long)b * p.tiles;
+    const long f0 = lo + (((long)g - lo) % G + G) % G;     // first flat tile >= lo owned by this CTA
+    if (!(f0 < lo + p.tiles)) {
+      float* dst = p.partial + (((long)b * G + g) * p.J + j) * 5;
+      dst[0] = SM ? -INFINITY : 0.0f; dst[1] = 0.f; dst[2] = 0.f; dst[3] = 0.f; dst[4] = 0.f;
     }
-    // ---- CTA merge: scratch[tid][i*5 + k] ----
-    consumer_bar();   // previous users of the scratch region (transpose staging) are done
-    {
-      float* my = scratch + tid * 20;
+  }
+
+  auto flush = [&](int b) {   // CTA merge of the per-thread states -> partial[b][g][*], then reset
+    consumer_bar();
+    float* my = scratch + tid * 20;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        SoftState z;
-        st_init(z, sm);
-        const SoftState& a = active ? st[i] : z;
-        my[i * 5] = a.m; my[i * 5 + 1] = a.d; my[i * 5 + 2] = a.sx; my[i * 5 + 3] = a.sy; my[i * 5 + 4] = a.sz;
-      }
+    for (int i = 0; i < 4; ++i) {
+      SoftState z;
+      st_init(z, SM);
+      const SoftState& a = active ? st[i] : z;
+      my[i * 5] = a.m; my[i * 5 + 1] = a.d; my[i * 5 + 2] = a.sx; my[i * 5 + 3] = a.sy; my[i * 5 + 4] = a.sz;
+      st_init(st[i], SM);
     }
     consumer_bar();
-    for (int j = warp; j < p.J; j += kFusedConsumers / 32) {
+    for (int j = warp; j < p.J; j += kStreamConsumers / 32) {
       const int cj = j >> 2, ij = j & 3;
       SoftState a;
-      st_init(a, sm);
+      st_init(a, SM);
       for (int r = lane; r < p.RPI; r += 32) {
         const float* src = scratch + (r * p.Q + cj) * 20 + ij * 5;
         SoftState t{src[0], src[1], src[2], src[3], src[4]};
-        st_merge(a, t, sm);
+        st_merge(a, t, SM);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(a, o); st_merge(a, t, sm); }
+      for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(a, o); st_merge(a, t, SM); }
       if (lane == 0) {
         float* dst = p.partial + (((long)b * G + g) * p.J + j) * 5;
-        __stcg(dst, a.m); __stcg(dst + 1, a.d); __stcg(dst + 2, a.sx); __stcg(dst + 3, a.sy); __stcg(dst + 4, a.sz);
-        __threadfence();
+        dst[0] = a.m; dst[1] = a.d; dst[2] = a.sx; dst[3] = a.sy; dst[4] = a.sz;
       }
-    }
-    consumer_bar();
-    if (tid == 0) {
-      __threadfence();
-      s_last = (atomicAdd(&p.counters[b], 1) == G - 1) ? 1 : 0;
-    }
-    consumer_bar();
-    if (s_last) {
-      // ---- last CTA of sample b: merge the G partials, write keypoints + (max, sum), raise the flag ----
-      __threadfence();
-      for (int j = warp; j < p.J; j += kFusedConsumers / 32) {
-        SoftState a;
-        st_init(a, sm);
-        for (int gg = lane; gg < G; gg += 32) {
-          const float* src = p.partial + (((long)b * G + gg) * p.J + j) * 5;
-          SoftState t{__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3), __ldcg(src + 4)};
-          st_merge(a, t, sm);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(a, o); st_merge(a, t, sm); }
-        if (lane == 0) {
-          float* k = p.keypoints + ((long)b * p.J + j) * 3;
-          if (sm) { k[0] = a.sx / a.d; k[1] = a.sy / a.d; k[2] = a.sz / a.d; }
-          else { k[0] = a.sx; k[1] = a.sy; k[2] = a.sz; }
-          __stcg(p.stats + ((long)b * p.J + j) * 2, a.m);
-          __stcg(p.stats + ((long)b * p.J + j) * 2 + 1, a.d);
-          __threadfence();
-        }
-      }
-      consumer_bar();
-      if (tid == 0) st_release_gpu(&p.flags[b], 1);
     }
   };
 
-  auto normalize_phase = [&](int b) {
-    if (tid == 0) {
-      if (ld_acquire_gpu(&p.flags[b]) == 0) {
-        const long long t0 = clock64();
-        while (ld_acquire_gpu(&p.flags[b]) == 0) {
-          if (clock64() - t0 > 4000000000LL) __trap();
-          __nanosleep(64);
+  uint32_t it = 0;
+  int cur_b = -1;
+  for (long f = g; f < p.total_tiles; f += G, ++it) {
+    const int b = (int)(f / p.tiles), t = (int)(f % p.tiles);
+    if (b != cur_b) {
+      if (cur_b >= 0) flush(cur_b);
+      cur_b = b;
+    }
+    const uint32_t s = it % kStreamStages;
+    const int rows = (int)min((long)p.T, p.nvox - (long)t * p.T);
+    mbar_wait(&full[s], (it / kStreamStages) & 1u);
+    const uint32_t lbase = smem_u32(smem + (size_t)s * kStreamStageBytes);
+    const float* cd = reinterpret_cast<const float*>(smem + (size_t)s * kStreamStageBytes + kStreamLogitBytes);
+    if (active) {
+      float l[4][4], x[4], y[4], z[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = k * p.RPI + row_l;
+        if (row < rows) {
+          const uint4 q = lds128(lbase + (uint32_t)(row * p.Q + c) * 16u);
+          l[0][k] = __uint_as_float(q.x) * p.mult; l[1][k] = __uint_as_float(q.y) * p.mult;
+          l[2][k] = __uint_as_float(q.z) * p.mult; l[3][k] = __uint_as_float(q.w) * p.mult;
+          x[k] = cd[row * 3]; y[k] = cd[row * 3 + 1]; z[k] = cd[row * 3 + 2];
+        } else {   // rows past the end of a sample's last tile: no weight, finite coordinates
+          l[0][k] = l[1][k] = l[2][k] = l[3][k] = SM ? -INFINITY : 0.0f;
+          x[k] = y[k] = z[k] = 0.0f;
         }
       }
-    }
-    consumer_bar();
-    __threadfence();
-    float mx[4], dn[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = min(4 * c + i, p.J - 1);
-      mx[i] = __ldcg(p.stats + ((long)b * p.J + j) * 2);
-      dn[i] = __ldcg(p.stats + ((long)b * p.J + j) * 2 + 1);
+      for (int i = 0; i < 4; ++i) st_push4<SM>(st[i], l[i], x, y, z);
     }
-    float* stag = scratch;   // [J][LD]
-    for (int t = g; t < p.tiles; t += G, ++it) {
-      const uint32_t s = it % kFusedStages;
-      const long v0 = (long)t * p.T;
-      const int rows = (int)min((long)p.T, p.nvox - v0);
-      mbar_wait(&full[s], (it / kFusedStages) & 1u);
-      const uint32_t lbase = smem_u32(smem + (size_t)s * kFusedStageBytes);
-      if (active) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = k * p.RPI + row_l;
-          if (row < rows) {
-            const uint4 q = lds128(lbase + (uint32_t)(row * p.Q + c) * 16u);
-            const float l[4] = {__uint_as_float(q.x) * p.mult, __uint_as_float(q.y) * p.mult,
-                                __uint_as_float(q.z) * p.mult, __uint_as_float(q.w) * p.mult};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (4 * c + i < p.J) stag[(4 * c + i) * p.LD + row] = sm ? __expf(l[i] - mx[i]) / dn[i] : fmaxf(l[i], 0.0f);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_local(&empty[s]);
-      consumer_bar();
-      for (int j = warp; j < p.J; j += kFusedConsumers / 32) {
-        float* dst = p.volumes + ((long)b * p.J + j) * p.nvox + v0;
-        const float* src = stag + j * p.LD;
-        for (int r = lane; r < rows; r += 32) __stcs(dst + r, src[r]);
-      }
-      consumer_bar();
-    }
-  };
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(&empty[s]);
+  }
+  if (cur_b >= 0) flush(cur_b);
+}
 
-  stats_phase(0);
-  for (int b = 0; b < p.B; ++b) {
-    if (b + 1 < p.B) stats_phase(b + 1);
-    if (want_vol) normalize_phase(b);
+// one warp per (sample, joint): merge the G partials -> keypoints, (max, 1 / sum)
+__global__ void __launch_bounds__(128) softargmax_stream_merge(const StreamParams p) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= p.B * p.J) return;
+  const int b = gw / p.J, j = gw % p.J;
+  const bool sm = p.softmax != 0;
+  SoftState a;
+  st_init(a, sm);
+  for (int gg = lane; gg < p.G; gg += 32) {
+    const float* src = p.partial + (((long)b * p.G + gg) * p.J + j) * 5;
+    SoftState t{src[0], src[1], src[2], src[3], src[4]};
+    st_merge(a, t, sm);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(a, o); st_merge(a, t, sm); }
+  if (lane == 0) {
+    float* k = p.keypoints + (long)gw * 3;
+    if (sm) { k[0] = a.sx / a.d; k[1] = a.sy / a.d; k[2] = a.sz / a.d; }
+    else { k[0] = a.sx; k[1] = a.sy; k[2] = a.sz; }
+    p.stats[gw * 2] = a.m;
+    p.stats[gw * 2 + 1] = 1.0f / a.d;
+  }
+}
+
+template <bool SM>
+__global__ void __launch_bounds__(kStreamThreads, 2) stream_normalize_kernel(const StreamParams p) {
+  extern __shared__ uint8_t fsm_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fsm_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStreamStages * kStreamStageBytes + kStreamScratchBytes);
+  uint64_t* empty = full + kStreamStages;
+  const int g = blockIdx.x, G = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStreamStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStreamConsumers / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == kStreamConsumers / 32) { stream_producer(p, smem, full, empty, false, true); return; }
+
+  // lane = (row within an 8-row group, joint within a 4-joint group): one LDS covers 8 rows x 4 joints -- 32 distinct banks
+  // for a row stride of 20 or 28 words (the compact 17/21..28-joint layouts) --, one STG writes four aligned 32-byte sectors (T and the tile origins are multiples of 8 rows)
+  const int ji = lane & 3, rr = lane >> 2;
+  const int jgroups = (p.J + 3) >> 2;
+  uint32_t it = 0;
+  for (long f = g; f < p.total_tiles; f += G, ++it) {
+    const int b = p.B - 1 - (int)(f / p.tiles), t = (int)(f % p.tiles);
+    const uint32_t s = it % kStreamStages;
+    const long v0 = (long)t * p.T;
+    const int rows = (int)min((long)p.T, p.nvox - v0);
+    const int rgroups = (rows + 7) >> 3;
+    mbar_wait(&full[s], (it / kStreamStages) & 1u);
+    const float* tile = reinterpret_cast<const float*>(smem + (size_t)s * kStreamStageBytes);
+    for (int jg = 0; jg < jgroups; ++jg) {
+      const int j = jg * 4 + ji;
+      const bool jok = j < p.J;
+      const float2 ms = jok ? __ldg(reinterpret_cast<const float2*>(p.stats + ((long)b * p.J + j) * 2)) : make_float2(0.f, 0.f);
+      const float nb = -ms.x * kLog2e;
+      float* dst = p.volumes + ((long)b * p.J + (jok ? j : 0)) * p.nvox + v0;
+      for (int rg = warp; rg < rgroups; rg += kStreamConsumers / 32) {
+        const int r = rg * 8 + rr;
+        if (jok && r < rows) {
+          const float v = tile[r * p.vs + j] * p.mult;          // same rounding as the statistics pass
+          const float o = SM ? ex2f(fmaf(v, kLog2e, nb)) * ms.y : fmaxf(v, 0.0f);
+          __stcs(dst + r, o);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_local(&empty[s]);
   }
 }
 
@@ -481,9 +496,9 @@ static inline int n_chunks(long nvox) { return (int)((nvox + kChunk - 1) / kChun
 
 extern "C" size_t lt_softargmax3d_workspace_bytes(int B, int J, long nvox) {
   const size_t classic = (size_t)B * J * ((size_t)lt::n_chunks(nvox) * 5 + 2) * sizeof(float);
-  // fused path: partial [B][G <= kMaxFusedCtas][J][5] + stats [B][J][2] + counters [B] + flags [B]
-  const size_t fused = (size_t)B * ((size_t)lt::kMaxFusedCtas * J * 5 + (size_t)J * 2 + 2) * sizeof(float) + 64;
-  return classic > fused ? classic : fused;
+  // streaming path: partial [B][G <= kMaxStreamCtas][J][5] + stats [B][J][2]
+  const size_t stream = (size_t)B * ((size_t)lt::kMaxStreamCtas * J * 5 + (size_t)J * 2) * sizeof(float) + 64;
+  return classic > stream ? classic : stream;
 }
 
 extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long voxel_stride, long chan_stride,
@@ -504,42 +519,46 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
   p.B = B; p.J = J; p.nvox = nvox; p.mult = multiplier; p.softmax = softmax;
   cudaStream_t st = (cudaStream_t)stream;
   const bool cl = (chan_stride == 1 && J <= 32 && voxel_stride >= J);
-  // ---- fused streaming path ----
-  static const int fused_mode = getenv("LT_SOFTARGMAX_FUSED") ? atoi(getenv("LT_SOFTARGMAX_FUSED")) : 1;
-  if (fused_mode && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 4 == 0 && batch_stride % 4 == 0 &&
-      nvox >= kFusedMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0) {
-    FusedParams f;
+  // ---- streaming path ----
+  static const int stream_mode = getenv("LT_SOFTARGMAX_FUSED") ? atoi(getenv("LT_SOFTARGMAX_FUSED")) : 1;
+  if (stream_mode && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 8 == 0 && batch_stride % 4 == 0 &&
+      nvox >= kStreamMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0 &&
+      (!volumes_out || ((uintptr_t)volumes_out & 31) == 0)) {
+    StreamParams f;
     f.logits = logits; f.coord = coord; f.volumes = volumes_out; f.keypoints = keypoints_out;
     f.bs = batch_stride; f.nvox = nvox; f.vs = (int)voxel_stride; f.B = B; f.J = J;
     f.Q = f.vs / 4;
-    f.RPI = kFusedConsumers / f.Q;
+    f.RPI = (kStreamConsumers / f.Q) & ~1;      // rows per pass, even -> T = 4 * RPI is a multiple of 8 rows
     f.T = 4 * f.RPI;
-    f.LD = f.T + 1;
     f.tiles = (int)((nvox + f.T - 1) / f.T);
+    f.total_tiles = (long)f.tiles * B;
     f.mult = multiplier; f.softmax = softmax;
+    LT_REQUIRE(f.T * f.vs * 4 <= kStreamLogitBytes && f.T * 12 <= kStreamCoordBytes, "softargmax stream: tile does not fit (vs=%d)", f.vs);
     static int max_ctas = 0;
     if (!max_ctas) {
-      cudaError_t e = cudaFuncSetAttribute(softargmax_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes);
-      if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      int per_sm = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, softargmax_fused_kernel, kFusedThreads, kFusedSmemBytes);
-      if (e != cudaSuccess || per_sm < 1) return fail(LT_ERR_CUDA, "softargmax_fused: occupancy query failed");
-      if (per_sm > 2) per_sm = 2;
-      max_ctas = per_sm * sm_count();
-      if (max_ctas > kMaxFusedCtas) max_ctas = kMaxFusedCtas;
+      cudaError_t e = cudaFuncSetAttribute(stream_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+      if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      max_ctas = 2 * sm_count();
+      if (max_ctas > kMaxStreamCtas) max_ctas = kMaxStreamCtas;
     }
-    const int G = f.tiles < max_ctas ? f.tiles : max_ctas;
-    LT_REQUIRE(f.T * f.vs * 4 <= kFusedLogitBytes && f.T * 12 <= kFusedCoordBytes && J * f.LD * 4 <= kFusedScratchBytes,
-               "softargmax_fused: tile does not fit (vs=%d J=%d)", f.vs, J);
+    const int G = f.total_tiles < max_ctas ? (int)f.total_tiles : max_ctas;
+    f.G = G;
     float* w = reinterpret_cast<float*>(workspace);
     f.partial = w;
-    f.stats = w + (size_t)B * G * J * 5;
-    f.counters = reinterpret_cast<int*>(f.stats + (size_t)B * J * 2);
-    f.flags = f.counters + B;
-    cudaError_t e = cudaMemsetAsync(f.counters, 0, (size_t)2 * B * sizeof(int), st);
-    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax_fused: memset: %s", cudaGetErrorString(e));
-    softargmax_fused_kernel<<<G, kFusedThreads, kFusedSmemBytes, st>>>(f);
-    LT_CHECK_LAUNCH("softargmax_fused_kernel");
+    f.stats = w + (((size_t)B * G * J * 5 + 3) & ~(size_t)3);   // 16-byte aligned (read as float2)
+    if (softmax) stream_stats_kernel<true><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
+    else stream_stats_kernel<false><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
+    LT_CHECK_LAUNCH("stream_stats_kernel");
+    softargmax_stream_merge<<<ceil_div((long)B * J * 32, 128), 128, 0, st>>>(f);
+    LT_CHECK_LAUNCH("softargmax_stream_merge");
+    if (volumes_out) {
+      if (softmax) stream_normalize_kernel<true><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
+      else stream_normalize_kernel<false><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
+      LT_CHECK_LAUNCH("stream_normalize_kernel");
+    }
     return LT_OK;
   }
   if (cl) softargmax_partial_cl<<<dim3(p.nch, B), 256, 0, st>>>(p);

@@ -440,8 +440,8 @@ __device__ __forceinline__ const float4* q_at(const float4* base, unsigned idx) 
   return reinterpret_cast<const float4*>(r);
 }
 
-template <int MAXV, int FMT, bool EXACT>   // EXACT: V == MAXV (no per-view predicates at all)
-__global__ void __launch_bounds__(256) unproject_v2_kernel(const UnprojParams p) {
+template <int MAXV, int FMT, bool EXACT, int MINB>   // EXACT: V == MAXV (no per-view predicates at all); MINB: min CTAs / SM
+__global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojParams p) {
   __shared__ float sP[MAXV * 12];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < p.V * 12; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
@@ -608,11 +608,16 @@ static int launch_unproject(const float* features, const float* proj, const floa
   const bool pow2q = (units & (units - 1)) == 0;
   static const int v2_mode = getenv("LT_UNPROJECT_V2") ? atoi(getenv("LT_UNPROJECT_V2")) : 1;
   if (v2_mode && C == 32 && agg == LT_AGG_SOFTMAX && partial == 0 && V <= 8 && (long)V * h * w * C < (1L << 30)) {
+    // register budget of the 4-view kernel (min CTAs/SM): 5 -> 48 registers (default), 4 -> 64, 6 -> 40, 1 -> 90
+    static const int lb = getenv("LT_UNPROJECT_LB") ? atoi(getenv("LT_UNPROJECT_LB")) : 5;
 #define LT_UNPROJ_V2(FMT)                                                                   \
-    if (V == 4) unproject_v2_kernel<4, FMT, true><<<grid, 256, 0, st>>>(p);                \
-    else if (V == 8) unproject_v2_kernel<8, FMT, true><<<grid, 256, 0, st>>>(p);           \
-    else if (V < 4) unproject_v2_kernel<4, FMT, false><<<grid, 256, 0, st>>>(p);           \
-    else unproject_v2_kernel<8, FMT, false><<<grid, 256, 0, st>>>(p)
+    if (V == 4 && lb == 4) unproject_v2_kernel<4, FMT, true, 4><<<grid, 256, 0, st>>>(p);  \
+    else if (V == 4 && lb == 6) unproject_v2_kernel<4, FMT, true, 6><<<grid, 256, 0, st>>>(p); \
+    else if (V == 4 && lb == 1) unproject_v2_kernel<4, FMT, true, 1><<<grid, 256, 0, st>>>(p); \
+    else if (V == 4) unproject_v2_kernel<4, FMT, true, 5><<<grid, 256, 0, st>>>(p);        \
+    else if (V == 8) unproject_v2_kernel<8, FMT, true, 3><<<grid, 256, 0, st>>>(p);        \
+    else if (V < 4) unproject_v2_kernel<4, FMT, false, 5><<<grid, 256, 0, st>>>(p);        \
+    else unproject_v2_kernel<8, FMT, false, 3><<<grid, 256, 0, st>>>(p)
     if (out_format == LT_FMT_F32) { LT_UNPROJ_V2(LT_FMT_F32); } else { LT_UNPROJ_V2(LT_FMT_S32); }
 #undef LT_UNPROJ_V2
   } else if (vec4 && stored && pow2q && C <= 128) {

@@ -474,10 +474,7 @@ class NativeEngine:
         ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=dev)
         with self._timed("softargmax", nbytes=B * (2 * J * nvox * 4 + nvox * 12)):
             capi.softargmax3d(logits.data, nvox * logits.C, logits.C, 1, coord, volumes, keypoints, ws, B, J, nvox, multiplier, softmax)
-        # one persistent streaming kernel when the fused path applies (csrc/softargmax.cu), else partial / finalize / normalize
-        fused = (os.environ.get("LT_SOFTARGMAX_FUSED", "1") != "0" and logits.C % 4 == 0 and 20 <= logits.C <= 32
-                 and nvox % 4 == 0 and nvox >= 16384)
-        self.launches += 1 if fused else 3
+        self.launches += 3   # statistics / merge / normalise (streaming or classic kernels, csrc/softargmax.cu)
         return keypoints, volumes
 
     # ------------------------------------------------------------------ whole device-side forward

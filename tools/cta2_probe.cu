@@ -179,6 +179,141 @@ static void run(int n1, int n2, int pattern, int chain, int grid, Result* dres) 
            r.d[0][3], r.d[1][0], r.d[1][1], r.d[1][2], r.d[1][3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mode "ring": the conv kernel's issue pattern with DISTINCT operands per chunk -- a ring of STAGES (A 16 KB + B 16 KB)
+// tiles, four MMAs per chunk (A_hi x [B_hi;B_lo] N=2Nt, A_lo x B_hi N=Nt, twice), no TMA (static shared memory), the
+// issue loop unrolled by the ring depth.  variant (cta_group::2 only): 0 = second MMA N=Nt into a third accumulator,
+// 1 = second MMA N=2Nt ("zero-row" B tile).  Reports cycles per chunk of the issuing CTA.
+// ------------------------------------------------------------------------------------------------
+template <int CG, int STAGES>
+__global__ void __launch_bounds__(128, 1) ring_kernel(int nt, int variant, int chunks, Result* res) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + STAGES * 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + STAGES * 32768 + 64);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < STAGES * 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0
+  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<CG>(slot, CG == 2 ? 512 : 256);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+  long long t0 = 0, t1 = 0;
+  int timeout = 0;
+  if (rank == 0 && warp == 1) {
+    const int n1 = 2 * nt, n2 = (CG == 2 && variant == 1) ? 2 * nt : nt;
+    const uint32_t id1 = make_idesc(128 * CG, n1), id2 = make_idesc(128 * CG, n2);
+    const uint32_t d1 = tmem, d2 = (CG == 2 && variant == 0) ? tmem + 2 * nt : tmem + nt;
+    if (lane == 0) {
+      t0 = clock64();
+      for (int q = 0; q < chunks; q += STAGES) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+          const uint32_t a_addr = smem_u32(smem + s * 32768);
+          const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw64_desc(a_addr + 16384);
+          const uint32_t acc = (q | s) ? 1u : 0u;
+          umma<CG>(d1, ad, bd, id1, acc);
+          umma<CG>(d2, ad + 4, bd, id2, acc);
+          umma<CG>(d1, ad + 2, bd + 2, id1, 1);
+          umma<CG>(d2, ad + 6, bd + 2, id2, 1);
+        }
+      }
+      commit<CG>(bar);
+    }
+    __syncwarp();
+  }
+  if (!mbar_wait(bar, 0)) timeout = 1;
+  if (rank == 0 && warp == 1 && lane == 0) t1 = clock64();
+  if (blockIdx.x == 0 && warp == 1 && lane == 0) { res->cycles = t1 - t0; res->n_instr = chunks; }
+  if (timeout && threadIdx.x == 0) atomicExch(&res->timeout, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 0) tmem_dealloc<CG>(tmem, CG == 2 ? 512 : 256);
+}
+
+template <int CG, int STAGES>
+static void run_ring(int nt, int variant, int grid, int ctas_per_sm, Result* dres) {
+  CK(cudaMemset(dres, 0, sizeof(Result)));
+  const size_t smem = (size_t)STAGES * 32768 + 128 + 1024;
+  CK(cudaFuncSetAttribute(ring_kernel<CG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  const int chunks = 256;
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaLaunchKernelEx(&cfg, ring_kernel<CG, STAGES>, nt, variant, chunks, dres));
+    CK(cudaDeviceSynchronize());
+  }
+  Result r;
+  CK(cudaMemcpy(&r, dres, sizeof(r), cudaMemcpyDeviceToHost));
+  const int n2 = (CG == 2 && variant == 1) ? 2 * nt : nt;
+  printf("ring cta_group=%d stages=%d Nt=%3d (MMA N=%3d + N=%3d) grid=%3d (%d CTA/SM): %.1f cyc/chunk (math floor %.1f; 1-CTA fetch model %.1f)%s\n",
+         CG, STAGES, nt, 2 * nt, n2, grid, ctas_per_sm, (double)r.cycles / r.n_instr, 2.0 * (2 * nt + n2) / 2.0,
+         2.0 * ((128 + 2 * nt) + (128 + nt)) / 2.0, r.timeout ? "  TIMEOUT" : "");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mode "feed": L2 -> shared-memory bandwidth of 1-D TMA bulk copies (16 KB each, DEPTH in flight per CTA) out of a
+// window that fits in L2: the ceiling for kernels that re-read operand tiles from L2 (implicit-GEMM taps).
+// ------------------------------------------------------------------------------------------------
+template <int DEPTH>
+__global__ void __launch_bounds__(64, 1) feed_kernel(const uint8_t* buf, size_t window, int copies, unsigned long long* total_cycles) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DEPTH * 16384);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DEPTH; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    size_t off = ((size_t)blockIdx.x * 1234567u * 16384u) % window;
+    for (int i = 0; i < copies + DEPTH; ++i) {
+      const int s = i % DEPTH;
+      if (i >= DEPTH) { if (!mbar_wait(&bars[s], ((i / DEPTH) - 1) & 1)) break; }
+      if (i < copies) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(16384u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem + s * 16384)), "l"(buf + off), "r"(16384u), "r"(smem_u32(&bars[s])) : "memory");
+        off += 16384u * 37u;
+        if (off >= window) off -= window;
+      }
+    }
+    atomicAdd(total_cycles, (unsigned long long)(clock64() - t0));
+  }
+}
+
+template <int DEPTH>
+static void run_feed(const uint8_t* buf, size_t window, int grid, unsigned long long* dcyc) {
+  const size_t smem = (size_t)DEPTH * 16384 + 256 + 1024;
+  CK(cudaFuncSetAttribute(feed_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int copies = 2048;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaMemset(dcyc, 0, 8));
+    CK(cudaEventRecord(e0));
+    feed_kernel<DEPTH><<<grid, 64, smem>>>(buf, window, copies, dcyc);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double bytes = (double)grid * copies * 16384.0;
+  printf("feed depth=%d window=%zu MB grid=%3d: %.1f GB/s aggregate (%.1f GB/s per CTA)\n", DEPTH, window >> 20, grid, bytes / best / 1e6,
+         bytes / best / 1e6 / grid);
+}
+
 int main() {
   Result* dres;
   CK(cudaMalloc(&dres, sizeof(Result)));
@@ -195,6 +330,28 @@ int main() {
   // product patterns: (2Nt, Nt) pairs
   const int nts[] = {32, 64, 96, 128};
   for (int nt : nts) { run<1>(2 * nt, nt, 1, 128, sms, dres); run<2>(2 * nt, nt, 1, 128, sms & ~1, dres); run<2>(2 * nt, 2 * nt, 1, 128, sms & ~1, dres); }
+  // product issue pattern with distinct operands
+  const int rnts[] = {64, 96, 128};
+  for (int nt : rnts) {
+    run_ring<1, 4>(nt, 0, sms, 1, dres);
+    run_ring<2, 4>(nt, 0, sms & ~1, 1, dres);
+    run_ring<2, 4>(nt, 1, sms & ~1, 1, dres);
+  }
+  run_ring<1, 3>(128, 0, 2 * sms, 2, dres);      // two independent CTAs per SM sharing the tensor pipe
+  run_ring<1, 3>(64, 0, 2 * sms, 2, dres);
+  // L2 -> shared memory feed rate
+  {
+    uint8_t* buf; unsigned long long* dcyc;
+    const size_t window = (size_t)48 << 20;
+    CK(cudaMalloc(&buf, window + (1 << 20)));
+    CK(cudaMemset(buf, 1, window + (1 << 20)));
+    CK(cudaMalloc(&dcyc, 8));
+    run_feed<4>(buf, window, sms, dcyc);
+    run_feed<8>(buf, window, sms, dcyc);
+    run_feed<4>(buf, window, 2 * sms, dcyc);
+    run_feed<8>(buf, (size_t)16 << 20, sms, dcyc);
+    run_feed<12>(buf, (size_t)16 << 20, sms, dcyc);
+  }
   printf("done\n");
   return 0;
 }
