@@ -273,12 +273,13 @@ __device__ __forceinline__ void stream_producer(const StreamParams& p, uint8_t* 
                                                 bool reverse) {
   const int lane = threadIdx.x & 31;
   uint32_t it = 0;
-  for (long f = blockIdx.x; f < p.total_tiles; f += gridDim.x, ++it) {
+  const unsigned total = (unsigned)p.total_tiles, tiles = (unsigned)p.tiles;
+  for (unsigned f = blockIdx.x; f < total; f += gridDim.x, ++it) {
     const uint32_t s = it % kStreamStages;
     mbar_wait(&empty[s], ((it / kStreamStages) & 1u) ^ 1u);
     if (lane == 0) {
-      int b = (int)(f / p.tiles);
-      const int t = (int)(f % p.tiles);
+      int b = (int)(f / tiles);
+      const int t = (int)(f - (unsigned)b * tiles);
       if (reverse) b = p.B - 1 - b;
       const long v0 = (long)t * p.T;
       const int rows = (int)min((long)p.T, p.nvox - v0);
@@ -382,8 +383,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_stats_kernel(const S
 
   uint32_t it = 0;
   int cur_b = -1;
-  for (long f = g; f < p.total_tiles; f += G, ++it) {
-    const int b = (int)(f / p.tiles), t = (int)(f % p.tiles);
+  const unsigned total = (unsigned)p.total_tiles, tiles = (unsigned)p.tiles;
+  for (unsigned f = g; f < total; f += G, ++it) {
+    const int b = (int)(f / tiles), t = (int)(f - (unsigned)b * tiles);
     if (b != cur_b) {
       if (cur_b >= 0) flush(cur_b);
       cur_b = b;
@@ -462,8 +464,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_normalize_kernel(con
   const int ji = lane & 3, rr = lane >> 2;
   const int jgroups = (p.J + 3) >> 2;
   uint32_t it = 0;
-  for (long f = g; f < p.total_tiles; f += G, ++it) {
-    const int b = p.B - 1 - (int)(f / p.tiles), t = (int)(f % p.tiles);
+  const unsigned total = (unsigned)p.total_tiles, tiles = (unsigned)p.tiles;
+  for (unsigned f = g; f < total; f += G, ++it) {
+    const int bf = (int)(f / tiles), t = (int)(f - (unsigned)bf * tiles);
+    const int b = p.B - 1 - bf;
     const uint32_t s = it % kStreamStages;
     const long v0 = (long)t * p.T;
     const int rows = (int)min((long)p.T, p.nvox - v0);
@@ -534,6 +538,7 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
     f.total_tiles = (long)f.tiles * B;
     f.mult = multiplier; f.softmax = softmax;
     LT_REQUIRE(f.T * f.vs * 4 <= kStreamLogitBytes && f.T * 12 <= kStreamCoordBytes, "softargmax stream: tile does not fit (vs=%d)", f.vs);
+    LT_REQUIRE(f.total_tiles < (1L << 31), "softargmax stream: too many tiles");
     static int max_ctas = 0;
     if (!max_ctas) {
       cudaError_t e = cudaFuncSetAttribute(stream_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);

@@ -608,13 +608,14 @@ static int launch_unproject(const float* features, const float* proj, const floa
   const bool pow2q = (units & (units - 1)) == 0;
   static const int v2_mode = getenv("LT_UNPROJECT_V2") ? atoi(getenv("LT_UNPROJECT_V2")) : 1;
   if (v2_mode && C == 32 && agg == LT_AGG_SOFTMAX && partial == 0 && V <= 8 && (long)V * h * w * C < (1L << 30)) {
-    // register budget of the 4-view kernel (min CTAs/SM): 5 -> 48 registers (default), 4 -> 64, 6 -> 40, 1 -> 90
-    static const int lb = getenv("LT_UNPROJECT_LB") ? atoi(getenv("LT_UNPROJECT_LB")) : 5;
+    // register budget of the 4-view kernel (min CTAs/SM), measured on B200 at config #2 shapes: 4 -> 64 registers 0.292 ms
+    // (default), 5 -> 48 registers 0.299 ms, 6 -> 40 registers 0.344 ms, 1 -> 90 registers 0.377 ms
+    static const int lb = getenv("LT_UNPROJECT_LB") ? atoi(getenv("LT_UNPROJECT_LB")) : 4;
 #define LT_UNPROJ_V2(FMT)                                                                   \
-    if (V == 4 && lb == 4) unproject_v2_kernel<4, FMT, true, 4><<<grid, 256, 0, st>>>(p);  \
-    else if (V == 4 && lb == 6) unproject_v2_kernel<4, FMT, true, 6><<<grid, 256, 0, st>>>(p); \
+    if (V == 4 && lb == 6) unproject_v2_kernel<4, FMT, true, 6><<<grid, 256, 0, st>>>(p); \
     else if (V == 4 && lb == 1) unproject_v2_kernel<4, FMT, true, 1><<<grid, 256, 0, st>>>(p); \
-    else if (V == 4) unproject_v2_kernel<4, FMT, true, 5><<<grid, 256, 0, st>>>(p);        \
+    else if (V == 4 && lb == 5) unproject_v2_kernel<4, FMT, true, 5><<<grid, 256, 0, st>>>(p); \
+    else if (V == 4) unproject_v2_kernel<4, FMT, true, 4><<<grid, 256, 0, st>>>(p);        \
     else if (V == 8) unproject_v2_kernel<8, FMT, true, 3><<<grid, 256, 0, st>>>(p);        \
     else if (V < 4) unproject_v2_kernel<4, FMT, false, 5><<<grid, 256, 0, st>>>(p);        \
     else unproject_v2_kernel<8, FMT, false, 3><<<grid, 256, 0, st>>>(p)

@@ -2,8 +2,10 @@
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) == 1:
-    for dbg in ("0", "3"):
-        env = dict(os.environ, LT_FOLD_DBG=dbg)
+    for dbg in ("0", "1", "2", "3", "0p"):   # "0p": production path with the in-kernel wait counters (LT_FOLD_PROF)
+        env = dict(os.environ, LT_FOLD_DBG=dbg[0])
+        if dbg.endswith("p"):
+            env["LT_FOLD_PROF"] = "1"
         r = subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True)
         print("LT_FOLD_DBG=" + dbg, r.stdout.strip())
         print("\n".join(sorted(set(l for l in r.stderr.strip().splitlines() if "fold prof" in l))[:8]))
