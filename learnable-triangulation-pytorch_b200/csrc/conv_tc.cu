@@ -46,6 +46,7 @@ struct TcParams {
   // writes its raw fp32 accumulator tile to ws[z][m tile][128][ws_ld]; splitk_reduce_kernel sums and applies the epilogue
   int splits, ws_ld;
   float* ws;
+  int bres;   // host-side request: B-resident persistent variant (Nt = 64 sub-tiles of the 128-wide packed weight tiles)
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
@@ -94,32 +95,37 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
 
   if (warp == 0) {
     // ================= TMA producer (whole warp runs the loop; one elected lane issues) =================
-    for (int q = 0; q < nchunks; ++q) {
-      const int s = q % p.stages;
-      const uint32_t ph = (uint32_t)((q / p.stages) & 1);
+    // chunk -> (tap, channel block) and ring slot / phase are advanced incrementally: no integer division in the loop
+    // (a handful of runtime divisions per chunk cost more issue latency than the chunk's MMAs take to execute)
+    int tap = q_begin / p.CB, cb = q_begin - tap * p.CB;
+    int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+    int s = 0;
+    uint32_t ph = 0;
+    const int ax = ow0 * p.sw - p.pw, ay = oh0 * p.sh - p.ph, az = od0 * p.sd - p.pd, bn0 = n0 * p.b_nmul;
+    for (int q = 0, qa = q_begin; q < nchunks; ++q, ++qa) {
       mbar_wait(&empty[s], ph ^ 1u);
-      const int qa = q_begin + q;
-      const int tap = qa / p.CB, cb = qa % p.CB;
-      const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
       uint8_t* a_dst = smem + (size_t)s * stage_bytes;
       uint8_t* b_dst = a_dst + kATileBytes;
       if (elect_one()) {
         mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-        tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 * p.sw - p.pw + kw, oh0 * p.sh - p.ph + kh, od0 * p.sd - p.pd + kd, nb0);
-        tma_load_2d(b_dst, &tmB, &full[s], qa * p.b_step0, qa * p.b_step1 + n0 * p.b_nmul);
+        tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ax + kw, ay + kh, az + kd, nb0);
+        tma_load_2d(b_dst, &tmB, &full[s], qa * p.b_step0, qa * p.b_step1 + bn0);
       }
       __syncwarp();
+      if (++cb == p.CB) { cb = 0; if (++kw == p.KW) { kw = 0; if (++kh == p.KH) { kh = 0; ++kd; } } }
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
     const uint32_t idesc = make_idesc_f16(p.Nt), idesc2 = make_idesc_f16(2 * p.Nt);
     const uint32_t tmem_d2 = tmem_base + (uint32_t)p.Nt;   // second accumulator: cross terms (scaled by 2^11)
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t ring0 = smem_u32(smem);
     for (int q = 0; q < nchunks; ++q) {
-      const int s = q % p.stages;
-      const uint32_t ph = (uint32_t)((q / p.stages) & 1);
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t a_addr = ring0 + (uint32_t)(s * stage_bytes);
       const uint32_t b_addr = a_addr + kATileBytes;
       const uint64_t ad = make_sw128_desc(a_addr);
       const uint64_t bd = (p.terms == 0) ? make_sw128_desc(b_addr) : make_sw64_desc(b_addr);
@@ -148,6 +154,7 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
         if (q == nchunks - 1) umma_commit(tmem_full); // accumulator complete
       }
       __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ================= epilogue (warps 2..9: two per TMEM lane quadrant, 16 channels of each block each) =================
@@ -285,6 +292,11 @@ struct TcPersistExtra {
   int n_tiles;        // N tiles
   long total_tiles;   // M tiles * N tiles
   int off_out, off_res, off_bar;   // smem offsets
+  // B-resident mode (1x1 convs with K * Nt * 128 B of weights <= ~64 KB): CTA = (N tile, M stream); the CTA's weight
+  // tile is loaded ONCE into shared memory (off_b) and only A tiles stream through the ring -- the per-SM L2 ingest
+  // (64 B/clk, tools/cta2_probe.cu) then carries 16 KB instead of 16 KB + Nt * 128 B per K chunk
+  int b_resident, off_b, m_streams;
+  long m_tiles;
 };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
@@ -299,15 +311,17 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.Nt * 128;
-  const int stage_bytes = kATileBytes + b_bytes;
+  const int stage_bytes = x.b_resident ? kATileBytes : kATileBytes + b_bytes;
   uint8_t* out_stage = smem + x.off_out;   // 2 x 16 KB
   uint8_t* res_stage = smem + x.off_res;   // 2 x 16 KB
+  uint8_t* b_smem = smem + x.off_b;        // resident weights (b_resident): nchunks x b_bytes
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + x.off_bar);
   uint64_t* empty = full + p.stages;
   uint64_t* acc_full = empty + p.stages;   // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint64_t* res_full = acc_empty + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* b_full = res_full + 2;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int nchunks = p.KD * p.KH * p.KW * p.CB;
@@ -316,6 +330,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads); mbar_init(&res_full[i], 1); }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
@@ -326,9 +341,15 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   // tile -> coordinates (N tile fastest: CTAs running side by side share the A tile in L2)
+  // B-resident mode: `tile` is this CTA's k-th M tile (k * m_streams + stream), the N tile is fixed per CTA
+  const int my_nt = x.b_resident ? (int)(blockIdx.x % x.n_tiles) : 0;
+  const long tile_first = x.b_resident ? (long)(blockIdx.x / x.n_tiles) : (long)blockIdx.x;
+  const long tile_step = x.b_resident ? (long)x.m_streams : (long)gridDim.x;
+  const long tile_end = x.b_resident ? x.m_tiles : x.total_tiles;
   auto decode = [&](long tile, int& ow0, int& oh0, int& od0, int& nb0, int& n0) {
-    n0 = (int)(tile % x.n_tiles) * p.Nt;
-    long t = tile / x.n_tiles;
+    long t;
+    if (x.b_resident) { n0 = my_nt * p.Nt; t = tile; }
+    else { n0 = (int)(tile % x.n_tiles) * p.Nt; t = tile / x.n_tiles; }
     ow0 = (int)(t % p.tw) * p.bw; t /= p.tw;
     oh0 = (int)(t % p.th) * p.bh; t /= p.th;
     od0 = (int)(t % p.td) * p.bd; t /= p.td;
@@ -337,39 +358,56 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 
   if (warp == 0) {
     // ================= TMA producer =================
-    uint32_t g = 0;   // global chunk counter (ring position)
-    for (long tile = blockIdx.x; tile < x.total_tiles; tile += gridDim.x) {
+    uint32_t rs = 0, rph = 0;   // ring slot / phase, running across tiles
+    if (x.b_resident) {
+      if (elect_one()) {
+        mbar_expect_tx(b_full, (uint32_t)(nchunks * b_bytes));
+        // weights are packed in 128-wide N tiles [128 hi rows ; 128 lo rows]; this CTA's 64-wide sub-tile = two 64-row boxes
+        const int n0r = my_nt * p.Nt;
+        for (int q = 0; q < nchunks; ++q) {
+          const int row = q * p.b_step1 + (n0r >> 7) * 256 + (n0r & 127);
+          tma_load_2d(b_smem + (size_t)q * b_bytes, &tmB, b_full, q * p.b_step0, row);
+          tma_load_2d(b_smem + (size_t)q * b_bytes + b_bytes / 2, &tmB, b_full, q * p.b_step0, row + 128);
+        }
+      }
+      __syncwarp();
+    }
+    for (long tile = tile_first; tile < tile_end; tile += tile_step) {
       int ow0, oh0, od0, nb0, n0;
       decode(tile, ow0, oh0, od0, nb0, n0);
-      for (int q = 0; q < nchunks; ++q, ++g) {
-        const uint32_t s = g % (uint32_t)p.stages;
-        mbar_wait(&empty[s], ((g / (uint32_t)p.stages) & 1u) ^ 1u);
-        const int tap = q / p.CB, cb = q % p.CB;
-        const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
-        uint8_t* a_dst = smem + (size_t)s * stage_bytes;
+      const int ax = ow0 * p.sw - p.pw, ay = oh0 * p.sh - p.ph, az = od0 * p.sd - p.pd, bn0 = n0 * p.b_nmul;
+      int cb = 0, kw = 0, kh = 0, kd = 0;     // incremental chunk -> (tap, channel block); ring slot / phase likewise
+      for (int q = 0; q < nchunks; ++q) {
+        mbar_wait(&empty[rs], rph ^ 1u);
+        uint8_t* a_dst = smem + (size_t)rs * stage_bytes;
         if (elect_one()) {
-          mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-          tma_load_5d(a_dst, &tmA, &full[s], cb * 64, ow0 * p.sw - p.pw + kw, oh0 * p.sh - p.ph + kh, od0 * p.sd - p.pd + kd, nb0);
-          tma_load_2d(a_dst + kATileBytes, &tmB, &full[s], q * p.b_step0, q * p.b_step1 + n0 * p.b_nmul);
+          mbar_expect_tx(&full[rs], (uint32_t)stage_bytes);
+          tma_load_5d(a_dst, &tmA, &full[rs], cb * 64, ax + kw, ay + kh, az + kd, nb0);
+          if (!x.b_resident) tma_load_2d(a_dst + kATileBytes, &tmB, &full[rs], q * p.b_step0, q * p.b_step1 + bn0);
         }
         __syncwarp();
+        if (++cb == p.CB) { cb = 0; if (++kw == p.KW) { kw = 0; if (++kh == p.KH) { kh = 0; ++kd; } } }
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = make_idesc_f16(p.Nt), idesc2 = make_idesc_f16(2 * p.Nt);
-    uint32_t g = 0, it = 0;
-    for (long tile = blockIdx.x; tile < x.total_tiles; tile += gridDim.x, ++it) {
+    uint32_t rs = 0, rph = 0, it = 0;
+    const uint32_t ring0 = smem_u32(smem), bres0 = smem_u32(b_smem);
+    if (x.b_resident) { mbar_wait(b_full, 0); tc_fence_after(); }
+    for (long tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
       const uint32_t as = it & 1u;
       mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d1 = tmem_base + as * (uint32_t)acc_cols, d2 = d1 + (uint32_t)p.Nt;
-      for (int q = 0; q < nchunks; ++q, ++g) {
-        const uint32_t s = g % (uint32_t)p.stages;
-        mbar_wait(&full[s], (g / (uint32_t)p.stages) & 1u);
+      for (int q = 0; q < nchunks; ++q) {
+        const uint32_t s = rs;
+        mbar_wait(&full[s], rph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw64_desc(a_addr + kATileBytes);
+        const uint32_t a_addr = ring0 + s * (uint32_t)stage_bytes;
+        const uint64_t ad = make_sw128_desc(a_addr);
+        const uint64_t bd = make_sw64_desc(x.b_resident ? bres0 + (uint32_t)(q * b_bytes) : a_addr + kATileBytes);
         const uint32_t first = (q == 0) ? 0u : 1u;
         if (elect_one()) {
           if (p.terms == 3) {
@@ -385,6 +423,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
           if (q == nchunks - 1) umma_commit(&acc_full[as]);
         }
         __syncwarp();
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1u; }
       }
     }
   } else {
@@ -399,10 +438,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     // Residual tiles stream through two 16 KB buffers indexed by a block counter that runs across tiles: global block
     // c = (k-th tile of this CTA, block c % nblk) lives in buffer c & 1 and is requested two blocks ahead, so the blocks of
     // the NEXT tile are already in flight while the main loop of that tile runs.
-    const long my_tiles = (x.total_tiles > (long)blockIdx.x) ? (x.total_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const long my_tiles = (tile_end > tile_first) ? (tile_end - 1 - tile_first) / tile_step + 1 : 0;
     const long total_blocks = my_tiles * nblk;
     auto issue_res = [&](long c) {   // leader only
-      const long tile_c = (long)blockIdx.x + (c / nblk) * (long)gridDim.x;
+      const long tile_c = tile_first + (c / nblk) * tile_step;
       const int blk = (int)(c % nblk);
       int a0, a1, a2, a3, an;
       decode(tile_c, a0, a1, a2, a3, an);
@@ -414,7 +453,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       for (long c = 0; c < 2 && c < total_blocks; ++c) issue_res(c);
     uint32_t it = 0;
     long c = 0;   // global block counter
-    for (long tile = blockIdx.x; tile < x.total_tiles; tile += gridDim.x, ++it) {
+    for (long tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
       int ow0, oh0, od0, nb0, n0;
       decode(tile, ow0, oh0, od0, nb0, n0);
       const uint32_t as = it & 1u;
@@ -602,27 +641,39 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // 0.73 -> 0.41 ms for three launches), where CTA setup (TMEM alloc, barrier init, descriptor fetch) dominates.
   const int nchunks_total = p.KD * p.KH * p.KW * p.CB;
   const bool tiny_tiles = nchunks_total * (p.Nt / 32) <= 2 && m_tiles * n_tiles > 4L * sm_count();
-  if ((persist_mode == 2 || (persist_mode == 1 && tiny_tiles)) && p.tma_epi && p.terms != 0 && m_tiles * n_tiles > (long)sm_count()) {
+  // B-resident persistent variant (requested by conv_tc_fwd_terms through p.bres): K-short 1x1 layers whose N tiles re-read
+  // the same A tiles -- the per-SM L2 ingest, not the tensor pipe, bounds them
+  const long bres_bytes = (long)nchunks_total * p.Nt * 128;
+  const bool bres = p.bres != 0;
+  if (bres || ((persist_mode == 2 || (persist_mode == 1 && tiny_tiles)) && p.tma_epi && p.terms != 0 && m_tiles * n_tiles > (long)sm_count())) {
     // persistent variant: one CTA per SM, deep operand ring + dedicated epilogue staging, two TMEM accumulator stages
     TcPersistExtra x;
     x.n_tiles = n_tiles;
     x.total_tiles = m_tiles * n_tiles;
-    int pst = (128 * 1024) / stage_bytes;
+    x.b_resident = bres ? 1 : 0;
+    x.m_tiles = m_tiles;
+    x.m_streams = bres ? sm_count() / n_tiles : 0;
+    const int ring_stage = bres ? kATileBytes : stage_bytes;
+    int pst = ((bres ? 96 : 128) * 1024) / ring_stage;
     if (pst > 8) pst = 8;
     if (pst < 2) pst = 2;
+    if (bres && pst > 6) pst = 6;
     p.stages = pst;
-    const int ring = pst * stage_bytes;
-    x.off_out = (ring + 1023) & ~1023;
+    const int ring = pst * ring_stage;
+    x.off_b = (ring + 1023) & ~1023;
+    x.off_out = bres ? (int)((x.off_b + bres_bytes + 1023) & ~1023L) : x.off_b;
     x.off_res = x.off_out + 32768;
     x.off_bar = x.off_res + 32768;
-    const size_t psmem = (size_t)x.off_bar + (2 * pst + 6) * 8 + 16 + 1024;
+    const size_t psmem = (size_t)x.off_bar + (2 * pst + 7) * 8 + 16 + 1024;
+    if (psmem > 227 * 1024) return fail(LT_ERR_INVALID, "conv_tc_persist: shared memory budget exceeded (%zu)", psmem);
     static bool pconf = false;
     if (!pconf) {
       cudaError_t e2 = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
       if (e2 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
       pconf = true;
     }
-    conv_tc_persist_kernel<<<(unsigned)sm_count(), 320, psmem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
+    const unsigned pgrid = bres ? (unsigned)(x.m_streams * n_tiles) : (unsigned)sm_count();
+    conv_tc_persist_kernel<<<pgrid, 320, psmem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
     cudaError_t e3 = cudaGetLastError();
     if (e3 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist_kernel: %s", cudaGetErrorString(e3));
     return LT_OK;
@@ -669,6 +720,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
   const int taps = d->KD * d->KH * d->KW;
 
   TcParams p;
+  p.bres = 0;
   p.OW = d->OW; p.OH = d->OH; p.OD = d->OD; p.N = d->N;
   int box[4];
   pick_box(d->OW, d->OH, d->OD, d->N, box);
@@ -697,20 +749,30 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     int rc = make_map(&tmA, in, 5, dims, str, bx, es, 1);
     if (rc) return rc;
   }
-  {
-    // weights: [tap][cb][n tile][hi|lo][Nt rows][32 channels] fp16, 64-byte rows, 64B swizzle
-    const uint64_t dims[2] = {32, (uint64_t)taps * CB * 2 * CoutP};
-    const uint64_t str[1] = {64};
-    const uint32_t bx[2] = {32, (uint32_t)(2 * Nt)};
-    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 2);
-    if (rc) return rc;
-  }
   CUtensorMap tmOut = tmA, tmRes = tmA;
   static const int direct_epi = getenv("LT_TC_EPILOGUE") && !strcmp(getenv("LT_TC_EPILOGUE"), "direct");
   // float32 outputs may be narrower than the (single) padded N tile: the tensor map then has FC channels and the TMA
   // store clips the box at the tensor bound (80-byte voxel rows for the 17-joint logits instead of 128)
   const bool clipped_f32 = d->out_format == LT_FMT_F32 && d->residual == LT_RES_NONE && CoutP == Nt && d->FC % 4 == 0 && d->FC < CoutP;
   p.tma_epi = (!direct_epi && Nt % 32 == 0 && ((d->FC % 32 == 0 && CoutP <= d->FC) || clipped_f32)) ? 1 : 0;
+  // B-resident persistent variant: 1x1-like layers (<= 8 K chunks) with more than one 128-wide N tile and enough M tiles
+  static const int bres_mode = getenv("LT_TC_BRES") ? atoi(getenv("LT_TC_BRES")) : 1;
+  const long m_tiles_all = (long)p.tw * p.th * p.td * p.tn;
+  int n_tiles = CoutP / Nt;
+  if (bres_mode && terms != 0 && p.tma_epi && taps * CB <= 8 && Nt == 128 && CoutP >= 256 && CoutP / 64 <= sm_count() / 2 &&
+      m_tiles_all >= 2L * (sm_count() / (CoutP / 64))) {
+    p.bres = 1;
+    p.Nt = 64;
+    n_tiles = CoutP / 64;
+  }
+  {
+    // weights: [tap][cb][n tile][hi|lo][Nt rows][32 channels] fp16, 64-byte rows, 64B swizzle
+    const uint64_t dims[2] = {32, (uint64_t)taps * CB * 2 * CoutP};
+    const uint64_t str[1] = {64};
+    const uint32_t bx[2] = {32, (uint32_t)(p.bres ? 64 : 2 * Nt)};
+    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 2);
+    if (rc) return rc;
+  }
   if (p.tma_epi) {
     int rc = make_out_map(&tmOut, out, d, p);
     if (rc) return rc;
@@ -719,7 +781,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
       if (rc) return rc;
     }
   }
-  return launch_tc(tmA, tmB, tmOut, tmRes, p, CoutP / Nt, (cudaStream_t)stream, d->workspace, d->workspace_bytes);
+  return launch_tc(tmA, tmB, tmOut, tmRes, p, n_tiles, (cudaStream_t)stream, d->workspace, d->workspace_bytes);
 }
 
 int conv_tc_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
@@ -793,7 +855,7 @@ extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M
   p.bw = 128; p.bh = 1; p.bd = 1; p.bn = 1;
   p.tw = ceil_div(M, 128); p.th = 1; p.td = 1; p.tn = 1;
   p.KW = p.KH = p.KD = 1; p.pw = p.ph = p.pd = 0; p.sw = p.sh = p.sd = 1;
-  p.CB = K / 64; p.b_step0 = 64; p.b_step1 = 0; p.b_nmul = 1; p.Nt = Nt; p.terms = 0;
+  p.CB = K / 64; p.b_step0 = 64; p.b_step1 = 0; p.b_nmul = 1; p.Nt = Nt; p.terms = 0; p.bres = 0;
   p.FC = N; p.FD = 1; p.FH = 1; p.FW = M; p.osd = p.osh = p.osw = 1; p.ood = p.ooh = p.oow = 0;
   p.relu = 0; p.residual = LT_RES_NONE; p.out_format = LT_FMT_F32;
   p.scale = ones; p.shift = zeros; p.res = nullptr; p.out = d;

@@ -45,6 +45,7 @@ struct FoldParams {
   int off_b, off_a, off_out, off_res, off_bar;
   unsigned long long* prof;   // optional [16] cycle counters (LT_FOLD_PROF=1): time spent waiting per role / barrier
   int dbg;               // bring-up knobs (LT_FOLD_DBG): 1 = hi*hi MMAs only, 2 = skip epilogue math/stores, 3 = load slabs once
+  int fast_issue;        // 1: single-lane MMA issue loop with the kh taps unrolled (fold_issue_loop), 0: generic loop
 };
 
 __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
@@ -56,6 +57,73 @@ __device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, u
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// MMA issue loop with K compile-time: the whole (converged) warp runs it so that slab / weight descriptors stay in uniform
+// registers; per kd one slab wait, then -- resident weights -- ONE election covering K x 4 tcgen05.mma whose descriptors
+// differ from the slab / weight base by compile-time constants (no per-tap address arithmetic, parameter reloads, modulo).
+// Measured on B200 (LT_FOLD_PROF): the generic loop spent ~590 cycles per (kd, kh) step issuing 4 MMAs whose execution
+// takes 288 (3^3) / 336 (7^3) cycles and never waited on TMA or the epilogue: the kernel was bound by its own issue latency.
+template <int K>
+__device__ __forceinline__ void fold_issue_loop(const FoldParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t b_base, uint64_t* a_full,
+                                                uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty, uint64_t* acc_full,
+                                                uint64_t* acc_empty) {
+  const uint32_t idesc = make_idesc_f16(p.NF), idesc2 = make_idesc_f16(2 * p.NF);
+  const uint32_t line_step = (uint32_t)(p.WX * 128) >> 4;     // descriptor address units (16 B) per slab line
+  const uint32_t b_bytes = (uint32_t)p.b_bytes, b_step = b_bytes >> 4;
+  const uint32_t slab_bytes = (uint32_t)p.slab_bytes, a_slots = (uint32_t)p.a_slots, b_slots = (uint32_t)p.b_slots;
+  const uint32_t nf = (uint32_t)p.NF;
+  const bool resident = p.b_resident != 0;
+  if (resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+  uint32_t slot = 0, a_ph = 0, bs = 0, b_ph = 0, it = 0;
+  for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    const uint32_t as = it & 1u;
+    mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+    tc_fence_after();
+    const uint32_t d1 = tmem_base + as * 2u * nf, d2 = d1 + nf;
+#pragma unroll 1
+    for (int kd = 0; kd < K; ++kd) {
+      mbar_wait(&a_full[slot], a_ph);
+      tc_fence_after();
+      const uint64_t ad0 = make_sw128_desc(a_base + slot * slab_bytes);
+      const uint32_t first = kd ? 1u : 0u;
+      if (resident) {
+        const uint64_t bd0 = make_sw64_desc(b_base + (uint32_t)(kd * K) * b_bytes);   // weights of (kd, kh = 0)
+        if (elect_one()) {
+#pragma unroll
+          for (int kh = 0; kh < K; ++kh) {
+            const uint64_t ad = ad0 + (uint64_t)((uint32_t)kh * line_step), bd = bd0 + (uint64_t)((uint32_t)kh * b_step);
+            umma_f16(d1, ad, bd, idesc2, kh == 0 ? first : 1u);   // A_hi(s0) x [B_hi;B_lo](s0) -> [D1|D2]
+            umma_f16(d2, ad + 4, bd, idesc, 1);                    // A_lo(s0) x B_hi(s0)        -> D2
+            umma_f16(d1, ad + 2, bd + 2, idesc2, 1);               // slice 1
+            umma_f16(d2, ad + 6, bd + 2, idesc, 1);
+          }
+          umma_commit(&a_empty[slot]);
+          if (kd == K - 1) umma_commit(&acc_full[as]);
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+          mbar_wait(&b_full[bs], b_ph);
+          tc_fence_after();
+          const uint64_t ad = ad0 + (uint64_t)((uint32_t)kh * line_step), bd = make_sw64_desc(b_base + bs * b_bytes);
+          if (elect_one()) {
+            umma_f16(d1, ad, bd, idesc2, kh == 0 ? first : 1u);
+            umma_f16(d2, ad + 4, bd, idesc, 1);
+            umma_f16(d1, ad + 2, bd + 2, idesc2, 1);
+            umma_f16(d2, ad + 6, bd + 2, idesc, 1);
+            umma_commit(&b_empty[bs]);
+            if (kh == K - 1) umma_commit(&a_empty[slot]);
+            if (kh == K - 1 && kd == K - 1) umma_commit(&acc_full[as]);
+          }
+          __syncwarp();
+          if (++bs == b_slots) { bs = 0; b_ph ^= 1u; }
+        }
+      }
+      if (++slot == a_slots) { slot = 0; a_ph ^= 1u; }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -105,6 +173,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       __syncwarp();
     }
     uint32_t pa = 0, pb = 0;
+    uint32_t slot = 0, a_ph = 0, bsl = 0, b_ph = 0;     // ring slots / phases advanced incrementally (no modulo per step)
     const bool prof = p.prof != nullptr;
     unsigned long long w_ae = 0, w_be = 0;
     const long long tstart = clock64();
@@ -115,8 +184,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       const int z = (int)(t % p.D);
       const int n = (int)(t / p.D);
       for (int kd = 0; kd < p.K; ++kd) {
-        const uint32_t slot = pa % p.a_slots;
-        mbar_wait_prof(&a_empty[slot], ((pa / p.a_slots) & 1u) ^ 1u, w_ae, prof);
+        mbar_wait_prof(&a_empty[slot], a_ph ^ 1u, w_ae, prof);
         if (elect_one()) {
           if (p.dbg == 3 && pa >= (uint32_t)p.a_slots) {
             mbar_arrive(&a_full[slot]);          // debug: reuse stale slab contents, no TMA traffic
@@ -128,21 +196,27 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
         }
         __syncwarp();
         ++pa;
+        if (++slot == (uint32_t)p.a_slots) { slot = 0; a_ph ^= 1u; }
         if (!p.b_resident) {
           for (int kh = 0; kh < p.K; ++kh) {
-            const uint32_t bs = pb % p.b_slots;
-            mbar_wait_prof(&b_empty[bs], ((pb / p.b_slots) & 1u) ^ 1u, w_be, prof);
+            const uint32_t bs = bsl;
+            mbar_wait_prof(&b_empty[bs], b_ph ^ 1u, w_be, prof);
             if (elect_one()) {
               mbar_expect_tx(&b_full[bs], (uint32_t)p.b_bytes);
               tma_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, &b_full[bs], 0, (kd * p.K + kh) * 2 * p.NF);
             }
             __syncwarp();
             ++pb;
+            if (++bsl == (uint32_t)p.b_slots) { bsl = 0; b_ph ^= 1u; }
           }
         }
       }
     }
     if (prof && lane == 0) { atomicAdd(&p.prof[0], w_ae); atomicAdd(&p.prof[1], w_be); atomicAdd(&p.prof[2], (unsigned long long)(clock64() - tstart)); }
+  } else if (warp == 1 && p.fast_issue) {
+    // ================= MMA issuer, fast path: converged warp, kh taps unrolled, one election per slab =================
+    if (p.K == 3) fold_issue_loop<3>(p, tmem_base, smem_u32(a_smem), smem_u32(b_smem), a_full, a_empty, b_full, b_empty, acc_full, acc_empty);
+    else fold_issue_loop<7>(p, tmem_base, smem_u32(a_smem), smem_u32(b_smem), a_full, a_empty, b_full, b_empty, acc_full, acc_empty);
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp runs the loops; one elected lane issues) =================
     const uint32_t idesc = make_idesc_f16(p.NF), idesc2 = make_idesc_f16(2 * p.NF);
@@ -336,6 +410,8 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   static const bool want_prof = getenv("LT_FOLD_PROF") != nullptr;
   if (want_prof && !prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long));
   p.prof = want_prof ? prof_buf : nullptr;
+  static const int fast_issue = getenv("LT_FOLD_FAST_ISSUE") ? atoi(getenv("LT_FOLD_FAST_ISSUE")) : 1;
+  p.fast_issue = (fast_issue && p.dbg == 0 && p.prof == nullptr) ? 1 : 0;
   if (want_prof) cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
   const int b_region = p.b_resident ? p.K * p.K * p.b_bytes : p.b_slots * p.b_bytes;
   p.off_b = 0;

@@ -108,6 +108,32 @@ def test_conv_tc_splitk_matches_single_pass(case, res_mode):
     assert err < TOL["tc"] and diff < 5e-6
 
 
+@pytest.mark.parametrize("case", [(64, 256, 1, (48, 48), 8), (128, 512, 1, (24, 24), 20), (256, 1024, 1, (24, 24), 9),
+                                  (256, 512, 2, (48, 48), 6), (192, 384, 1, (40, 24), 5)])
+@pytest.mark.parametrize("res_mode", ["none", "before"])
+def test_conv_tc_b_resident_vs_torch(case, res_mode):
+    """1x1 layers with <= 8 K chunks and >= 256 outputs take the B-resident persistent variant (weights of the CTA's 64-wide
+    N sub-tile stay in shared memory; CTA = (N tile, M stream)): uneven tile counts per stream, residual prefetch, stride 2."""
+    cin, cout, stride, spatial, N = case
+    torch.manual_seed(cin + cout + N)
+    conv = torch.nn.Conv2d(cin, cout, 1, stride, 0, bias=False).eval()
+    bn = _bn_for(conv, 5)
+    x = torch.randn(N, cin, *spatial)
+    with torch.no_grad():
+        y0 = bn(conv(x))
+        res = torch.randn_like(y0)
+        want = F.relu(y0 + res) if res_mode == "before" else F.relu(y0)
+    e = _engine("tc")
+    pk = e._pack_conv(conv.to(DEV), bn.to(DEV))
+    ra = act_from_nchw(res, capi.FMT_S32) if res_mode == "before" else None
+    ya = e._conv(act_from_nchw(x, capi.FMT_S32), pk, relu=True, residual=ra,
+                 res_mode=capi.RES_BEFORE_RELU if res_mode == "before" else capi.RES_NONE)
+    torch.cuda.synchronize()
+    err = rel_err(act_to_nchw(ya, cout).squeeze(2).cpu().numpy(), want.numpy())
+    print("conv_tc b-resident %s %s rel err %.2e" % (case, res_mode, err))
+    assert err < TOL["tc"]
+
+
 @pytest.mark.parametrize("case", [(64, 64, 3, 2, 1, (12, 12), 2), (64, 128, 1, 2, 0, (12, 12), 2), (128, 128, 3, 2, 1, (48, 48), 4),
                                   (256, 512, 1, 2, 0, (48, 48), 4)])
 def test_conv_tc_stride2_vs_torch(case):
