@@ -303,6 +303,10 @@ def main_native(args, rank, world, local_rank):
     pk = peaks()
     roof = None
     extra = {}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # DRAM bytes per launch from the committed ncu launch list
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
     tensor_kernels = [k for k in ("conv_tc", "conv_fold", "conv_ffma") if k in agg]
     conv_key = max(tensor_kernels, key=lambda k: agg[k][0]) if tensor_kernels else None
 
@@ -312,7 +316,8 @@ def main_native(args, rank, world, local_rank):
         tc = key != "conv_ffma"
         peak = pk["bf16_tflops"] if tc else 75.0
         r = {"kernel": {"conv_tc": "conv_tc_kernel", "conv_fold": "conv_fold_kernel", "conv_ffma": "conv_simt_kernel"}[key],
-             "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+             "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+             "traffic": traffic.get({"conv_tc": "conv_tc_kernel", "conv_fold": "conv_fold_kernel"}.get(key)),
              "launches": cnt, "ms_per_step": ms,
              "peak_source": pk["src"] + (" sustained dense bf16/fp16 (cuBLAS)" if tc else " nominal fp32 FFMA")}
         if tc and args.mode == "tc":
@@ -331,7 +336,7 @@ def main_native(args, rank, world, local_rank):
             ms, fl, nb, cnt = agg[key]
             ach = nb / (ms / 1e3) / 1e9
             extra["roofline_" + key] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                        "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt,
+                                        "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt, "traffic": traffic.get(key),
                                         "peak_source": pk["src"] + " copy bandwidth"}
     extra["step_breakdown_ms"] = {k: round(v[0], 3) for k, v in agg.items()}
 
