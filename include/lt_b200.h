@@ -108,6 +108,14 @@ int lt_unproject_push_fwd(const float* features, const float* proj, const float*
 int lt_unproject_reduce_finalize_fwd(const float* slots, int nslots, void* out, int out_format, int B, int C, long nvox,
                                      int agg, void* stream);
 
+/* Backward of lt_unproject_aggregate_fwd for the training loop (train.py:236 total_loss.backward(); the reference gets it
+ * from autograd through F.grid_sample and the aggregation ops of op.py:131-162).  grad_out [B][nvox][C] float32;
+ * grad_features [B][V][h][w][C] and grad_conf [B][V][C] (LT_AGG_CONF, may be NULL) are ACCUMULATED into (zero them first).
+ * Projection matrices and coordinate volumes carry no gradient (they do not in the reference either).  C % 4 == 0. */
+int lt_unproject_aggregate_bwd(const float* features, const float* proj, const float* coord, const float* conf,
+                               const float* grad_out, float* grad_features, float* grad_conf, int B, int V, int C, int h, int w,
+                               long nvox, int agg, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Volumetric soft-argmax.  Replaces op.integrate_tensor_3d_with_coordinates (op.py:84-96).
  *   logits: element (b, j, vox) at logits[b*batch_stride + vox*voxel_stride + j*chan_stride]
@@ -119,6 +127,10 @@ int lt_unproject_reduce_finalize_fwd(const float* slots, int nslots, void* out, 
  *   workspace: lt_softargmax3d_workspace_bytes(B, J, nvox) bytes
  *   softmax = 0 selects the ReLU variant (op.py:90-91).
  * ---------------------------------------------------------------------------------------- */
+/* Backward of the soft-argmax in the op-level (NCDHW) layout: probs = the forward's volumes_out [B][J][nvox],
+ * grad_keypoints [B][J][3], grad_volumes [B][J][nvox] or NULL, scratch >= B*J floats -> grad_logits [B][J][nvox]. */
+int lt_softargmax3d_bwd(const float* probs, const float* coord, const float* grad_keypoints, const float* grad_volumes,
+                        float* grad_logits, float* scratch, int B, int J, long nvox, float multiplier, int softmax, void* stream);
 size_t lt_softargmax3d_workspace_bytes(int B, int J, long nvox);
 int lt_softargmax3d_fwd(const float* logits, long batch_stride, long voxel_stride, long chan_stride,
                         const float* coord, float* volumes_out, float* keypoints_out,

@@ -47,6 +47,8 @@ SIGNATURES = {
     "lt_unproject_finalize_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
     "lt_unproject_push_fwd": (c_int, [c_void_p] * 4 + [ctypes.POINTER(c_void_p), c_int, c_int] + [c_int] * 5 + [c_long, c_int, c_void_p]),
     "lt_unproject_reduce_finalize_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
+    "lt_unproject_aggregate_bwd": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_long, c_int, c_void_p]),
+    "lt_softargmax3d_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_long, c_float, c_int, c_void_p]),
     "lt_softargmax3d_workspace_bytes": (c_size_t, [c_int, c_int, c_long]),
     "lt_softargmax3d_fwd": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                     c_int, c_int, c_long, c_float, c_int, c_void_p]),
@@ -159,6 +161,18 @@ def softargmax3d(logits, batch_stride, voxel_stride, chan_stride, coord, volumes
     _check(lib().lt_softargmax3d_fwd(_ptr(logits), batch_stride, voxel_stride, chan_stride, _ptr(coord), _ptr(volumes_out),
                                      _ptr(keypoints_out), _ptr(workspace), workspace.numel() * workspace.element_size(),
                                      B, J, nvox, float(multiplier), int(softmax), _stream()), "lt_softargmax3d_fwd")
+
+
+def unproject_aggregate_bwd(features_cl, proj, coord, conf, grad_out_cl, grad_features_cl, grad_conf, agg):
+    B, V, h, w, C = features_cl.shape
+    nvox = coord.shape[1]
+    _check(lib().lt_unproject_aggregate_bwd(_ptr(features_cl), _ptr(proj), _ptr(coord), _ptr(conf), _ptr(grad_out_cl), _ptr(grad_features_cl),
+                                            _ptr(grad_conf), B, V, C, h, w, nvox, agg, _stream()), "lt_unproject_aggregate_bwd")
+
+
+def softargmax3d_bwd(probs, coord, grad_keypoints, grad_volumes, grad_logits, scratch, B, J, nvox, multiplier, softmax):
+    _check(lib().lt_softargmax3d_bwd(_ptr(probs), _ptr(coord), _ptr(grad_keypoints), _ptr(grad_volumes), _ptr(grad_logits), _ptr(scratch),
+                                     B, J, nvox, float(multiplier), int(softmax), _stream()), "lt_softargmax3d_bwd")
 
 
 def softargmax3d_workspace_bytes(B, J, nvox):

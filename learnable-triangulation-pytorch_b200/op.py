@@ -3,14 +3,15 @@
 Same names / argument meaning / error behaviour as `/root/reference/mvn/utils/op.py`:
 `unproject_heatmaps` (:99-166) and `integrate_tensor_3d_with_coordinates` (:84-96).
 CUDA tensors without grad go to the hand-written kernels through the C ABI; anything else must
-ask for the torch formulation explicitly (backend="torch" or LT_B200_BACKEND=torch) -- there is
-no silent fallback.
+ask for another formulation explicitly -- there is no silent fallback: backend="torch" (or
+LT_B200_BACKEND=torch) is the autograd/CPU torch formulation, backend="hybrid" keeps the native
+forward kernels and adds their native backward (autograd_ops.py, csrc/backward.cu) for training.
 """
 import os
 
 import torch
 
-from . import capi, torch_ops
+from . import autograd_ops, capi, torch_ops
 
 _AGGS = ("sum", "max", "softmax", "conf", "conf_norm")
 
@@ -19,8 +20,12 @@ def _resolve_backend(backend, *tensors):
     backend = backend or os.environ.get("LT_B200_BACKEND", "native")
     if backend == "torch":
         return "torch"
-    if backend != "native":
+    if backend not in ("native", "hybrid"):
         raise ValueError("unknown backend {!r}".format(backend))
+    if backend == "hybrid":
+        if not all(t.is_cuda for t in tensors if t is not None):
+            raise RuntimeError("lt_b200 hybrid ops need CUDA tensors")
+        return "hybrid"
     if not all(t.is_cuda for t in tensors if t is not None):
         raise RuntimeError("lt_b200 native ops need CUDA tensors; pass backend='torch' (or LT_B200_BACKEND=torch) "
                            "for the autograd/CPU formulation")
@@ -33,8 +38,11 @@ def unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregati
                        backend=None):
     if not (volume_aggregation_method in _AGGS or volume_aggregation_method.startswith("conf")):
         raise ValueError("Unknown volume_aggregation_method: {}".format(volume_aggregation_method))
-    if _resolve_backend(backend, heatmaps, proj_matricies, coord_volumes, vol_confidences) == "torch":
+    which = _resolve_backend(backend, heatmaps, proj_matricies, coord_volumes, vol_confidences)
+    if which == "torch":
         return torch_ops.unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregation_method, vol_confidences)
+    if which == "hybrid":
+        return autograd_ops.unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregation_method, vol_confidences)
     B, V, C, h, w = heatmaps.shape
     vol_shape = tuple(coord_volumes.shape[1:4])
     nvox = vol_shape[0] * vol_shape[1] * vol_shape[2]
@@ -52,8 +60,11 @@ def unproject_heatmaps(heatmaps, proj_matricies, coord_volumes, volume_aggregati
 
 
 def integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax=True, backend=None):
-    if _resolve_backend(backend, volumes, coord_volumes) == "torch":
+    which = _resolve_backend(backend, volumes, coord_volumes)
+    if which == "torch":
         return torch_ops.integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax)
+    if which == "hybrid":
+        return autograd_ops.integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax)
     B, J = volumes.shape[:2]
     nvox = volumes[0, 0].numel()
     logits = volumes.float().contiguous()
@@ -67,7 +78,7 @@ def integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax=True, b
 
 def integrate_tensor_2d(heatmaps, softmax=True, backend=None):
     """Drop-in for reference op.py:11-47: (B, J, h, w) -> coordinates (B, J, 2) [x, y in pixels], normalised heatmaps."""
-    if _resolve_backend(backend, heatmaps) == "torch" or not softmax:
+    if _resolve_backend(backend, heatmaps) in ("torch", "hybrid") or not softmax:
         return torch_ops.integrate_tensor_2d(heatmaps, softmax)
     B, J, h, w = heatmaps.shape
     dev = heatmaps.device

@@ -91,7 +91,8 @@ class VolumetricTriangulationNet(nn.Module):
 
     # ---------------------------------------------------------------- forward
     def forward(self, images, proj_matricies, batch):
-        if self.backend == "torch":
+        if self.backend in ("torch", "hybrid"):
+            # "hybrid": torch/cuDNN convolutions with the native custom ops (forward + backward kernels) in the autograd graph
             return self._forward_torch(images, batch)
         if self.backend != "native":
             raise ValueError("unknown backend {!r}".format(self.backend))
@@ -145,9 +146,14 @@ class VolumetricTriangulationNet(nn.Module):
             coord = coord.permute(0, 1, 3, 2, 4).flip(2)
         features = self.process_features(features)
         features = features.view(B, V, *features.shape[1:])
-        volumes = torch_ops.unproject_heatmaps(features, proj_t, coord, self.volume_aggregation_method, vol_conf)
+        ops = torch_ops
+        if self.backend == "hybrid":
+            if not images.is_cuda:
+                raise RuntimeError("lt_b200 hybrid backend needs CUDA tensors (native custom ops); use backend='torch' on CPU")
+            from . import autograd_ops as ops
+        volumes = ops.unproject_heatmaps(features, proj_t, coord, self.volume_aggregation_method, vol_conf)
         volumes = self.volume_net(volumes)
-        kp, volumes = torch_ops.integrate_tensor_3d_with_coordinates(volumes * self.volume_multiplier, coord, self.volume_softmax)
+        kp, volumes = ops.integrate_tensor_3d_with_coordinates(volumes * self.volume_multiplier, coord, self.volume_softmax)
         return kp, features, volumes, vol_conf, cuboids, coord, cen_t
 
 
