@@ -314,6 +314,105 @@ static void run_feed(const uint8_t* buf, size_t window, int grid, unsigned long 
          bytes / best / 1e6 / grid);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mode "issue": what does it cost to ISSUE one chunk (mbarrier wait that is already satisfied + descriptor arithmetic +
+// election + four tiny MMAs + commit), for the loop shapes used by the conv kernels?  N = 16 so that the tensor pipe itself
+// is never the limit.  The kw-folded kernel was bound by exactly this.
+//   style 0: converged warp, runtime ring slot (modulo by increment), one election per iteration        (conv_tc today)
+//   style 1: one lane runs the whole loop                                                               (divergent: waterfalls)
+//   style 2: converged warp, four iterations unrolled with compile-time slot offsets, one election per four iterations
+//   style 3: as 0 with the slot computed by integer modulo of a runtime stage count                     (conv_tc before r01e)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__global__ void __launch_bounds__(128, 1) issue_kernel(int style, int stages, int stage_bytes, int iters, Result* res) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* ready = reinterpret_cast<uint64_t*>(smem + 4 * 32768);     // never armed: waiting for parity 1 returns at once
+  uint64_t* sink = ready + 1;                                          // receives the commits
+  uint64_t* done = ready + 2;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(ready + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 4 * 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(ready, 1); mbar_init(sink, (1u << 20) - 1); mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc<1>(slot, 64);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+  if (warp == 1) {
+    const uint32_t id = make_idesc(128, 16);
+    const uint32_t base = smem_u32(smem);
+    const long long t0 = clock64();
+    if (style == 1) {
+      if (lane == 0) {
+        int s = 0;
+        for (int q = 0; q < iters; ++q) {
+          mbar_wait(ready, 1);
+          const uint32_t a = base + (uint32_t)(s * stage_bytes);
+          const uint64_t ad = make_sw128_desc(a), bd = make_sw64_desc(a + 16384);
+          umma<1>(tmem, ad, bd, id, q > 0); umma<1>(tmem + 16, ad + 4, bd, id, q > 0); umma<1>(tmem, ad + 2, bd + 2, id, 1); umma<1>(tmem + 16, ad + 6, bd + 2, id, 1);
+          commit<1>(sink);
+          if (++s == stages) s = 0;
+        }
+      }
+      __syncwarp();
+    } else if (style == 2) {
+      for (int q = 0; q < iters; q += 4) {
+        mbar_wait(ready, 1);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t a = base + (uint32_t)(u * 32768);
+            const uint64_t ad = make_sw128_desc(a), bd = make_sw64_desc(a + 16384);
+            umma<1>(tmem, ad, bd, id, (q | u) ? 1u : 0u); umma<1>(tmem + 16, ad + 4, bd, id, (q | u) ? 1u : 0u); umma<1>(tmem, ad + 2, bd + 2, id, 1); umma<1>(tmem + 16, ad + 6, bd + 2, id, 1);
+            commit<1>(sink);
+          }
+        }
+        __syncwarp();
+      }
+    } else {
+      int s = 0;
+      for (int q = 0; q < iters; ++q) {
+        if (style == 3) s = q % stages;
+        mbar_wait(ready, 1);
+        const uint32_t a = base + (uint32_t)(s * stage_bytes);
+        const uint64_t ad = make_sw128_desc(a), bd = make_sw64_desc(a + 16384);
+        if (elect_one_sync()) {
+          umma<1>(tmem, ad, bd, id, q > 0); umma<1>(tmem + 16, ad + 4, bd, id, q > 0); umma<1>(tmem, ad + 2, bd + 2, id, 1); umma<1>(tmem + 16, ad + 6, bd + 2, id, 1);
+          commit<1>(sink);
+        }
+        __syncwarp();
+        if (style == 0 && ++s == stages) s = 0;
+      }
+    }
+    if (lane == 0) { commit<1>(done); }
+    __syncwarp();
+    mbar_wait(done, 0);
+    if (lane == 0 && blockIdx.x == 0) { res->cycles = clock64() - t0; res->n_instr = iters; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem, 64);
+}
+
+static void run_issue(int style, Result* dres) {
+  CK(cudaMemset(dres, 0, sizeof(Result)));
+  const size_t smem = 4 * 32768 + 256 + 1024;
+  CK(cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = 0; rep < 2; ++rep) {
+    issue_kernel<<<1, 128, smem>>>(style, 4, 32768, 1024, dres);
+    CK(cudaDeviceSynchronize());
+  }
+  Result r;
+  CK(cudaMemcpy(&r, dres, sizeof(r), cudaMemcpyDeviceToHost));
+  printf("issue style=%d: %.1f cycles per chunk (4 MMAs N=16 + commit; math ~32)\n", style, (double)r.cycles / r.n_instr);
+}
+
 int main() {
   Result* dres;
   CK(cudaMalloc(&dres, sizeof(Result)));
@@ -352,6 +451,7 @@ int main() {
     run_feed<8>(buf, (size_t)16 << 20, sms, dcyc);
     run_feed<12>(buf, (size_t)16 << 20, sms, dcyc);
   }
+  for (int st = 0; st < 4; ++st) run_issue(st, dres);
   printf("done\n");
   return 0;
 }

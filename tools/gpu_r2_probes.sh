@@ -3,8 +3,8 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 O=gpurun_out
-for p in tma_probe pair_probe; do
+for p in cta2_probe tma_probe pair_probe; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/$p tools/$p.cu -lcuda > $O/${p}_build.log 2>&1 \
     && timeout 120 /tmp/$p > $O/$p.log 2>&1
-  echo "$p exit $?"; cat $O/$p.log | head -40
+  echo "$p exit $?"; grep -E "issue|ring|feed|b64|b128|a5d|cta_group|TIMEOUT|error" $O/$p.log | tail -40
 done
