@@ -8,3 +8,5 @@ for p in cta2_probe tma_probe pair_probe; do
     && timeout 120 /tmp/$p > $O/$p.log 2>&1
   echo "$p exit $?"; grep -E "issue|ring|feed|b64|b128|a5d|cta_group|TIMEOUT|error" $O/$p.log | tail -40
 done
+echo "== hybrid (native backward kernels) gradient parity"
+LT_TEST_HYBRID=1 timeout 600 python -m pytest tests/test_gpu_hybrid.py -q -m gpu -p no:cacheprovider --tb=short > $O/r2_hybrid.log 2>&1; tail -5 $O/r2_hybrid.log
