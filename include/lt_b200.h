@@ -228,6 +228,17 @@ int lt_cl_to_cf_f32(const float* in, float* out, int N, long P, int Cs, int C, v
 int lt_tc_gemm_selftest(const void* a_fp16, const void* b_fp16, float* d, int M, int N, int K,
                         int variant, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Test hooks (NOT part of the product path): the per-item code of the two backward kernels executed on the CPU with HOST
+ * pointers, so that the `-m "not gpu"` suite can check the gradient arithmetic against torch autograd without a B200.
+ * Same arguments as the device entry points minus scratch / stream.
+ * ---------------------------------------------------------------------------------------- */
+int lt_test_unproject_aggregate_bwd_host(const float* features, const float* proj, const float* coord, const float* conf,
+                                         const float* grad_out, float* grad_features, float* grad_conf, int B, int V, int C, int h, int w,
+                                         long nvox, int agg);
+int lt_test_softargmax3d_bwd_host(const float* probs, const float* coord, const float* grad_keypoints, const float* grad_volumes,
+                                  float* grad_logits, int B, int J, long nvox, float multiplier, int softmax);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,8 @@ SIGNATURES = {
     "lt_unproject_reduce_finalize_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
     "lt_unproject_aggregate_bwd": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_long, c_int, c_void_p]),
     "lt_softargmax3d_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_long, c_float, c_int, c_void_p]),
+    "lt_test_unproject_aggregate_bwd_host": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_long, c_int]),
+    "lt_test_softargmax3d_bwd_host": (c_int, [c_void_p] * 5 + [c_int, c_int, c_long, c_float, c_int]),
     "lt_softargmax3d_workspace_bytes": (c_size_t, [c_int, c_int, c_long]),
     "lt_softargmax3d_fwd": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                     c_int, c_int, c_long, c_float, c_int, c_void_p]),

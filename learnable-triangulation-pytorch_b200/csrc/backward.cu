@@ -13,6 +13,16 @@
 // Soft-argmax backward (HBM bound, NCDHW like the op-level API): with t_i = g_vol_i + <g_kp, x_i>,
 //     softmax: d logit_i = mult * p_i * (t_i - sum_k p_k t_k)      ReLU: d logit_i = mult * [mult * logit_i > 0] * t_i
 #include "common.cuh"
+#include <math.h>
+
+// The per-item bodies are __host__ __device__: the kernels run them on the GPU, and lt_test_*_bwd_host (bottom of the file)
+// runs the SAME code on the CPU so that `-m "not gpu"` tests can check the gradient arithmetic against torch autograd
+// without a B200 (test hook only: nothing on the product path calls it).
+#ifdef __CUDA_ARCH__
+#define LT_LD(p) __ldg(p)
+#else
+#define LT_LD(p) (*(p))
+#endif
 
 namespace lt {
 
@@ -22,7 +32,7 @@ struct BwdTaps {
 };
 
 // identical arithmetic to make_taps() in unproject.cu (op.py:116-135, multiview.py:89-110)
-__device__ __forceinline__ BwdTaps bwd_taps(const float* __restrict__ P, float X, float Y, float Z, int h, int w) {
+__host__ __device__ __forceinline__ BwdTaps bwd_taps(const float* __restrict__ P, float X, float Y, float Z, int h, int w) {
   BwdTaps t;
   float px = fmaf(Z, P[2], fmaf(Y, P[1], X * P[0])) + P[3];
   float py = fmaf(Z, P[6], fmaf(Y, P[5], X * P[4])) + P[7];
@@ -40,8 +50,8 @@ __device__ __forceinline__ BwdTaps bwd_taps(const float* __restrict__ P, float X
   const bool vx0 = (x0 >= 0.0f) && (x0 <= wm), vx1 = (x1 >= 0.0f) && (x1 <= wm);
   const bool vy0 = (y0 >= 0.0f) && (y0 <= hm), vy1 = (y1 >= 0.0f) && (y1 <= hm);
   const int xi = (int)fminf(fmaxf(x0, -2.0f), wm + 1.0f), yi = (int)fminf(fmaxf(y0, -2.0f), hm + 1.0f);
-  const int xa = min(max(xi, 0), w - 1), xb = min(max(xi + 1, 0), w - 1);
-  const int ya = min(max(yi, 0), h - 1), yb = min(max(yi + 1, 0), h - 1);
+  const int xa = xi < 0 ? 0 : (xi > w - 1 ? w - 1 : xi), xb = xi + 1 < 0 ? 0 : (xi + 1 > w - 1 ? w - 1 : xi + 1);
+  const int ya = yi < 0 ? 0 : (yi > h - 1 ? h - 1 : yi), yb = yi + 1 < 0 ? 0 : (yi + 1 > h - 1 ? h - 1 : yi + 1);
   t.o[0] = ya * w + xa; t.o[1] = ya * w + xb; t.o[2] = yb * w + xa; t.o[3] = yb * w + xb;
   t.w[0] = (depth_ok && vx0 && vy0) ? (x1 - ix) * (y1 - iy) : 0.0f;
   t.w[1] = (depth_ok && vx1 && vy0) ? (ix - x0) * (y1 - iy) : 0.0f;
@@ -50,22 +60,33 @@ __device__ __forceinline__ BwdTaps bwd_taps(const float* __restrict__ P, float X
   return t;
 }
 
-__device__ __forceinline__ float4 sample4(const float* __restrict__ fmap, int C, int c0, const BwdTaps& t) {
+__host__ __device__ __forceinline__ float4 sample4(const float* __restrict__ fmap, int C, int c0, const BwdTaps& t) {
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (t.w[k] != 0.0f) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(fmap + (long)t.o[k] * C + c0));
+      const float4 q = LT_LD(reinterpret_cast<const float4*>(fmap + (long)t.o[k] * C + c0));
       s.x = fmaf(q.x, t.w[k], s.x); s.y = fmaf(q.y, t.w[k], s.y); s.z = fmaf(q.z, t.w[k], s.z); s.w = fmaf(q.w, t.w[k], s.w);
     }
   return s;
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+__host__ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+#ifdef __CUDA_ARCH__
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  addr[0] += v.x; addr[1] += v.y; addr[2] += v.z; addr[3] += v.w;
+#endif
+}
+__host__ __device__ __forceinline__ void acc_add(float* addr, float v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(addr, v);
+#else
+  *addr += v;
+#endif
 }
 
-__device__ __forceinline__ void scatter4(float* __restrict__ gmap, int C, int c0, const BwdTaps& t, float4 gs) {
+__host__ __device__ __forceinline__ void scatter4(float* __restrict__ gmap, int C, int c0, const BwdTaps& t, float4 gs) {
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (t.w[k] != 0.0f)
@@ -86,38 +107,32 @@ struct UnprojBwdParams {
 
 constexpr int kBwdSmemViews = 64;
 
-__global__ void __launch_bounds__(256) unproject_bwd_kernel(const UnprojBwdParams p) {
-  __shared__ float sP[kBwdSmemViews * 12];
-  extern __shared__ float sConf[];          // [V][C] block-level accumulator of d conf (only with grad_conf)
-  const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < min(p.V, kBwdSmemViews) * 12; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
-  const bool want_gconf = p.grad_conf != nullptr && p.agg == LT_AGG_CONF;
-  if (want_gconf)
-    for (int i = threadIdx.x; i < p.V * p.C; i += blockDim.x) sConf[i] = 0.0f;
-  __syncthreads();
+// one (voxel, 4-channel quad) of sample b.  projs: the sample's first kBwdSmemViews projection matrices (shared memory on
+// the GPU) or null; gconf_acc: [V][C] accumulator of d conf (shared memory on the GPU, the output itself on the host) or null
+__host__ __device__ __forceinline__ void unproject_bwd_item(const UnprojBwdParams& p, int b, long it, const float* projs, float* gconf_acc) {
   const int quads = p.C >> 2;
-  const long items = p.nvox * quads;
   const long map_elems = (long)p.h * p.w * p.C;
-  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
+  const bool want_gconf = gconf_acc != nullptr && p.agg == LT_AGG_CONF;
+  {
     const long vox = it / quads;
     const int c0 = (int)(it % quads) * 4;
     const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
-    const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(p.grad_out + ((long)b * p.nvox + vox) * p.C + c0));
+    const float X = LT_LD(cp), Y = LT_LD(cp + 1), Z = LT_LD(cp + 2);
+    const float4 g = LT_LD(reinterpret_cast<const float4*>(p.grad_out + ((long)b * p.nvox + vox) * p.C + c0));
     const float* fb = p.features + (long)b * p.V * map_elems;
     float* gb = p.grad_features + (long)b * p.V * map_elems;
-    auto view_proj = [&](int v) { return v < kBwdSmemViews ? sP + v * 12 : p.proj + ((long)b * p.V + v) * 12; };
+    auto view_proj = [&](int v) { return (projs != nullptr && v < kBwdSmemViews) ? projs + v * 12 : p.proj + ((long)b * p.V + v) * 12; };
 
     if (p.agg == LT_AGG_SUM || p.agg == LT_AGG_CONF) {
       for (int v = 0; v < p.V; ++v) {
         const BwdTaps t = bwd_taps(view_proj(v), X, Y, Z, p.h, p.w);
         float4 gs = g;
         if (p.agg == LT_AGG_CONF) {
-          const float4 cf = __ldg(reinterpret_cast<const float4*>(p.conf + ((long)b * p.V + v) * p.C + c0));
+          const float4 cf = LT_LD(reinterpret_cast<const float4*>(p.conf + ((long)b * p.V + v) * p.C + c0));
           if (want_gconf) {
             const float4 s = sample4(fb + v * map_elems, p.C, c0, t);
-            float* a = sConf + v * p.C + c0;
-            atomicAdd(a, g.x * s.x); atomicAdd(a + 1, g.y * s.y); atomicAdd(a + 2, g.z * s.z); atomicAdd(a + 3, g.w * s.w);
+            float* a = gconf_acc + v * p.C + c0;
+            acc_add(a, g.x * s.x); acc_add(a + 1, g.y * s.y); acc_add(a + 2, g.z * s.z); acc_add(a + 3, g.w * s.w);
           }
           gs = make_float4(g.x * cf.x, g.y * cf.y, g.z * cf.z, g.w * cf.w);
         }
@@ -164,6 +179,20 @@ __global__ void __launch_bounds__(256) unproject_bwd_kernel(const UnprojBwdParam
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) unproject_bwd_kernel(const UnprojBwdParams p) {
+  __shared__ float sP[kBwdSmemViews * 12];
+  extern __shared__ float sConf[];          // [V][C] block-level accumulator of d conf (only with grad_conf)
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < min(p.V, kBwdSmemViews) * 12; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
+  const bool want_gconf = p.grad_conf != nullptr && p.agg == LT_AGG_CONF;
+  if (want_gconf)
+    for (int i = threadIdx.x; i < p.V * p.C; i += blockDim.x) sConf[i] = 0.0f;
+  __syncthreads();
+  const long items = p.nvox * (p.C >> 2);
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x)
+    unproject_bwd_item(p, b, it, sP, want_gconf ? sConf : nullptr);
   if (want_gconf) {
     __syncthreads();
     for (int i = threadIdx.x; i < p.V * p.C; i += blockDim.x) atomicAdd(p.grad_conf + (long)b * p.V * p.C + i, sConf[i]);
@@ -183,11 +212,15 @@ struct SoftBwdParams {
   float mult;
 };
 
-__device__ __forceinline__ float soft_t(const SoftBwdParams& p, int b, int j, long i, float gx, float gy, float gz) {
+__host__ __device__ __forceinline__ float soft_t(const SoftBwdParams& p, int b, int j, long i, float gx, float gy, float gz) {
   const float* c = p.coord + ((long)b * p.nvox + i) * 3;
-  float t = fmaf(gx, __ldg(c), fmaf(gy, __ldg(c + 1), gz * __ldg(c + 2)));
-  if (p.g_vol) t += __ldg(p.g_vol + ((long)b * p.J + j) * p.nvox + i);
+  float t = fmaf(gx, LT_LD(c), fmaf(gy, LT_LD(c + 1), gz * LT_LD(c + 2)));
+  if (p.g_vol) t += LT_LD(p.g_vol + ((long)b * p.J + j) * p.nvox + i);
   return t;
+}
+__host__ __device__ __forceinline__ float soft_grad(const SoftBwdParams& p, float pi, float t, float S) {
+  // ReLU: probs = relu(mult * logit) > 0 exactly where the gradient passes
+  return p.softmax ? p.mult * pi * (t - S) : (pi > 0.0f ? p.mult * t : 0.0f);
 }
 
 // one CTA per (b, j): S = sum_i p_i t_i
@@ -215,9 +248,7 @@ __global__ void __launch_bounds__(256) softargmax_bwd_apply_kernel(const SoftBwd
   const float* pr = p.probs + (long)bj * p.nvox;
   float* out = p.grad_logits + (long)bj * p.nvox;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.nvox; i += (long)gridDim.x * blockDim.x) {
-    const float pi = __ldg(pr + i), t = soft_t(p, b, j, i, gx, gy, gz);
-    // ReLU: probs = relu(mult * logit) > 0 exactly where the gradient passes
-    out[i] = p.softmax ? p.mult * pi * (t - S) : (pi > 0.0f ? p.mult * t : 0.0f);
+    out[i] = soft_grad(p, __ldg(pr + i), soft_t(p, b, j, i, gx, gy, gz), S);
   }
 }
 
@@ -260,5 +291,35 @@ extern "C" int lt_softargmax3d_bwd(const float* probs, const float* coord, const
   if (bx > 64) bx = 64;
   softargmax_bwd_apply_kernel<<<dim3((unsigned)bx, (unsigned)(B * J)), 256, 0, st>>>(p);
   LT_CHECK_LAUNCH("softargmax_bwd_apply_kernel");
+  return LT_OK;
+}
+
+// ---- test hooks: the same per-item code on the CPU (host pointers), for the `-m "not gpu"` gradient tests -------------
+extern "C" int lt_test_unproject_aggregate_bwd_host(const float* features, const float* proj, const float* coord, const float* conf,
+                                                    const float* grad_out, float* grad_features, float* grad_conf, int B, int V, int C, int h,
+                                                    int w, long nvox, int agg) {
+  LT_REQUIRE(features && proj && coord && grad_out && grad_features && C % 4 == 0, "test_unproject_bwd_host: bad arguments");
+  LT_REQUIRE(agg >= LT_AGG_SUM && agg <= LT_AGG_CONF && (agg != LT_AGG_CONF || conf), "test_unproject_bwd_host: bad aggregation");
+  UnprojBwdParams p{features, proj, coord, conf, grad_out, grad_features, grad_conf, B, V, C, h, w, agg, nvox};
+  const long items = nvox * (C / 4);
+  for (int b = 0; b < B; ++b)
+    for (long it = 0; it < items; ++it)
+      unproject_bwd_item(p, b, it, nullptr, (grad_conf && agg == LT_AGG_CONF) ? grad_conf + (long)b * V * C : nullptr);
+  return LT_OK;
+}
+
+extern "C" int lt_test_softargmax3d_bwd_host(const float* probs, const float* coord, const float* grad_keypoints, const float* grad_volumes,
+                                             float* grad_logits, int B, int J, long nvox, float multiplier, int softmax) {
+  LT_REQUIRE(probs && coord && grad_keypoints && grad_logits, "test_softargmax3d_bwd_host: null pointer");
+  SoftBwdParams p{probs, coord, grad_keypoints, grad_volumes, nullptr, grad_logits, B, J, softmax, nvox, multiplier};
+  for (int bj = 0; bj < B * J; ++bj) {
+    const int b = bj / J, j = bj % J;
+    const float gx = grad_keypoints[bj * 3], gy = grad_keypoints[bj * 3 + 1], gz = grad_keypoints[bj * 3 + 2];
+    const float* pr = probs + (long)bj * nvox;
+    double S = 0.0;
+    if (softmax)
+      for (long i = 0; i < nvox; ++i) S += (double)pr[i] * soft_t(p, b, j, i, gx, gy, gz);
+    for (long i = 0; i < nvox; ++i) grad_logits[(long)bj * nvox + i] = soft_grad(p, pr[i], soft_t(p, b, j, i, gx, gy, gz), (float)S);
+  }
   return LT_OK;
 }
