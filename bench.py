@@ -39,7 +39,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch_gpu"],
+                    help="native: this repo's kernels; reference: the CPU oracle port of the reference path (contract arm); torch_gpu: the "
+                         "same torch formulation as the reference on cuda:0 through ATen/cuDNN (secondary bar of SURVEY 8d, not a contract arm)")
+    ap.add_argument("--tf32", action="store_true", help="torch_gpu only: allow TF32 in cuDNN / matmul (default: true fp32)")
     ap.add_argument("--mode", default=os.environ.get("LT_B200_CONV", "tc"), choices=["tc", "tc1", "simt"])
     ap.add_argument("--batch", type=int, default=8, help="samples per GPU per step")
     ap.add_argument("--views", type=int, default=4)
@@ -134,6 +137,43 @@ def main_reference(args, rank):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def main_torch_gpu(args, rank):
+    """Secondary bar: the reference's own formulation -- torch ops through ATen/cuDNN -- on one B200, eval mode."""
+    if rank != 0:
+        return
+    import lt_b200
+    from lt_b200 import testing
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    torch.backends.cudnn.benchmark = True
+    B, V, S, n = args.batch, args.views, args.image, args.volume
+    cfg = testing.make_config(num_layers=args.layers, volume_size=n)
+    torch.manual_seed(0)
+    model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="torch")
+    if not args.no_calibrate:
+        testing.randomize_weights(model, seed=0, calib_size=S, calib_views=1)
+    model = model.to(dev).eval()
+    images, batch = testing.make_batch(B, V, image_size=S, seed=0)
+    images_dev = images.to(dev)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            model(images_dev, None, batch)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            model(images_dev, None, batch)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"impl": "torch_gpu", "metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "dtype": "tf32" if args.tf32 else "f32", "data": "synthetic",
+                      "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch %d, torch ops (ATen/cuDNN) on cuda:0"
+                                 % (args.layers, V, S, S, n, B)}}), flush=True)
 
 
 def main_native(args, rank, world, local_rank):
@@ -381,6 +421,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         main_reference(args, rank)
+    elif args.impl == "torch_gpu":
+        main_torch_gpu(args, rank)
     else:
         main_native(args, rank, world, local_rank)
 

@@ -10,3 +10,6 @@ for p in cta2_probe tma_probe pair_probe; do
 done
 echo "== hybrid (native backward kernels) gradient parity"
 LT_TEST_HYBRID=1 timeout 600 python -m pytest tests/test_gpu_hybrid.py -q -m gpu -p no:cacheprovider --tb=short > $O/r2_hybrid.log 2>&1; tail -5 $O/r2_hybrid.log
+echo "== secondary bar: the torch formulation through ATen/cuDNN on the same B200 (fp32, then TF32)"
+timeout 600 python bench.py --impl torch_gpu --steps 5 --warmup 3 2>&1 | tail -1 | tee $O/r2_bench_torch_gpu_fp32.json | cut -c1-200
+timeout 600 python bench.py --impl torch_gpu --tf32 --steps 5 --warmup 3 2>&1 | tail -1 | tee $O/r2_bench_torch_gpu_tf32.json | cut -c1-200
