@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--collective", default="features", choices=["all_reduce", "reduce_scatter", "p2p", "features"],
                     help="view-group exchange: one NCCL all-reduce (contract), reduce-scatter, or the fused P2P-store kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the ATen/cuDNN secondary bars (fp32 and TF32) of the native arm")
     ap.add_argument("--no-calibrate", action="store_true", help="keep PyTorch default init (faster start, degenerate signal)")
     return ap.parse_args()
 
@@ -96,47 +97,87 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(args, steps, warmup):
-    """samples/sec of the CPU oracle port of the reference path on this box's host cores (bounded sample: B=1)."""
-    from oracle import vol_oracle as O
+def cpu_oracle_rate(args, steps, sd=None, images=None, batch=None):
+    """samples/sec of the CPU oracle port of the reference path on this box's host cores.
+
+    Bounded sample of the SAME workload: one untimed warm-up forward of one sample, then `steps` timed forwards of a
+    whole batch (args.batch samples, ~20 s each for config #2 on 32 threads).  With `sd/images/batch` given (the
+    native arm's own weights and inputs) the last forward's outputs are returned as well, for the parity object.
+    """
+    from oracle import parity
     import lt_b200
     from lt_b200 import testing
     # all host threads the reference can use productively: intra-op scaling of fp32 convs flattens (and on shared,
     # oversubscribed hosts reverses) beyond ~32 threads; LT_BENCH_CPU_THREADS overrides
     torch.set_num_threads(int(os.environ.get("LT_BENCH_CPU_THREADS", min(os.cpu_count(), 32))))
-    cfg = testing.make_config(num_layers=args.layers, volume_size=args.volume)
-    model = lt_b200.VolumetricTriangulationNet(cfg, device="cpu", backend="torch")   # parameter holder only
-    sd = model.state_dict()
-    images, batch = testing.make_batch(1, args.views, image_size=args.image, seed=0)
-    base = np.stack([k[6, :3] for k in batch["keypoints_3d"]])
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.volumetric_forward(sd, images, batch["cameras"], base, volume_size=args.volume)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
-    return 1.0 / dt, dt, torch.get_num_threads()
+    if sd is None:
+        cfg = testing.make_config(num_layers=args.layers, volume_size=args.volume)
+        sd = lt_b200.VolumetricTriangulationNet(cfg, device="cpu", backend="torch").state_dict()   # parameter holder only
+    if images is None:
+        images, batch = testing.make_batch(args.batch, args.views, image_size=args.image, seed=0)
+    B = images.shape[0]
+    one = {k: ([c[:1] for c in v] if k == "cameras" else v[:1]) for k, v in batch.items()}
+    parity.oracle_forward(sd, images[:1], one, args.volume)       # warm-up (thread pool, allocator)
+    total, out = 0.0, None
+    for _ in range(steps):
+        out, secs = parity.oracle_forward(sd, images, batch, args.volume)
+        total += secs
+    dt = total / steps
+    return B / dt, dt, torch.get_num_threads(), out
 
 
 def main_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 2)), max(1, min(args.warmup, 1))
-    rate, dt, threads = cpu_oracle_rate(args, steps, warmup)
+    steps, warmup = max(1, min(args.steps, 2)), 1
+    rate, dt, threads, _ = cpu_oracle_rate(args, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch 1 per step (bounded CPU sample)"
-                   % (args.layers, args.views, args.image, args.image, args.volume)},
+        "config": {"workload": "Volumetric(softmax) ResNet-%d, %d views %dx%d, %d^3 grid, batch %d per GPU"
+                   % (args.layers, args.views, args.image, args.image, args.volume, args.batch),
+                   "note": "CPU arm: %d timed forward(s) of one batch (bounded sample of the same workload), warm-up = one sample" % steps},
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "%d timed forwards of one %d-view sample, CPU oracle port (torch fp32 + numpy), %d threads"
-                                   % (steps, args.views, threads)},
+                         "sample": "%d timed forward(s) of a %d-sample batch of %d-view inputs, CPU oracle port (torch fp32 + numpy), %d of %d host threads"
+                                   % (steps, args.batch, args.views, threads, os.cpu_count())},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def torch_gpu_rate(args, dev, sd, images_dev, batch, tf32, steps=None):
+    """The reference formulation (torch ops through ATen/cuDNN, eval, no autograd) on `dev`: samples/s, CUDA-event timed."""
+    import lt_b200
+    from lt_b200 import testing
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    torch.backends.cudnn.benchmark = True
+    try:
+        cfg = testing.make_config(num_layers=args.layers, volume_size=args.volume)
+        model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="torch")
+        model.load_state_dict(sd)
+        model = model.to(dev).eval()
+        steps = steps or max(2, min(args.steps, 5))
+        with torch.no_grad():
+            for _ in range(3):
+                model(images_dev, None, batch)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model(images_dev, None, batch)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del model
+        torch.cuda.empty_cache()
+        return {"value": images_dev.shape[0] / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+                "dtype": "tf32" if tf32 else "f32", "what": "same module with backend='torch' (ATen/cuDNN, cudnn.benchmark) on the same GPU, weights and inputs"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
 
 
 def main_torch_gpu(args, rank):
@@ -381,10 +422,33 @@ def main_native(args, rank, world, local_rank):
     extra["step_breakdown_ms"] = {k: round(v[0], 3) for k, v in agg.items()}
 
     cpu = None
+    parity_obj = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, dt, threads = cpu_oracle_rate(args, 1, 1)
+        # the CPU arm runs the bench's own weights and inputs, so its outputs double as the parity check of this very run:
+        # full-size config #2 batch through the native path (graph-free replay of the timed step) vs the oracle
+        from oracle import parity
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            native_out = model(images_dev, None, batch)
+        torch.cuda.synchronize()
+        rate, dt, threads, oracle_out = cpu_oracle_rate(args, 1, sd_cpu, images, batch)
         cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "1 warm-up + 1 timed forward of one %d-view sample (same config), CPU oracle port, %d of %d host threads" % (V, threads, os.cpu_count())}
+               "sample": "1 warm-up forward of one sample + 1 timed forward of the bench's %d-sample batch (same config, same weights and "
+                         "inputs as the GPU arm), CPU oracle port, %d of %d host threads" % (B, threads, os.cpu_count())}
+        parity_obj = parity.compare_outputs(native_out, oracle_out)
+        parity_obj["against"] = "oracle/vol_oracle.volumetric_forward (CPU restatement of reference triangulation.py:245-355) on the bench batch"
+        del native_out, oracle_out
+
+    torch_bars = {}
+    if rank == 0 and world == 1 and not args.no_torch_gpu:
+        # secondary bar: the reference's own torch formulation through ATen/cuDNN on the same B200, same weights/inputs
+        sd_dev = model.state_dict()
+        for key, tf32 in (("torch_gpu", False), ("torch_gpu_tf32", True)):
+            try:
+                torch_bars[key] = torch_gpu_rate(args, dev, sd_dev, images_dev, batch, tf32)
+                torch_bars[key]["native_over_this"] = value / torch_bars[key]["value"]
+            except Exception as exc:   # noqa: BLE001 - reported in the line
+                torch_bars[key] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
         line = {
@@ -407,7 +471,9 @@ def main_native(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity_obj,
         }
+        line.update(torch_bars)
         line.update(extra)
         print(json.dumps(line), flush=True)
     if dist is not None:

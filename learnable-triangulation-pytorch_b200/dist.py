@@ -63,7 +63,7 @@ def new_view_groups(plan):
     return mine
 
 
-def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum"):
+def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum", out=None):
     """partial: [B][P][nvox][C] float32 on every rank of the group -> the block of fully reduced samples this rank owns.
 
     Returns a tensor [B/G][P][nvox][C].  `reduce_op` is "sum" (softmax num/den, sum, conf) or "max".
@@ -75,7 +75,8 @@ def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum
     B = partial.shape[0]
     per = B // plan.group_size
     if collective == "reduce_scatter":
-        out = torch.empty((per,) + tuple(partial.shape[1:]), dtype=partial.dtype, device=partial.device)
+        if out is None:
+            out = torch.empty((per,) + tuple(partial.shape[1:]), dtype=partial.dtype, device=partial.device)
         dist.reduce_scatter_tensor(out, partial.contiguous(), op=op, group=pg)
         return out
     dist.all_reduce(partial, op=op, group=pg)

@@ -94,6 +94,7 @@ class NativeEngine:
         self.tc_impl = {"simt": CONV_SIMT, "tc": CONV_TC, "tc1": CONV_TC1}[mode]
         self._packs = None
         self._packs_version = None
+        self._epoch = 0
         self._graphs = {}
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
         self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
@@ -105,7 +106,17 @@ class NativeEngine:
 
     # ------------------------------------------------------------------ weight packing
     def _param_version(self):
-        return tuple(p._version for p in self.model.parameters()) + tuple(b._version for b in self.model.buffers())
+        """Key that changes whenever the packed filters / captured graphs may be stale: in-place updates bump `_version`;
+        `p.data = ...`, `.to()/.cuda()/.double()` and `load_state_dict(assign=True)` change storage pointer, device or dtype
+        instead.  (`p.data.copy_()` bypasses both: call `invalidate()` after such an update.)"""
+        items = list(self.model.parameters()) + list(self.model.buffers())
+        return tuple((t._version, t.data_ptr(), t.device, t.dtype) for t in items) + (self._epoch,)
+
+    def invalidate(self):
+        """Drop the packed filters and the captured CUDA graphs; the next forward re-packs from the module's tensors."""
+        self._epoch += 1
+        self._packs = None
+        self._graphs = {}
 
     def _pack(self, w_taps, bias, bn, k, stride, pad, force_simt=False, out_fmt=None):
         """w_taps: float32 [taps][Cin][Cout] (device)."""
@@ -505,69 +516,169 @@ class NativeEngine:
             return keypoints, features, volumes, coord, conf
         return keypoints, features, volumes, coord
 
+    # ------------------------------------------------------------------ multi-GPU (view-sharded) step
+    def _sh_exchange_state(self, plan, pg, collective, B, feats_shape, planes, nvox, dev):
+        """Peer-memory buffers of the `features` / `p2p` exchanges (symmetric memory, allocated once per shape)."""
+        from . import dist as lt_dist
+        h, w, C = feats_shape
+        if collective == "features":
+            key = ("feat", B, plan.n_views, h, w, C)
+            if getattr(self, "_peer_key", None) != key:
+                self._peer = lt_dist.FeatureExchange(plan, pg, B, plan.n_views, h, w, C, dev)
+                self._peer_key = key
+        elif collective == "p2p":
+            key = ("p2p", B, planes, nvox, C)
+            if getattr(self, "_peer_key", None) != key:
+                self._peer = lt_dist.PeerExchange(plan, pg, B, planes, nvox, C, dev)
+                self._peer_key = key
+        return getattr(self, "_peer", None)
+
+    def _sh_pre(self, images_local, proj_local, position, center, step, rot, plan, collective):
+        """Stage 1 (capturable: our kernels only): coordinate volumes, backbone on this rank's views, and -- for the NCCL
+        exchanges -- the packed partial aggregates of those views."""
+        m = self.model
+        B, Vl = images_local.shape[:2]
+        n = m.volume_size
+        nvox = n * n * n
+        dev = images_local.device
+        coord = torch.empty((B, n, n, n, 3), dtype=torch.float32, device=dev)
+        capi.coord_volume(position, center, step, rot, coord, m.transfer_cmu_to_human36m)
+        self.launches += 1
+        feats = self.backbone_features(images_local.reshape(B * Vl, *images_local.shape[2:]))
+        partial = None
+        if plan.group_size > 1 and collective in ("all_reduce", "reduce_scatter"):
+            planes = 2 if m.volume_aggregation_method == "softmax" else 1
+            partial = torch.empty((B, planes, nvox, feats.C), dtype=torch.float32, device=dev)
+            capi.unproject_partial(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None, partial,
+                                   capi.AGG[m.volume_aggregation_method])
+            self.launches += 1
+        return coord, feats, partial
+
+    def _sh_exchange(self, coord, feats, partial, proj_local, plan, pg, collective, out=None):
+        """Stage 2: the ONE exchange step of the view group (NCCL collective, or peer-memory stores + group barriers)."""
+        from . import dist as lt_dist
+        m = self.model
+        B = coord.shape[0]
+        Vl = feats.N // B
+        nvox = coord.shape[1] ** 3
+        agg = capi.AGG[m.volume_aggregation_method]
+        if plan.group_size == 1:
+            return None
+        if collective == "features":
+            fx = self._peer
+            fx.barrier()      # every owner has finished reading the previous step's maps
+            fx.scatter(feats.data.view(B, Vl, feats.H, feats.W, feats.C))
+            self.launches += 1
+            fx.barrier()      # all stores of the group have landed
+            return None
+        if collective == "p2p":
+            px = self._peer
+            px.barrier()
+            capi.unproject_push(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None,
+                                px.peer_ptrs, plan.view_rank, agg)
+            self.launches += 1
+            px.barrier()
+            return None
+        return lt_dist.complete_partials(partial, plan, pg, collective, "max" if m.volume_aggregation_method == "max" else "sum", out=out)
+
+    def _sh_post(self, coord, feats, mine, proj_local, proj_all, plan, collective):
+        """Stage 3 (capturable): aggregate volume of the samples this rank owns, V2V, soft-argmax."""
+        m = self.model
+        B = coord.shape[0]
+        n = m.volume_size
+        nvox = n * n * n
+        dev = coord.device
+        agg = capi.AGG[m.volume_aggregation_method]
+        own = plan.owned_samples(B)
+        Bl = len(own)
+        coord_own = coord[own[0]:own[-1] + 1]
+        vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
+        if plan.group_size == 1:
+            capi.unproject_aggregate(feats.data.view(B, feats.N // B, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None,
+                                     vol.data, vol.fmt, agg)
+        elif collective == "features":
+            # the owner unprojects all views of its samples with exactly the single-GPU arithmetic
+            capi.unproject_aggregate(self._peer.buf, proj_all[own[0]:own[-1] + 1].contiguous(), coord_own.reshape(Bl, nvox, 3), None,
+                                     vol.data, vol.fmt, agg)
+        elif collective == "p2p":
+            capi.unproject_reduce_finalize(self._peer.buf, plan.group_size, vol.data, vol.fmt, Bl, feats.C, nvox, agg)
+        else:
+            capi.unproject_finalize(mine.contiguous(), vol.data, vol.fmt, Bl, feats.C, nvox, agg)
+        self.launches += 1
+        logits = self.v2v(vol)
+        kp, volumes = self.softargmax(logits, coord_own.contiguous(), m.num_joints, m.volume_multiplier, m.volume_softmax)
+        return kp, volumes
+
     def forward_view_sharded(self, images_local, proj_local, position, center, step, rot, plan, pg, collective="all_reduce",
-                             proj_all=None):
+                             proj_all=None, use_graph=False):
         """Multi-GPU step of one rank (see dist.py): this rank's views of the group's batch in, all keypoints out.
 
         images_local (B, V_local, 3, H, W), proj_local (B, V_local, 3, 4); the other inputs cover all B samples.
-        backbone + unprojection partials -> ONE collective over the view group -> V2V + soft-argmax on the
+        backbone (+ unprojection partials) -> ONE exchange over the view group -> V2V + soft-argmax on the
         B / group_size samples this rank owns -> all-gather of the (B, 17, 3) keypoints.
+
+        use_graph: stages 1 and 3 are captured into two CUDA graphs (one pair per input shape and exchange kind); only the
+        exchange itself and the key-point all-gather are issued eagerly between / after the replays.
         """
         from . import dist as lt_dist
         self.prepare()
         m = self.model
         B, Vl = images_local.shape[:2]
         n = m.volume_size
-        nvox = n * n * n
         dev = images_local.device
-        self.launches = 0
-        coord = torch.empty((B, n, n, n, 3), dtype=torch.float32, device=dev)
-        capi.coord_volume(position, center, step, rot, coord, m.transfer_cmu_to_human36m)
-        feats = self.backbone_features(images_local.reshape(B * Vl, *images_local.shape[2:]))
-        agg = capi.AGG[m.volume_aggregation_method]
         planes = 2 if m.volume_aggregation_method == "softmax" else 1
         if collective == "features" and plan.group_size > 1:
-            # exchange feature maps (14x fewer bytes than voxel partials), then unproject all views of the owned samples
             assert proj_all is not None, "collective='features' needs the projection matrices of all views"
-            V = plan.n_views
-            key = ("feat", B, V, feats.H, feats.W, feats.C)
-            if getattr(self, "_peer_key", None) != key:
-                self._peer = lt_dist.FeatureExchange(plan, pg, B, V, feats.H, feats.W, feats.C, dev)
-                self._peer_key = key
-            fx = self._peer
-            fx.barrier()
-            fx.scatter(feats.data.view(B, Vl, feats.H, feats.W, feats.C))
-            fx.barrier()
-            own = plan.owned_samples(B)
-            Bl = len(own)
-            vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
-            capi.unproject_aggregate(fx.buf, proj_all[own[0]:own[-1] + 1].contiguous(),
-                                     coord[own[0]:own[-1] + 1].reshape(Bl, nvox, 3), None, vol.data, vol.fmt, agg)
-        elif collective == "p2p" and plan.group_size > 1:
-            # fused unprojection + exchange: partials are stored straight into the owner's buffer over NVLink
-            key = (B, planes, nvox, feats.C)
-            if getattr(self, "_peer_key", None) != key:
-                self._peer = lt_dist.PeerExchange(plan, pg, B, planes, nvox, feats.C, dev)
-                self._peer_key = key
-            px = self._peer
-            px.barrier()      # every owner has finished reducing the previous step's slots
-            capi.unproject_push(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None,
-                                px.peer_ptrs, plan.view_rank, agg)
-            px.barrier()      # all pushes of the group have landed
-            Bl = B // plan.group_size
-            vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
-            capi.unproject_reduce_finalize(px.buf, plan.group_size, vol.data, vol.fmt, Bl, feats.C, nvox, agg)
+        if proj_all is None:
+            proj_all = proj_local
+        ins = (images_local, proj_local, position, center, step, rot, proj_all)
+        if not use_graph:
+            self.launches = 0
+            coord, feats, partial = self._sh_pre(*ins[:6], plan, collective)
+            self._sh_exchange_state(plan, pg, collective, B, (feats.H, feats.W, feats.C), planes, n ** 3, dev)
+            mine = self._sh_exchange(coord, feats, partial, proj_local, plan, pg, collective)
+            kp, volumes = self._sh_post(coord, feats, mine, proj_local, proj_all, plan, collective)
         else:
-            partial = torch.empty((B, planes, nvox, feats.C), dtype=torch.float32, device=dev)
-            capi.unproject_partial(feats.data.view(B, Vl, feats.H, feats.W, feats.C), proj_local, coord.view(B, nvox, 3), None, partial, agg)
-            mine = lt_dist.complete_partials(partial, plan, pg, collective, "max" if m.volume_aggregation_method == "max" else "sum")
-            Bl = mine.shape[0]
-            vol = Act(Bl, n, n, n, feats.C, self.act_fmt, dev)
-            capi.unproject_finalize(mine.contiguous(), vol.data, vol.fmt, Bl, feats.C, nvox, agg)
-        self.launches += 3
-        logits = self.v2v(vol)
-        own = plan.owned_samples(B)
-        kp, volumes = self.softargmax(logits, coord[own[0]:own[-1] + 1].contiguous(), m.num_joints, m.volume_multiplier, m.volume_softmax)
+            key = ("sharded", tuple(images_local.shape), dev.index, collective, plan.group_size, plan.view_rank)
+            g = self._graphs.get(key)
+            if g is None:
+                static_in = [t.clone() for t in ins]
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):      # eager warm-up: module load, function attributes, peer buffers, NCCL communicator
+                    self.launches = 0
+                    c0, f0, p0 = self._sh_pre(*static_in[:6], plan, collective)
+                    self._sh_exchange_state(plan, pg, collective, B, (f0.H, f0.W, f0.C), planes, n ** 3, dev)
+                    m0 = self._sh_exchange(c0, f0, p0, static_in[1], plan, pg, collective)
+                    self._sh_post(c0, f0, m0, static_in[1], static_in[6], plan, collective)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                del c0, f0, p0, m0
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                self.launches = 0
+                with torch.cuda.graph(ga):
+                    coord, feats, partial = self._sh_pre(*static_in[:6], plan, collective)
+                la = self.launches
+                # stage 3 reads the reduced block from a static address: the in-place all-reduce leaves it in this rank's
+                # slice of `partial`; the reduce-scatter writes into a buffer allocated here
+                per = B // plan.group_size
+                mine_static = None
+                if partial is not None:
+                    mine_static = (torch.empty((per,) + tuple(partial.shape[1:]), dtype=torch.float32, device=dev)
+                                   if collective == "reduce_scatter" else partial[plan.view_rank * per:(plan.view_rank + 1) * per])
+                with torch.cuda.graph(gb, pool=ga.pool()):
+                    kp, volumes = self._sh_post(coord, feats, mine_static, static_in[1], static_in[6], plan, collective)
+                g = (ga, gb, static_in, (coord, feats, partial, mine_static), (kp, volumes), la, self.launches)
+                self._graphs[key] = g
+            ga, gb, static_in, (coord, feats, partial, mine_static), (kp, volumes), la, lall = g
+            for dst, src in zip(static_in, ins):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            ga.replay()
+            self.launches = lall
+            self._sh_exchange(coord, feats, partial, static_in[1], plan, pg, collective,
+                              out=mine_static if collective == "reduce_scatter" else None)
+            gb.replay()
         kp_all = lt_dist.gather_keypoints(kp, plan, pg)
         features = feats.data.view(B, Vl, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
         return kp_all, features, volumes, coord

@@ -20,6 +20,18 @@ from . import multiview, op, pose_resnet, torch_ops, volumetric
 from .v2v import V2VModel
 
 
+def backbone_map_size(size):
+    """Spatial size of the backbone's heat-map / feature output for an input side `size` (pose_resnet.py:293-313):
+    7x7 s2 p3 stem, 3x3 s2 p1 max-pool, three 3x3 s2 p1 stages, three k4 s2 p1 transposed convs.  This is the same
+    arithmetic the engine's launch plan follows, so the intrinsics are rescaled by the size the kernels really produce
+    (the reference reads it off `heatmaps.shape`, triangulation.py:264-265)."""
+    s = (size + 6 - 7) // 2 + 1
+    s = (s + 2 - 3) // 2 + 1
+    for _ in range(3):
+        s = (s + 2 - 3) // 2 + 1
+    return s * 8
+
+
 def _base_points(batch, batch_size, kind, use_gt_pelvis):
     """Pelvis (mpii: joint 6) or hip midpoint (coco) per sample, float64 (triangulation.py:286-296)."""
     pts = np.empty((batch_size, 3), dtype=np.float64)
@@ -34,7 +46,27 @@ def _base_points(batch, batch_size, kind, use_gt_pelvis):
     return pts
 
 
-class VolumetricTriangulationNet(nn.Module):
+class _EngineOwner(nn.Module):
+    """Keeps the native engine's packed filters / CUDA graphs in step with the module's tensors: `.to()/.cuda()/.float()`
+    (`_apply`) and `load_state_dict` invalidate them explicitly (tensor versions alone miss `p.data` updates)."""
+
+    def _invalidate_engine(self):
+        eng = self.__dict__.get("_engine")
+        if eng is not None:
+            eng.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate_engine()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._invalidate_engine()
+        return out
+
+
+class VolumetricTriangulationNet(_EngineOwner):
     def __init__(self, config, device="cuda:0", backend=None, conv_mode=None, use_cuda_graph=True):
         super().__init__()
         m = config.model
@@ -104,19 +136,25 @@ class VolumetricTriangulationNet(nn.Module):
                                "or construct the model with backend='torch' (LT_B200_BACKEND=torch) for training")
         B, V = images.shape[:2]
         H, W = images.shape[3:]
-        hm_shape = (H // 4, W // 4)   # stem /2, maxpool /2, three stride-2 stages, three x2 deconvs
+        if H % 2 or W % 2:
+            raise ValueError("lt_b200 native backend needs even image sides (space-to-depth stem), got %dx%d" % (H, W))
+        hm_shape = (backbone_map_size(H), backbone_map_size(W))   # == H // 4 only when H is a multiple of 32
         proj, base, position, step, rots, cuboids = self._host_geometry(batch, B, (H, W), hm_shape)
         dev = images.device
 
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=True)
 
-        outs = self.engine().forward(
-            images.float().contiguous(), up(proj), up(position), up(base), up(step), up(rots.reshape(B, 9)))
-        base_points = up(base)
+        with torch.cuda.device(dev):      # launches go to the model's device, whatever the caller's current device is
+            outs = self.engine().forward(
+                images.float().contiguous(), up(proj), up(position), up(base), up(step), up(rots.reshape(B, 9)))
+            base_points = up(base)
         if self.clone_outputs and self.use_cuda_graph:
             outs = tuple(o.clone() for o in outs)
         kp, features, volumes, coord = outs[:4]
+        if tuple(features.shape[3:]) != hm_shape:
+            raise RuntimeError("feature map %s differs from the heat-map size %s used for the projection matrices"
+                               % (tuple(features.shape[3:]), hm_shape))
         vol_conf = outs[4] if len(outs) > 4 else None
         return kp, features, volumes, vol_conf, cuboids, coord, base_points
 
@@ -157,7 +195,7 @@ class VolumetricTriangulationNet(nn.Module):
         return kp, features, volumes, vol_conf, cuboids, coord, cen_t
 
 
-class AlgebraicTriangulationNet(nn.Module):
+class AlgebraicTriangulationNet(_EngineOwner):
     """Drop-in for reference mvn/models/triangulation.py:131-200 (BASELINE config #5): backbone heatmaps -> 2-D
     soft-argmax -> confidence-weighted DLT.  Same ctor keys (`config.model.use_confidences`, `heatmap_softmax`,
     `heatmap_multiplier`, `backbone.*`), same config side effects, same 4-tuple."""

@@ -116,3 +116,28 @@ def test_config2_sizes_tensor_core_vs_exact_fp32():
     assert float((s - 1).abs().max()) < 1e-4
     lo, hi = a[5].reshape(B, -1, 3).min(1)[0], a[5].reshape(B, -1, 3).max(1)[0]
     assert bool(((a[0] >= lo[:, None]) & (a[0] <= hi[:, None])).all()), "expected coordinates must lie inside the cuboid"
+
+
+def test_config2_full_size_vs_oracle():
+    """BASELINE config #2 at full size (ResNet-152, 4 views 384x384, 64^3 grid, calibrated weights, B=1): the native tensor-core
+    path against the CPU oracle's restatement of reference triangulation.py:245-355 on the same inputs -- features, unprojected
+    volume, V2V logits, softmaxed volumes <= 1e-3 relative, keypoints <= 1e-3 of the cuboid, arg-max voxels bit-equal."""
+    from oracle import parity
+    B, V, S, n = 1, 4, 384, 64
+    cfg = testing.make_config(num_layers=152, volume_size=n)
+    holder = lt_b200.VolumetricTriangulationNet(cfg, device=DEV, backend="torch")
+    testing.randomize_weights(holder, seed=2, calib_size=S, calib_views=1)
+    sd = {k: v.detach().cpu() for k, v in holder.state_dict().items()}
+    del holder
+    torch.cuda.empty_cache()
+    images, batch = testing.make_batch(B, V, image_size=S, seed=4)
+    oracle_out, secs = parity.oracle_forward(sd, images, batch, n)
+    model = _native(sd, n, "tc", False, num_layers=152)
+    with torch.no_grad():
+        out = model(images.to(DEV), None, batch)
+    res = parity.compare_outputs(out, oracle_out)
+    res.update(parity.compare_stages(model, images, batch, oracle_out, DEV))
+    print("config2 full size vs oracle (%.1f s CPU): %s" % (secs, res))
+    assert res["coord_volumes_bit_exact"] and res["argmax_equal"]
+    assert res["features_rel"] < 1e-3 and res["unprojected_rel"] < 1e-3 and res["logits_rel"] < 1e-3 and res["volumes_rel"] < 1e-3
+    assert res["keypoints_mm"] < 1e-3 * parity.CUBOID_MM
