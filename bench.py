@@ -49,8 +49,10 @@ def parse():
     ap.add_argument("--image", type=int, default=384)
     ap.add_argument("--volume", type=int, default=64)
     ap.add_argument("--layers", type=int, default=152)
-    ap.add_argument("--collective", default="features", choices=["all_reduce", "reduce_scatter", "p2p", "features"],
-                    help="view-group exchange: one NCCL all-reduce (contract), reduce-scatter, or the fused P2P-store kernel")
+    ap.add_argument("--collective", default="both", choices=["both", "all_reduce", "reduce_scatter", "p2p", "features"],
+                    help="view-group exchange(s) to measure at N > 1: both = the NCCL all-reduce contract path AND the feature-map exchange "
+                         "(value = the faster one, both reported under `exchanges`)")
+    ap.add_argument("--no-config4", action="store_true", help="N = 8 only: skip the extra 8-view / one-view-per-GPU measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true", help="skip the ATen/cuDNN secondary bars (fp32 and TF32) of the native arm")
     ap.add_argument("--no-calibrate", action="store_true", help="keep PyTorch default init (faster start, degenerate signal)")
@@ -217,6 +219,94 @@ def main_torch_gpu(args, rank):
                                  % (args.layers, V, S, S, n, B)}}), flush=True)
 
 
+EXCHANGE_TEXT = {
+    "all_reduce": "packed (sum s*e^s, sum e^s) voxel partials completed by ONE NCCL all-reduce over the view group (north-star contract)",
+    "reduce_scatter": "packed voxel partials completed by one NCCL reduce-scatter (each rank receives only its samples)",
+    "p2p": "voxel partials stored into the owner rank by the unprojection kernel over NVLink peer memory",
+    "features": "32-channel feature maps stored into the owner rank over NVLink peer memory (14x fewer bytes); the owner unprojects all views",
+}
+
+
+class ShardedArm:
+    """One view-sharded configuration of the multi-GPU bench: `views` views per sample split over the ranks of a view group."""
+
+    def __init__(self, args, model, world, rank, dev, views):
+        from lt_b200 import dist as lt_dist, testing
+        self.args, self.model, self.eng, self.dev, self.rank, self.world = args, model, model.engine(), dev, rank, world
+        B, S = args.batch, args.image
+        self.plan = plan = lt_dist.make_plan(world, rank, views)
+        self.pg = lt_dist.new_view_groups(plan)
+        self.Bg = Bg = B * plan.group_size
+        self.images_g, self.batch = testing.make_batch(Bg, views, image_size=S, seed=100 + plan.group_index)
+        self.images = self.images_g[:, plan.views].contiguous()
+        self.pinned = self.images.pin_memory()
+        self.images_dev = self.images.to(dev)
+        from lt_b200.triangulation import backbone_map_size
+        hm = (backbone_map_size(S), backbone_map_size(S))
+        proj, base, position, stepv, rots, _ = model._host_geometry(self.batch, Bg, (S, S), hm)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        self.geo = (up(proj[:, plan.views]), up(position), up(base), up(stepv), up(rots.reshape(Bg, 9)), up(proj))
+        self.h2d = self.images.numel() * 4
+        self.views = views
+
+    def step(self, img, collective, graph=True):
+        g = self.geo
+        return self.eng.forward_view_sharded(img, g[0], g[1], g[2], g[3], g[4], self.plan, self.pg, collective, proj_all=g[5],
+                                             use_graph=graph)[0]
+
+    def describe(self, collective):
+        p = self.plan
+        return "view-sharded: %d group(s) x %d ranks, %d of %d view(s) per rank, group batch %d; exchange = %s; V2V + soft-argmax batch-sharded; " \
+               "stages 1 and 3 replayed as CUDA graphs" % (p.n_groups, p.group_size, len(p.views), self.views, self.Bg, EXCHANGE_TEXT[collective])
+
+    def check_against_single_gpu(self, collective):
+        """Key points of the samples this rank owns vs a plain single-GPU forward (all views) of the same samples."""
+        own = self.plan.owned_samples(self.Bg)
+        lo, hi = own[0], own[-1] + 1
+        sub = {"cameras": [c[lo:hi] for c in self.batch["cameras"]], "keypoints_3d": self.batch["keypoints_3d"][lo:hi],
+               "pred_keypoints_3d": self.batch["pred_keypoints_3d"][lo:hi]}
+        kp_all = self.step(self.images_dev, collective).clone()
+        saved = (self.model.use_cuda_graph, self.eng.use_graph)
+        self.model.use_cuda_graph = self.eng.use_graph = False
+        kp_single = self.model(self.images_g[lo:hi].to(self.dev), None, sub)[0]
+        self.model.use_cuda_graph, self.eng.use_graph = saved
+        torch.cuda.synchronize()
+        return float((kp_all[lo:hi] - kp_single).abs().max())
+
+    def measure(self, collective, steps, warmup, flush, barrier):
+        """-> dict(dev_ms, e2e_s, launches, kp_err_mm) for this exchange (device-resident arm, then end-to-end arm)."""
+        err = self.check_against_single_gpu(collective)
+        for _ in range(max(warmup, 3)):
+            self.step(self.images_dev, collective)
+        barrier()
+        launches = self.eng.launches
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.step(self.images_dev, collective)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        for _ in range(2):
+            kp = self.step(self.pinned.to(self.dev, non_blocking=True), collective).cpu()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            kp = self.step(self.pinned.to(self.dev, non_blocking=True), collective).cpu()
+        barrier()
+        return {"dev_ms": dev_ms, "e2e_s": time.perf_counter() - t0, "launches": launches, "kp_err_mm": err, "d2h": kp.numel() * 4}
+
+
+def reduce_max(vals, dev, dist):
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
 def main_native(args, rank, world, local_rank):
     import lt_b200
     from lt_b200 import testing
@@ -234,7 +324,7 @@ def main_native(args, rank, world, local_rank):
     torch.manual_seed(0)
     np.random.seed(0)
     sharded = world > 1
-    model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="native", conv_mode=args.mode, use_cuda_graph=not sharded)
+    model = lt_b200.VolumetricTriangulationNet(cfg, device=dev, backend="native", conv_mode=args.mode, use_cuda_graph=True)
     if not args.no_calibrate:
         testing.randomize_weights(model, seed=0, calib_size=S, calib_views=1)
     model = model.to(dev).eval()
@@ -248,90 +338,51 @@ def main_native(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    if not sharded:
-        images, batch = testing.make_batch(B, V, image_size=S, seed=rank)
-        pinned = images.pin_memory()
-        images_dev = images.to(dev)
-        parallelism = "dp1"
-
-        def step(img):
-            return model(img, None, batch)[0]
-    else:
-        # view-sharded: G ranks share a group batch of B*G samples and split its views; W/G groups are replicas
-        from lt_b200 import dist as lt_dist
-        plan = lt_dist.make_plan(world, rank, V)
-        pg = lt_dist.new_view_groups(plan)
-        Bg = B * plan.group_size
-        images_g, batch = testing.make_batch(Bg, V, image_size=S, seed=100 + plan.group_index)
-        views = plan.views
-        images = images_g[:, views].contiguous()
-        pinned = images.pin_memory()
-        images_dev = images.to(dev)
-        proj, base, position, stepv, rots, _ = model._host_geometry(batch, Bg, (S, S), (S // 4, S // 4))
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-        geo = (up(proj[:, views]), up(position), up(base), up(stepv), up(rots.reshape(Bg, 9)), up(proj))
-        parallelism = "view-sharded: %d group(s) x %d ranks, %d view(s)/rank, packed num/den %s, V2V batch-sharded" % (
-            plan.n_groups, plan.group_size, len(views),
-            "stored into the owner rank by the unprojection kernel over NVLink peer memory" if args.collective == "p2p"
-            else ("replaced by a feature-map exchange over NVLink peer memory (unprojection on the owner)" if args.collective == "features"
-                  else args.collective + " over NCCL"))
-
-        def step(img):
-            return eng.forward_view_sharded(img, geo[0], geo[1], geo[2], geo[3], geo[4], plan, pg, args.collective, proj_all=geo[5])[0]
-    h2d = images.numel() * 4
-
+    exchanges, config4 = None, None
     with torch.no_grad():
-        if sharded and args.collective != "all_reduce":
-            # the peer-memory exchanges need CUDA IPC / symmetric memory between all ranks of a view group; if any rank
-            # cannot set them up, every rank falls back to the NCCL all-reduce contract path (reported in config)
-            failed = 0
-            try:
-                step(images_dev)
-                torch.cuda.synchronize()
-            except Exception as exc:   # noqa: BLE001 - reported, then the contract path is used
-                failed = 1
-                print("rank %d: collective %r unavailable (%s: %s); using all_reduce" % (rank, args.collective, type(exc).__name__, exc),
-                      file=sys.stderr, flush=True)
-            flag = torch.tensor([failed], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            if int(flag.item()):
-                parallelism += " [requested %s exchange unavailable on this box -> all_reduce over NCCL]" % args.collective
-                args.collective = "all_reduce"
-        # ---- device-resident arm: CUDA events, L2 flushed between iterations ----
-        for _ in range(max(args.warmup, 3)):
-            step(images_dev)
-        barrier()
-        launches = eng.launches
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        evs = []
-        for _ in range(args.steps):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step(images_dev)
-            e1.record()
-            evs.append((e0, e1))
-        barrier()
-        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-        clocks = sampler.summary()
-
-        # ---- end-to-end arm: pinned host images -> device, forward, keypoints -> host ----
-        for _ in range(2):
-            kp = step(pinned.to(dev, non_blocking=True)).cpu()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            kp = step(pinned.to(dev, non_blocking=True)).cpu()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        d2h = kp.numel() * 4
-        e2e_sync_s = e2e_s
-
-        # ---- end-to-end, pipelined (single-GPU path): the collated HWC batch in pinned memory goes through
-        # lt_b200.pipeline.InferenceStream -- every step still uploads its own images and reads its own keypoints back,
-        # but the upload of batch i+1 overlaps the forward of batch i ----
         if not sharded:
+            images, batch = testing.make_batch(B, V, image_size=S, seed=rank)
+            pinned = images.pin_memory()
+            images_dev = images.to(dev)
+            parallelism = "dp1"
+            h2d = images.numel() * 4
+
+            def step(img):
+                return model(img, None, batch)[0]
+
+            # ---- device-resident arm: CUDA events around graph replays, L2 flushed between iterations ----
+            for _ in range(max(args.warmup, 3)):
+                step(images_dev)
+            barrier()
+            launches = eng.launches
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            evs = []
+            for _ in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step(images_dev)
+                e1.record()
+                evs.append((e0, e1))
+            barrier()
+            dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+            clocks = sampler.summary()
+
+            # ---- end-to-end arm, synchronous: pinned host images -> device, forward, keypoints -> host ----
+            for _ in range(2):
+                kp = step(pinned.to(dev, non_blocking=True)).cpu()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                kp = step(pinned.to(dev, non_blocking=True)).cpu()
+            barrier()
+            e2e_sync_s = time.perf_counter() - t0
+            d2h = kp.numel() * 4
+
+            # ---- end-to-end, pipelined: the collated HWC batch in pinned memory goes through lt_b200.pipeline.InferenceStream --
+            # every step still uploads its own images and reads its own keypoints back, but the upload of batch i+1 overlaps
+            # the forward of batch i ----
             from lt_b200 import pipeline
             hwc = pipeline.pinned_empty((B, V, S, S, 3), np.float32)
             hwc[...] = images.permute(0, 1, 3, 4, 2).numpy()
@@ -352,13 +403,54 @@ def main_native(args, rank, world, local_rank):
             barrier()
             e2e_s = time.perf_counter() - t0
             assert stream.h2d_bytes == h2d * args.steps and stream.d2h_bytes == d2h * args.steps
+            eager_step = lambda: step(images_dev)
+        else:
+            # ---- view-sharded: G ranks share a group batch of B*G samples and split its views; W/G groups are replicas ----
+            arm = ShardedArm(args, model, world, rank, dev, V)
+            names = ["all_reduce", "features"] if args.collective == "both" else [args.collective]
+            results = {}
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            for name in names:
+                failed = 0
+                try:
+                    results[name] = arm.measure(name, args.steps, args.warmup, flush, barrier)
+                except Exception as exc:   # noqa: BLE001 - an exchange that cannot be set up on this box is reported, not fatal
+                    failed = 1
+                    print("rank %d: exchange %r unavailable (%s: %s)" % (rank, name, type(exc).__name__, exc), file=sys.stderr, flush=True)
+                if int(reduce_max([failed], dev, dist)[0]):
+                    results.pop(name, None)
+            clocks = sampler.summary()
+            if not results:
+                raise SystemExit("no view-group exchange could be set up")
+            exchanges = {}
+            for name, r in results.items():
+                dms, es, err = reduce_max([r["dev_ms"], r["e2e_s"], r["kp_err_mm"]], dev, dist)
+                exchanges[name] = {"value": B * world * args.steps / (dms / 1e3), "unit": "samples/s", "ms_per_step": dms / args.steps,
+                                   "e2e": B * world * args.steps / es, "keypoints_vs_single_gpu_mm": err,
+                                   "gpu_launches_per_step": r["launches"], "exchange": EXCHANGE_TEXT[name]}
+                assert err < 0.05, "view-sharded key points (%s) differ from the single-GPU forward by %.4f mm" % (name, err)
+            best = max(exchanges, key=lambda k: exchanges[k]["value"])
+            r = results[best]
+            dev_ms, e2e_s, e2e_sync_s, launches, d2h, h2d = r["dev_ms"], r["e2e_s"], r["e2e_s"], r["launches"], r["d2h"], arm.h2d
+            parallelism = arm.describe(best)
+            eager_step = lambda: arm.step(arm.images_dev, best, graph=False)
+            if world == 8 and V == 4 and not args.no_config4:
+                # BASELINE config #4: 8 views, one view per GPU (one view group of 8 ranks)
+                arm8 = ShardedArm(args, model, world, rank, dev, 8)
+                r8 = arm8.measure(best, max(2, args.steps // 2), args.warmup, flush, barrier)
+                dms, es, err = reduce_max([r8["dev_ms"], r8["e2e_s"], r8["kp_err_mm"]], dev, dist)
+                k8 = max(2, args.steps // 2)
+                config4 = {"workload": "Volumetric(softmax) ResNet-%d, 8 views %dx%d, %d^3 grid, one view per GPU, group batch %d" % (args.layers, S, S, n, arm8.Bg),
+                           "value": arm8.Bg * k8 / (dms / 1e3), "unit": "samples/s", "ms_per_step": dms / k8, "e2e": arm8.Bg * k8 / es,
+                           "exchange": best, "keypoints_vs_single_gpu_mm": err, "parallelism": arm8.describe(best)}
 
-        # ---- per-kernel timing for the roofline: one eager (non-graph) forward with event pairs per launch ----
+        # ---- per-kernel timing for the roofline: one eager (non-graph) step with a CUDA-event pair per launch ----
         eng.use_graph = False
         model.use_cuda_graph = False
-        step(images_dev)
+        eager_step()
         eng.timeline = []
-        step(images_dev)
+        eager_step()
         torch.cuda.synchronize()
         agg = {}
         per_launch = []
@@ -373,10 +465,7 @@ def main_native(args, rank, world, local_rank):
         eng.timeline = None
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_s, e2e_sync_s = reduce_max([dev_ms, e2e_s, e2e_sync_s], dev, dist)
     total_samples = B * world * args.steps
     value = total_samples / (dev_ms / 1e3)
     e2e = total_samples / e2e_s
@@ -388,7 +477,8 @@ def main_native(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # DRAM bytes per launch from the committed ncu launch list
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
-    tensor_kernels = [k for k in ("conv_tc", "conv_fold", "conv_ffma") if k in agg]
+    kernel_names = {"conv_tc": "conv_tc_kernel", "conv_pair": "conv_pair_kernel", "conv_fold": "conv_fold_kernel", "conv_ffma": "conv_simt_kernel"}
+    tensor_kernels = [k for k in kernel_names if k in agg]
     conv_key = max(tensor_kernels, key=lambda k: agg[k][0]) if tensor_kernels else None
 
     def tensor_roof(key):
@@ -396,11 +486,12 @@ def main_native(args, rank, world, local_rank):
         ach = fl / (ms / 1e3) / 1e12
         tc = key != "conv_ffma"
         peak = pk["bf16_tflops"] if tc else 75.0
-        r = {"kernel": {"conv_tc": "conv_tc_kernel", "conv_fold": "conv_fold_kernel", "conv_ffma": "conv_simt_kernel"}[key],
+        r = {"kernel": kernel_names[key],
              "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-             "traffic": traffic.get({"conv_tc": "conv_tc_kernel", "conv_fold": "conv_fold_kernel"}.get(key)),
+             "traffic": traffic.get(kernel_names[key]),
              "launches": cnt, "ms_per_step": ms,
-             "peak_source": pk["src"] + (" sustained dense bf16/fp16 (cuBLAS)" if tc else " nominal fp32 FFMA")}
+             "peak_source": pk["src"] + (" sustained dense bf16/fp16 (cuBLAS)" if tc else " nominal fp32 FFMA"),
+             "timing": "per-launch CUDA-event pairs in one eager (graph-free) step; graph replay is up to ~6 % faster"}
         if tc and args.mode == "tc":
             # fp32-grade results cost three fp16 products per term (hi*hi, hi*lo, lo*hi): tensor-pipe work actually issued
             r["issued_mma_tflops"] = 3.0 * ach
@@ -412,6 +503,14 @@ def main_native(args, rank, world, local_rank):
     for key in tensor_kernels:
         if key != conv_key:
             extra["roofline_" + key] = tensor_roof(key)
+    if tensor_kernels:
+        # all tensor-core conv kernels together (the V2V + backbone conv path of the north star)
+        ms = sum(agg[k][0] for k in tensor_kernels if k != "conv_ffma")
+        fl = sum(agg[k][1] for k in tensor_kernels if k != "conv_ffma")
+        if ms > 0:
+            extra["roofline_conv_all"] = {"bound": "tensor", "achieved": fl / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                                          "frac": fl / (ms / 1e3) / 1e12 / pk["bf16_tflops"], "ms_per_step": ms,
+                                          "issued_frac": 3.0 * fl / (ms / 1e3) / 1e12 / pk["bf16_tflops"] if args.mode == "tc" else None}
     for key in ("unproject", "softargmax"):
         if key in agg:
             ms, fl, nb, cnt = agg[key]
@@ -419,6 +518,8 @@ def main_native(args, rank, world, local_rank):
             extra["roofline_" + key] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                         "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt, "traffic": traffic.get(key),
                                         "peak_source": pk["src"] + " copy bandwidth"}
+    if traffic.get("_source"):
+        extra["traffic_source"] = traffic["_source"]
     extra["step_breakdown_ms"] = {k: round(v[0], 3) for k, v in agg.items()}
 
     cpu = None
@@ -464,7 +565,7 @@ def main_native(args, rank, world, local_rank):
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": ("lt_b200.pipeline.InferenceStream(model).run(batches): pinned HWC batch -> H2D on a copy stream -> layout kernel "
                             "-> forward -> keypoints D2H, upload of batch i+1 overlapping forward i") if not sharded
-                           else "engine.forward_view_sharded per step, synchronous",
+                           else "engine.forward_view_sharded(..., use_graph=True) per step on pinned images (H2D inside), keypoints .cpu(), synchronous",
                     "sync_value": total_samples / e2e_sync_s,
                     "sync_api": "model(images_pinned.to(device, non_blocking=True), None, batch)[0].cpu() per step, no overlap"},
             "gpu_launches": launches * args.steps,
@@ -473,6 +574,10 @@ def main_native(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "parity": parity_obj,
         }
+        if exchanges is not None:
+            line["exchanges"] = exchanges
+        if config4 is not None:
+            line["config4"] = config4
         line.update(torch_bars)
         line.update(extra)
         print(json.dumps(line), flush=True)

@@ -46,8 +46,11 @@ enum lt_conv_impl {
   LT_CONV_SIMT = 0, /* fp32 FFMA implicit GEMM (exact, any shape) */
   LT_CONV_TC = 1,   /* tcgen05, split-fp16 3-term products (fp32-grade) */
   LT_CONV_TC1 = 2,  /* tcgen05, high parts only (plain fp16 precision, fast mode) */
-  LT_CONV_TC_FOLD = 3 /* tcgen05, kw taps folded into N, persistent (Cin = 32 cubic 3^3 / 7^3 stride-1 layers; weights from
+  LT_CONV_TC_FOLD = 3, /* tcgen05, kw taps folded into N, persistent (Cin = 32 cubic 3^3 / 7^3 stride-1 layers; weights from
                          lt_conv_fold_pack_weights; desc->Cout = real channel count <= 32, FC = 32) */
+  LT_CONV_TC_PAIR = 4  /* tcgen05 cta_group::2: CTA pairs compute 256 x {128,256} tiles, persistent, 3-term products into one
+                         accumulator (layers with Cout % 128 == 0 that lt_conv_pair_eligible accepts; weights from
+                         lt_conv_pair_pack_weights) */
 };
 
 /* residual placement in the conv epilogue */
@@ -108,6 +111,13 @@ int lt_unproject_push_fwd(const float* features, const float* proj, const float*
 int lt_unproject_reduce_finalize_fwd(const float* slots, int nslots, void* out, int out_format, int B, int C, long nvox,
                                      int agg, void* stream);
 
+/* Feature-map exchange of the view-sharded path (alternative to the voxel-partial exchanges): rank `view_rank` of an n_peers-rank
+ * view group stores its feature maps [B][V_local][row_elems] (float32) into the owner ranks' peer-mapped buffers
+ * ([B/n_peers][V][row_elems] each; local view j = global view view_rank + j*n_peers); a cross-rank barrier orders the stores,
+ * then each owner runs lt_unproject_aggregate_fwd on its buffer -- exactly the single-GPU arithmetic. */
+int lt_feature_scatter_fwd(const float* feats, float* const* peer_buffers, int n_peers, int view_rank, int B, int V_local,
+                           int V, long row_elems, void* stream);
+
 /* Backward of lt_unproject_aggregate_fwd for the training loop (train.py:236 total_loss.backward(); the reference gets it
  * from autograd through F.grid_sample and the aggregation ops of op.py:131-162).  grad_out [B][nvox][C] float32;
  * grad_features [B][V][h][w][C] and grad_conf [B][V][C] (LT_AGG_CONF, may be NULL) are ACCUMULATED into (zero them first).
@@ -125,7 +135,9 @@ int lt_unproject_aggregate_bwd(const float* features, const float* proj, const f
  *   volumes_out [B][J][nvox] (may be NULL to skip the normalised-volume write)
  *   keypoints_out [B][J][3]
  *   workspace: lt_softargmax3d_workspace_bytes(B, J, nvox) bytes
- *   softmax = 0 selects the ReLU variant (op.py:90-91).
+ *   softmax = 1: softmax over the voxels (op.py:88-89); 0: the ReLU variant (op.py:90-91: no normalisation);
+ *   2: ReLU with mass-normalised coordinates, the non-softmax branch of the 2-D op (integrate_tensor_2d, op.py:25-41:
+ *   volumes_out = relu(logits), keypoints = sum(relu * coord) / sum(relu)).
  * ---------------------------------------------------------------------------------------- */
 /* Backward of the soft-argmax in the op-level (NCDHW) layout: probs = the forward's volumes_out [B][J][nvox],
  * grad_keypoints [B][J][3], grad_volumes [B][J][nvox] or NULL, scratch >= B*J floats -> grad_logits [B][J][nvox]. */
@@ -173,6 +185,13 @@ int lt_conv_nd_fwd(const lt_conv_desc* desc, const void* in, const void* weight,
  * Cin % 32 == 0. */
 size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout);
 int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
+
+/* CTA-pair weight packing: float32 [taps][Cin][Cout] (DEVICE) -> fp16 [taps][Cin/32][CoutP][32 hi | 32 lo] (128-byte rows),
+ * CoutP = round_up(Cout, 128).  lt_conv_pair_eligible: 1 if LT_CONV_TC_PAIR covers this launch (shape / tiling heuristics),
+ * else 0 (use LT_CONV_TC). */
+size_t lt_conv_pair_weight_bytes(int taps, int Cin, int Cout);
+int lt_conv_pair_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
+int lt_conv_pair_eligible(const lt_conv_desc* desc);
 
 /* kw-folded weight packing: float32 [K^3][32][Cout] (DEVICE) -> split-fp16 [kd][kh][kw*NC + co][64], NC = round_up(Cout, 16). */
 size_t lt_conv_fold_weight_bytes(int K, int Cout);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
 
 FMT_F32, FMT_S32 = 0, 1
 AGG = {"sum": 0, "max": 1, "softmax": 2, "conf": 3, "conf_norm": 3}
-CONV_SIMT, CONV_TC, CONV_TC1, CONV_TC_FOLD = 0, 1, 2, 3
+CONV_SIMT, CONV_TC, CONV_TC1, CONV_TC_FOLD, CONV_TC_PAIR = 0, 1, 2, 3, 4
 RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU = 0, 1, 2
 
 c_int, c_long, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
@@ -47,6 +47,7 @@ SIGNATURES = {
     "lt_unproject_finalize_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
     "lt_unproject_push_fwd": (c_int, [c_void_p] * 4 + [ctypes.POINTER(c_void_p), c_int, c_int] + [c_int] * 5 + [c_long, c_int, c_void_p]),
     "lt_unproject_reduce_finalize_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_long, c_int, c_void_p]),
+    "lt_feature_scatter_fwd": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_long, c_void_p]),
     "lt_unproject_aggregate_bwd": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_long, c_int, c_void_p]),
     "lt_softargmax3d_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_long, c_float, c_int, c_void_p]),
     "lt_test_unproject_aggregate_bwd_host": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_long, c_int]),
@@ -57,6 +58,9 @@ SIGNATURES = {
     "lt_conv_nd_fwd": (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6 + [c_int, c_void_p]),
     "lt_conv_tc_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lt_conv_pair_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lt_conv_pair_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lt_conv_pair_eligible": (c_int, [ctypes.POINTER(ConvDesc)]),
     "lt_conv_fold_weight_bytes": (c_size_t, [c_int, c_int]),
     "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
@@ -153,6 +157,15 @@ def unproject_push(features_cl, proj, coord, conf, peer_ptrs, src_rank, agg):
                                        B, V, C, h, w, nvox, agg, _stream()), "lt_unproject_push_fwd")
 
 
+def feature_scatter(feats_local, peer_ptrs, view_rank, n_views):
+    """feats_local (B, V_local, h, w, C) float32 -> rows of the owners' peer buffers ([B/G][V][h*w*C] each)."""
+    B, Vl = feats_local.shape[:2]
+    row = feats_local[0, 0].numel()
+    arr = (c_void_p * len(peer_ptrs))(*peer_ptrs)
+    _check(lib().lt_feature_scatter_fwd(_ptr(feats_local), arr, len(peer_ptrs), view_rank, B, Vl, n_views, row, _stream()),
+           "lt_feature_scatter_fwd")
+
+
 def unproject_reduce_finalize(slots, nslots, out, out_format, B, C, nvox, agg):
     _check(lib().lt_unproject_reduce_finalize_fwd(_ptr(slots), nslots, _ptr(out), out_format, B, C, nvox, agg, _stream()),
            "lt_unproject_reduce_finalize_fwd")
@@ -192,6 +205,18 @@ def conv_tc_weight_bytes(taps, cin, cout):
 
 def conv_tc_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
     _check(lib().lt_conv_tc_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), taps, cin, cout, _stream()), "lt_conv_tc_pack_weights")
+
+
+def conv_pair_weight_bytes(taps, cin, cout):
+    return lib().lt_conv_pair_weight_bytes(taps, cin, cout)
+
+
+def conv_pair_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
+    _check(lib().lt_conv_pair_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), taps, cin, cout, _stream()), "lt_conv_pair_pack_weights")
+
+
+def conv_pair_eligible(desc):
+    return bool(lib().lt_conv_pair_eligible(ctypes.byref(desc)))
 
 
 def conv_fold_weight_bytes(k, cout):

@@ -35,6 +35,9 @@ int conv_simt_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
 int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
                       const void* residual, void* out, int terms, void* stream);
 
+int conv_pair_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                  const void* residual, void* out, void* stream, int probe_only);
+
 int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
                   const void* residual, void* out, void* stream);
 
@@ -72,5 +75,11 @@ extern "C" int lt_conv_nd_fwd(const lt_conv_desc* d, const void* in, const void*
   if (impl == LT_CONV_TC) return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 3, stream);
   if (impl == LT_CONV_TC_FOLD) return conv_fold_fwd(d, in, weight, scale, shift, residual, out, stream);
   if (impl == LT_CONV_TC1) return conv_tc_fwd_terms(d, in, weight, scale, shift, residual, out, 1, stream);
+  if (impl == LT_CONV_TC_PAIR) return conv_pair_fwd(d, in, weight, scale, shift, residual, out, stream, 0);
   return fail(LT_ERR_INVALID, "conv_nd: unknown impl %d", impl);
+}
+
+extern "C" int lt_conv_pair_eligible(const lt_conv_desc* d) {
+  if (!d || d->in_format != LT_FMT_S32 || d->Cin % 32 != 0) return 0;
+  return lt::conv_pair_fwd(d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1) == 0 ? 1 : 0;
 }

@@ -29,13 +29,16 @@ int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---- split-fp16 ("S32") format ----------------------------------------------------------------
-// x ~= hi + lo / 2048 with hi = fp16_rn(x), lo = fp16_rn((x - hi) * 2048): 22 significand bits in two
-// fp16 tensor-core operands.  The low part is pre-scaled by 2^11 so that it stays in the fp16 normal
-// range (|x - hi| <= 2^-11 |x|); the tensor-core kernel accumulates the cross terms separately and
-// applies 2^-11 in the epilogue.  |x| is saturated at the fp16 maximum (65504).
+// x ~= hi + lo with hi = fp16_rn(x), lo = fp16_rn(x - hi): two fp16 tensor-core operands carrying ~22 significand bits.
+// The low part is stored UNSCALED (round 2; it was pre-scaled by 2^11 in round 1), so the three products hi*hi, hi*lo,
+// lo*hi of a K slice can accumulate into ONE fp32 accumulator (half the TMEM columns and tcgen05.ld traffic, 256-wide N
+// tiles double-buffered).  Price: for |x| < ~0.125 the low part is an fp16 subnormal, i.e. the representation error is
+// max(2^-22 |x|, 2^-25) absolute -- 3e-8, far below the 1e-3 contract for BatchNorm-scaled activations and Kaiming-scaled
+// weights (CPU emulation on the calibrated test model: per-layer relative error 1.9e-7..9.0e-7, tools/lo_scale_experiment.py;
+// measured on the B200 in tests/test_gpu_tc.py / test_gpu_forward.py).  |x| is saturated at the fp16 maximum (65504).
 typedef __half sh_t;
-constexpr float kLoScale = 2048.0f;
-constexpr float kLoInv = 1.0f / 2048.0f;
+constexpr float kLoScale = 1.0f;   // kept as named constants: the two-accumulator kernels (conv_tc.cu, conv_tc_fold.cu) form D1 + kLoInv * D2
+constexpr float kLoInv = 1.0f;
 
 __device__ __forceinline__ void split_s32(float x, sh_t& hi, sh_t& lo) {
   x = fminf(fmaxf(x, -65504.0f), 65504.0f);

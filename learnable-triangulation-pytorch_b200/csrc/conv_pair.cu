@@ -1,0 +1,384 @@
+// CTA-pair tensor-core implicit-GEMM convolution for sm_100a (tcgen05 cta_group::2).
+//
+// Why: the one-CTA-per-tile kernel (conv_tc.cu) moves 32 KB of operands per 128x128x32 chunk and is bound by the SM's TMA
+// ingest (~57 B/clk for 128-byte rows, ~44 B/clk for the 5-D activation boxes; tools/tma_probe.cu, profiles/r02_probes.md),
+// not by the tensor pipe.  Here two CTAs of a cluster (one TPC) compute a 256 x Nt tile together: each CTA loads its own
+// 128-position activation tile and HALF of the weight tile, one thread of the leader issues M = 256 MMAs that read both
+// halves, and each CTA's accumulator (its 128 rows x Nt fp32 columns) lives in its own TMEM.  At Nt = 256 a CTA ingests
+// 32 KB per 768 math cycles (42 B/clk) instead of 32 KB per 384.
+//
+// Precision: split-fp16 operands with UNSCALED low parts (common.cuh): the three products hi*hi, hi*lo, lo*hi of a 16-wide
+// K slice accumulate into ONE fp32 accumulator (Nt TMEM columns per stage; two stages so the epilogue of tile i overlaps
+// the main loop of tile i+1).  Weights: [tap][Cin/32][CoutP rows][32 hi | 32 lo] fp16 = 128-byte rows, 128B swizzle, so the
+// K slices of both operands are descriptor offsets (+0,+2 hi; +4,+6 lo, in 16-byte units) into MMA-ready rows.
+//
+// Persistent: grid = 2 x min(#SM / 2, tiles); pair k walks tiles k, k + P, ...  (tile = (pair of M tiles, N tile), N fastest
+// so that concurrently running pairs share the activation tile in L2).
+//
+// Warp roles per CTA (320 threads): warp 0 TMA producer (both CTAs), warp 1 TMEM allocator + MMA issuer (leader CTA only),
+// warps 2..9 epilogue (both CTAs, each draining its own TMEM lanes): tcgen05.ld -> scale/shift (+ residual tile that arrived
+// by TMA) -> ReLU -> split-fp16 repack into a swizzled smem tile -> TMA store (also implements the stride-phase mapping).
+//
+// Barriers (same smem offsets in both CTAs):
+//   full[s]       leader's copy is used: 1 arrival (leader producer's expect_tx of both CTAs' bytes) + complete_tx of all four
+//                 TMA loads (the non-leader's loads signal the leader's barrier through the .cta_group::2 form)
+//   empty[s]      per CTA; tcgen05.commit multicast from the leader frees the slot in both CTAs
+//   acc_full[a]   per CTA; commit multicast when a tile's last MMA has completed
+//   acc_empty[a]  leader's copy is used: 16 arrivals = 8 epilogue warps x 2 CTAs (remote mbarrier.arrive from the peer)
+#include "conv_tc_params.cuh"
+
+namespace lt {
+
+struct PairExtra {
+  int n_tiles;
+  long m_tiles, m_pairs, total_tiles;
+  int stage_bytes, off_out, off_res, off_bar;
+  int b_rows;   // weight rows per chunk = CoutP
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all previously issued MMAs have completed) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA loads whose completion is signalled on a barrier that may live in the peer (leader) CTA
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// kind::f16 instruction descriptor for the pair: D = f32, A = B = fp16, K-major, M = 256, N = n
+__device__ __forceinline__ uint32_t make_idesc_f16_m256(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+constexpr int kPairEpiWarps = 8;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcParams p,
+                 const PairExtra x) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_stage = smem + x.off_out;   // 2 x 16 KB
+  uint8_t* res_stage = smem + x.off_res;   // 2 x 16 KB
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + x.off_bar);
+  uint64_t* empty = full + p.stages;
+  uint64_t* acc_full = empty + p.stages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* res_full = acc_empty + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nchunks = p.KD * p.KH * p.KW * p.CB;
+  const int stage_bytes = x.stage_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kPairEpiWarps); mbar_init(&res_full[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
+  if (warp == 1) tmem_alloc2(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // both CTAs' barriers initialised and TMEM allocated before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // persistent schedule: pair k of P walks tiles k, k + P, ...; tile -> (M-tile pair, N tile), N fastest
+  const long pair_idx = (long)(blockIdx.x >> 1), n_pairs = (long)(gridDim.x >> 1);
+  auto decode = [&](long tile, int& ow0, int& oh0, int& od0, int& nb0, int& n0) {
+    n0 = (int)(tile % x.n_tiles) * p.Nt;
+    long t = (tile / x.n_tiles) * 2 + rank;      // this CTA's 128-position M tile; t >= m_tiles decodes to nb0 >= N (all OOB)
+    ow0 = (int)(t % p.tw) * p.bw; t /= p.tw;
+    oh0 = (int)(t % p.th) * p.bh; t /= p.th;
+    od0 = (int)(t % p.td) * p.bd; t /= p.td;
+    nb0 = (int)t * p.bn;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own activation tile + own half of the weight tile) =================
+    uint32_t rs = 0, rph = 0;
+    const uint32_t full0 = map_to_cta(smem_u32(&full[0]), 0);   // leader's full[] in cluster address space
+    const int b_half = p.Nt >> 1;
+    for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs) {
+      int ow0, oh0, od0, nb0, n0;
+      decode(tile, ow0, oh0, od0, nb0, n0);
+      const int ax = ow0 * p.sw - p.pw, ay = oh0 * p.sh - p.ph, az = od0 * p.sd - p.pd;
+      const int brow0 = n0 + (int)rank * b_half;
+      int cb = 0, kw = 0, kh = 0, kd = 0;
+      for (int q = 0; q < nchunks; ++q) {
+        mbar_wait(&empty[rs], rph ^ 1u);
+        uint8_t* a_dst = smem + (size_t)rs * stage_bytes;
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&full[rs], 2u * (uint32_t)stage_bytes);
+          const uint32_t bar = full0 + rs * 8u;
+          tma2_load_5d(a_dst, &tmA, bar, cb * 64, ax + kw, ay + kh, az + kd, nb0);
+          tma2_load_2d(a_dst + kATileBytes, &tmB, bar, 0, q * x.b_rows + brow0);
+        }
+        __syncwarp();
+        if (++cb == p.CB) { cb = 0; if (++kw == p.KW) { kw = 0; if (++kh == p.KH) { kh = 0; ++kd; } } }
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only; M = 256 spans both CTAs) =================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_f16_m256(p.Nt);
+      uint32_t rs = 0, rph = 0, it = 0;
+      const uint64_t ad0 = make_sw128_desc(smem_u32(smem));
+      const uint64_t bd0 = make_sw128_desc(smem_u32(smem) + kATileBytes);
+      const uint64_t sdelta = (uint64_t)(stage_bytes >> 4);
+      for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
+        const uint32_t as = it & 1u;
+        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + as * (uint32_t)p.Nt;
+        for (int q = 0; q < nchunks; ++q) {
+          mbar_wait(&full[rs], rph);
+          tc_fence_after();
+          const uint64_t ad = ad0 + sdelta * rs, bd = bd0 + sdelta * rs;
+          if (elect_one()) {
+            // rows = [32 hi | 32 lo] fp16: slices hi0 +0, hi1 +2, lo0 +4, lo1 +6 (16-byte units)
+            umma2_f16(d, ad, bd, idesc, q == 0 ? 0u : 1u);   // hi * hi
+            umma2_f16(d, ad + 2, bd + 2, idesc, 1u);
+            umma2_f16(d, ad, bd + 4, idesc, 1u);             // hi * lo
+            umma2_f16(d, ad + 2, bd + 6, idesc, 1u);
+            umma2_f16(d, ad + 4, bd, idesc, 1u);             // lo * hi
+            umma2_f16(d, ad + 6, bd + 2, idesc, 1u);
+            umma2_commit_mc(&empty[rs]);
+            if (q == nchunks - 1) umma2_commit_mc(&acc_full[as]);
+          }
+          __syncwarp();
+          if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..9 of both CTAs; each CTA drains its own 128 TMEM lanes) =================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const bool leader = threadIdx.x == 64;
+    const int nblk = p.Nt >> 5;
+    const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
+    const bool has_res = p.residual != LT_RES_NONE;
+    const uint32_t acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
+    const long my_tiles = (x.total_tiles > pair_idx) ? (x.total_tiles - 1 - pair_idx) / n_pairs + 1 : 0;
+    const long total_blocks = my_tiles * nblk;
+    auto issue_res = [&](long c) {   // leader thread only: residual block c of this CTA's tile sequence
+      const long tile_c = pair_idx + (c / nblk) * n_pairs;
+      const int blk = (int)(c % nblk);
+      int a0, a1, a2, a3, an;
+      decode(tile_c, a0, a1, a2, a3, an);
+      const int buf = (int)(c & 1);
+      mbar_expect_tx(&res_full[buf], 16384u);
+      tma_load_5d(res_stage + buf * 16384, &tmRes, &res_full[buf], an * esz + blk * 32 * esz, a0, a1, a2, a3);
+    };
+    if (leader && has_res)
+      for (long c = 0; c < 2 && c < total_blocks; ++c) issue_res(c);
+    uint32_t it = 0;
+    long c = 0;
+    for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
+      int ow0, oh0, od0, nb0, n0;
+      decode(tile, ow0, oh0, od0, nb0, n0);
+      const uint32_t as = it & 1u;
+      const int cbase = n0 * esz;
+      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.Nt;
+      for (int i = 0; i < nblk; ++i, ++c) {
+        const int buf = (int)(c & 1);
+        float v[16], r[16];
+        {
+          uint32_t t1[16];
+          tmem_ld16(tlane + (uint32_t)(i * 32 + half * 16), t1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
+        }
+        if (i == nblk - 1) {               // accumulator stage fully read by this warp: release it to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(acc_empty0 + as * 8u);
+        }
+        epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
+        if (has_res) {
+          mbar_wait(&res_full[buf], (uint32_t)((c >> 1) & 1));
+          epi_load16(smem_u32(res_stage + buf * 16384), row, half, p.out_format, r);
+        }
+        epi_activate16(v, r, p.residual, p.relu);
+        if (leader) bulk_wait_read<1>();      // the store that last read out_stage[buf] (two blocks ago) is done with it
+        epi_bar_sync();                       // also: every thread has finished reading res_stage[buf]
+        epi_store16(smem_u32(out_stage + buf * 16384), row, half, p.out_format, v);
+        fence_proxy_async();
+        epi_bar_sync();
+        if (leader) {
+          tma_store_5d(&tmOut, out_stage + buf * 16384, cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+          bulk_commit();
+          if (has_res && c + 2 < total_blocks) issue_res(c + 2);
+        }
+      }
+    }
+    if (leader) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer may still read this CTA's operand half / signal its barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* plan) {
+  if (!p.tma_epi || p.terms != 3 || CoutP % 128 != 0) return false;
+  const long m_tiles = (long)p.tw * p.th * p.td * p.tn;
+  const long m_pairs = (m_tiles + 1) / 2;
+  const int nchunks = p.KD * p.KH * p.KW * p.CB;
+  const int P = sm_count() / 2;
+  // pick the N tile that minimises (waves) x (cycles per chunk): math 3*Nt, TMA ingest ~ (16 KB + Nt*64 B) / 50 B/clk,
+  // issue ~ 450 cycles per chunk
+  double best = 1e300;
+  int best_nt = 0;
+  for (int nt = 256; nt >= 128; nt >>= 1) {
+    if (CoutP % nt) continue;
+    const long tiles = m_pairs * (CoutP / nt);
+    const double waves = (double)((tiles + P - 1) / P);
+    const double per_chunk = fmax(fmax(3.0 * nt, (16384.0 + nt * 64.0) / 50.0), 450.0);
+    const double epi = 250.0 * (nt / 32);     // exposed only when the main loop is shorter
+    const double t = waves * fmax(per_chunk * nchunks, epi) + epi;
+    if (t < best) { best = t; best_nt = nt; }
+  }
+  if (!best_nt) return false;
+  // tiny grids (deep V2V levels): the split-K path of the one-CTA kernel spreads the K loop over the SMs instead
+  if (m_pairs * (CoutP / best_nt) * 4 < P && nchunks >= 16) return false;
+  (void)d;
+  plan->Nt = best_nt;
+  plan->n_tiles = CoutP / best_nt;
+  plan->m_tiles = m_tiles;
+  plan->m_pairs = m_pairs;
+  const int stage_bytes = kATileBytes + best_nt * 64;
+  int stages = (227 * 1024 - 1024 - 65536 - 512) / stage_bytes;
+  if (stages > 8) stages = 8;
+  plan->stages = stages;
+  const long tiles = m_pairs * plan->n_tiles;
+  plan->grid = 2u * (unsigned)(tiles < P ? tiles : P);
+  return true;
+}
+
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes, TcParams& p,
+                const PairPlan& plan, int CoutP, cudaStream_t st) {
+  PairExtra x;
+  p.Nt = plan.Nt;
+  p.stages = plan.stages;
+  p.splits = 1; p.ws = nullptr; p.ws_ld = 0;
+  x.n_tiles = plan.n_tiles;
+  x.m_tiles = plan.m_tiles;
+  x.m_pairs = plan.m_pairs;
+  x.total_tiles = plan.m_pairs * plan.n_tiles;
+  x.stage_bytes = kATileBytes + plan.Nt * 64;
+  x.b_rows = CoutP;
+  const int ring = plan.stages * x.stage_bytes;
+  x.off_out = (ring + 1023) & ~1023;
+  x.off_res = x.off_out + 32768;
+  x.off_bar = x.off_res + 32768;
+  const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 6) * 8 + 16 + 1024;
+  if (smem > 227 * 1024) return fail(LT_ERR_INVALID, "conv_pair: shared memory budget exceeded (%zu)", smem);
+  static thread_local int conf_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (conf_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    conf_dev = dev;
+  }
+  conv_pair_kernel<<<plan.grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_pair_kernel: %s", cudaGetErrorString(e));
+  return LT_OK;
+}
+
+// ---- weight packing: fp32 [taps][Cin][Cout] -> fp16 [taps][Cin/32][CoutP][32 hi | 32 lo] (128-byte rows) ----------
+__global__ void __launch_bounds__(256) pack_weights_pair_kernel(const float* __restrict__ w, sh_t* __restrict__ out,
+                                                                int taps, int Cin, int Cout, int CoutP) {
+  const int CB = Cin / 32;
+  const long total = (long)taps * CB * CoutP * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % 32);
+    long r = i / 32;
+    const int n = (int)(r % CoutP); r /= CoutP;
+    const int cb = (int)(r % CB);
+    const int tap = (int)(r / CB);
+    const float v = (n < Cout) ? w[((long)tap * Cin + cb * 32 + j) * Cout + n] : 0.0f;
+    sh_t hi, lo;
+    split_s32(v, hi, lo);
+    sh_t* rowp = out + ((((long)tap * CB + cb) * CoutP + n) << 6);
+    rowp[j] = hi;
+    rowp[32 + j] = lo;
+  }
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" size_t lt_conv_pair_weight_bytes(int taps, int Cin, int Cout) {
+  const int CoutP = (Cout + 127) & ~127;
+  return (size_t)taps * (Cin / 32) * CoutP * 128;
+}
+
+extern "C" int lt_conv_pair_pack_weights(const float* w, void* packed, int taps, int Cin, int Cout, void* stream) {
+  LT_REQUIRE(w && packed, "conv_pair_pack_weights: null pointer");
+  LT_REQUIRE(Cin % 32 == 0 && taps > 0 && Cout > 0, "conv_pair_pack_weights: bad sizes");
+  const int CoutP = (Cout + 127) & ~127;
+  const long total = (long)taps * (Cin / 32) * CoutP * 32;
+  long blocks = (total + 255) / 256;
+  if (blocks > 65535) blocks = 65535;
+  pack_weights_pair_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<sh_t*>(packed), taps, Cin, Cout, CoutP);
+  LT_CHECK_LAUNCH("pack_weights_pair_kernel");
+  return LT_OK;
+}

@@ -16,6 +16,7 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-9 = epilogue (two warps per TMEM lane quadrant, each converting 16 of a block's 32 channels).
 #include "tc_common.cuh"
+#include "conv_tc_params.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -24,32 +25,6 @@ namespace lt {
 // ------------------------------------------------------------------------------------------------
 // Kernel
 // ------------------------------------------------------------------------------------------------
-struct TcParams {
-  int OW, OH, OD, N;       // output grid computed by this launch
-  int bw, bh, bd, bn;      // M-tile box, product 128
-  int tw, th, td, tn;      // tiles per dim
-  int KW, KH, KD, pw, ph, pd;
-  int sw, sh, sd;          // input stride (TMA element strides)
-  int CB;                  // 64-element K chunks per tap
-  int b_step0, b_step1;    // B-map coordinates of chunk q: (q*b_step0, q*b_step1 + n0*b_nmul)
-  int b_nmul;
-  int Nt, stages, terms;   // N tile, pipeline depth, 1 or 3 product terms
-  int tmem_cols;
-  int tma_epi;             // 1: epilogue stages 32-channel blocks through smem and uses TMA store / residual load
-  // epilogue
-  int FC, FD, FH, FW, osd, osh, osw, ood, ooh, oow, relu, residual, out_format;
-  const float* scale;
-  const float* shift;
-  const void* res;
-  void* out;
-  // split-K (latency-bound layers with fewer CTAs than SMs): blockIdx.z owns a contiguous range of the K chunks and
-  // writes its raw fp32 accumulator tile to ws[z][m tile][128][ws_ld]; splitk_reduce_kernel sums and applies the epilogue
-  int splits, ws_ld;
-  float* ws;
-  int bres;   // host-side request: B-resident persistent variant (Nt = 64 sub-tiles of the 128-wide packed weight tiles)
-};
-
-constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
 
 __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
@@ -706,6 +681,83 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "splitk_reduce_kernel: %s", cudaGetErrorString(e));
   }
   return LT_OK;
+}
+
+// fills the geometry / epilogue part of the launch parameters (M-tile box, taps, output mapping)
+static void fill_params(const lt_conv_desc* d, TcParams& p, int CB, int CoutP, int Nt, int terms, const float* scale, const float* shift,
+                        const void* residual, void* out) {
+  p.bres = 0;
+  p.OW = d->OW; p.OH = d->OH; p.OD = d->OD; p.N = d->N;
+  int box[4];
+  pick_box(d->OW, d->OH, d->OD, d->N, box);
+  p.bw = box[0]; p.bh = box[1]; p.bd = box[2]; p.bn = box[3];
+  p.tw = ceil_div(d->OW, p.bw); p.th = ceil_div(d->OH, p.bh); p.td = ceil_div(d->OD, p.bd); p.tn = ceil_div(d->N, p.bn);
+  p.KW = d->KW; p.KH = d->KH; p.KD = d->KD; p.pw = d->pw; p.ph = d->ph; p.pd = d->pd;
+  p.sw = d->sw; p.sh = d->sh; p.sd = d->sd;
+  p.CB = CB; p.b_step0 = 0; p.b_step1 = 2 * CoutP; p.b_nmul = 2; p.Nt = Nt; p.terms = terms;
+  p.FC = d->FC; p.FD = d->FD; p.FH = d->FH; p.FW = d->FW;
+  p.osd = d->osd; p.osh = d->osh; p.osw = d->osw; p.ood = d->ood; p.ooh = d->ooh; p.oow = d->oow;
+  p.relu = d->relu; p.residual = d->residual; p.out_format = d->out_format;
+  p.scale = scale; p.shift = shift; p.res = residual; p.out = out;
+  p.splits = 1; p.ws = nullptr; p.ws_ld = 0; p.stages = 0; p.tmem_cols = 0; p.tma_epi = 0;
+}
+
+static int make_in_map(CUtensorMap* tmA, const lt_conv_desc* d, const TcParams& p, const void* in) {
+  const uint64_t rowb = (uint64_t)d->Cin * 2 * 2;  // 2*Cin fp16 per position
+  const uint64_t dims[5] = {(uint64_t)d->Cin * 2, (uint64_t)d->IW, (uint64_t)d->IH, (uint64_t)d->ID, (uint64_t)d->N};
+  const uint64_t str[4] = {rowb, rowb * d->IW, rowb * d->IW * d->IH, rowb * d->IW * d->IH * d->ID};
+  // strided convs: TMA traversal strides; the box spans (b-1)*s+1 input positions and delivers b of them
+  const uint32_t es[5] = {1, (uint32_t)d->sw, (uint32_t)d->sh, (uint32_t)d->sd, 1};
+  uint32_t bx[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  for (int i = 1; i <= 3; ++i) bx[i] = (bx[i] - 1) * es[i] + 1;
+  LT_REQUIRE(bx[1] <= 256 && bx[2] <= 256 && bx[3] <= 256, "conv_tc: strided box exceeds 256");
+  return make_map(tmA, in, 5, dims, str, bx, es, 1);
+}
+
+static bool staged_epilogue_ok(const lt_conv_desc* d, int CoutP, int Nt) {
+  // float32 outputs may be narrower than the (single) padded N tile: the tensor map then has FC channels and the TMA
+  // store clips the box at the tensor bound (80-byte voxel rows for the 17-joint logits instead of 128)
+  const bool clipped_f32 = d->out_format == LT_FMT_F32 && d->residual == LT_RES_NONE && CoutP == Nt && d->FC % 4 == 0 && d->FC < CoutP;
+  return Nt % 32 == 0 && ((d->FC % 32 == 0 && CoutP <= d->FC) || clipped_f32);
+}
+
+// CTA-pair kernel (conv_pair.cu): weights packed by lt_conv_pair_pack_weights
+int conv_pair_fwd(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,
+                  const void* residual, void* out, void* stream, int probe_only) {
+  LT_REQUIRE(d->in_format == LT_FMT_S32, "conv_pair: input must be split-fp16");
+  LT_REQUIRE(d->Cin % 32 == 0, "conv_pair: Cin=%d must be a multiple of 32", d->Cin);
+  const int CoutP = (d->Cout + 127) & ~127;
+  const int CB = d->Cin / 32;
+  const int taps = d->KD * d->KH * d->KW;
+  TcParams p;
+  fill_params(d, p, CB, CoutP, 128, 3, scale, shift, residual, out);
+  p.tma_epi = (d->Cout % 128 == 0 && staged_epilogue_ok(d, CoutP, 128)) ? 1 : 0;
+  PairPlan plan;
+  if (!pair_plan(d, p, CoutP, &plan)) {
+    if (probe_only) return 1;
+    return fail(LT_ERR_INVALID, "conv_pair: shape not covered by the CTA-pair kernel (Cout=%d FC=%d)", d->Cout, d->FC);
+  }
+  if (probe_only) return 0;
+  p.Nt = plan.Nt;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  int rc = make_in_map(&tmA, d, p, in);
+  if (rc) return rc;
+  {
+    // weights: [tap][cb][CoutP rows][32 hi | 32 lo] fp16, 128-byte rows, 128B swizzle; each CTA of a pair loads Nt/2 rows
+    const uint64_t dims[2] = {64, (uint64_t)taps * CB * CoutP};
+    const uint64_t str[1] = {128};
+    const uint32_t bx[2] = {64, (uint32_t)(plan.Nt / 2)};
+    rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
+    if (rc) return rc;
+  }
+  rc = make_out_map(&tmOut, out, d, p);
+  if (rc) return rc;
+  tmRes = tmOut;
+  if (d->residual != LT_RES_NONE) {
+    rc = make_out_map(&tmRes, residual, d, p);
+    if (rc) return rc;
+  }
+  return launch_pair(tmA, tmB, tmOut, tmRes, p, plan, CoutP, (cudaStream_t)stream);
 }
 
 int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight, const float* scale, const float* shift,

@@ -195,6 +195,39 @@ static inline unsigned grid_for(long total, int per_block = 256) {
   return (unsigned)b;
 }
 
+// ---- multi-GPU feature exchange: this rank's feature maps -> the owner ranks' buffers (peer memory over NVLink) ----------
+// src [B][Vl][row] (row = h*w*C floats); sample b belongs to rank b / per; dst buffer of owner o: [per][V][row], this rank's local
+// view j is global view view_rank + j*G.  One CTA column per (sample, local view); float4 stores straight into peer memory.
+struct PeerPtrs { float* p[8]; };
+__global__ void __launch_bounds__(256) feature_scatter_kernel(const float* __restrict__ src, PeerPtrs peers, int Vl, int V, int G,
+                                                              int view_rank, int per, long row4) {
+  const int bv = blockIdx.y;
+  const int b = bv / Vl, j = bv - b * Vl;
+  const int owner = b / per, bl = b - owner * per, v = view_rank + j * G;
+  const float4* s4 = reinterpret_cast<const float4*>(src) + (long)bv * row4;
+  float4* d4 = reinterpret_cast<float4*>(peers.p[owner]) + ((long)bl * V + v) * row4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < row4; i += (long)gridDim.x * blockDim.x) d4[i] = s4[i];
+}
+
+}  // namespace lt
+
+extern "C" int lt_feature_scatter_fwd(const float* feats, float* const* peer_buffers, int n_peers, int view_rank, int B, int V_local,
+                                      int V, long row_elems, void* stream) {
+  using namespace lt;
+  LT_REQUIRE(feats && peer_buffers && n_peers >= 1 && n_peers <= 8, "feature_scatter: need 1..8 peer buffers");
+  LT_REQUIRE(B % n_peers == 0 && row_elems % 4 == 0 && V_local * n_peers == V, "feature_scatter: bad sizes (B=%d G=%d Vl=%d V=%d)", B, n_peers, V_local, V);
+  PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < n_peers ? peer_buffers[i] : nullptr;
+  const long row4 = row_elems / 4;
+  int gx = (int)((row4 + 255) / 256);
+  if (gx > 64) gx = 64;
+  dim3 grid((unsigned)gx, (unsigned)(B * V_local));
+  feature_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feats, pp, V_local, V, n_peers, view_rank, B / n_peers, row4);
+  LT_CHECK_LAUNCH("feature_scatter_kernel");
+  return LT_OK;
+}
+
+namespace lt {
 }  // namespace lt
 
 using namespace lt;

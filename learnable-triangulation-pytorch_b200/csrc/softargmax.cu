@@ -39,7 +39,8 @@ __device__ __forceinline__ void st_push(SoftState& s, float l, float x, float y,
     s.sz = fmaf(s.sz, r, e * z);
     s.m = mn;
   } else {
-    const float e = fmaxf(l, 0.0f);     // op.py:90-91: ReLU, no normalisation
+    const float e = fmaxf(l, 0.0f);     // op.py:90-91: ReLU, no normalisation (d = mass, only used by mode 2, op.py:25-41)
+    s.d += e;
     s.sx = fmaf(e, x, s.sx);
     s.sy = fmaf(e, y, s.sy);
     s.sz = fmaf(e, z, s.sz);
@@ -56,7 +57,7 @@ __device__ __forceinline__ void st_merge(SoftState& a, const SoftState& b, bool 
     a.sz = a.sz * ra + b.sz * rb;
     a.m = mn;
   } else {
-    a.sx += b.sx; a.sy += b.sy; a.sz += b.sz;
+    a.d += b.d; a.sx += b.sx; a.sy += b.sy; a.sz += b.sz;
   }
 }
 __device__ __forceinline__ SoftState st_shfl_xor(const SoftState& s, int o) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) softargmax_partial_cl(const SoftParams p)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long v0 = (long)chunk * kChunk;
   const long v1 = min(v0 + kChunk, p.nvox);
-  const bool sm = p.softmax != 0;
+  const bool sm = p.softmax == 1;
   const bool active = lane < p.J;
   const float* lg = p.logits + (long)b * p.bs + lane;
   const float* cd = p.coord + (long)b * p.nvox * 3;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) softargmax_partial_generic(const SoftPara
   const int chunk = blockIdx.x, j = blockIdx.y, b = blockIdx.z;
   const long v0 = (long)chunk * kChunk;
   const long v1 = min(v0 + kChunk, p.nvox);
-  const bool sm = p.softmax != 0;
+  const bool sm = p.softmax == 1;
   const float* lg = p.logits + (long)b * p.bs + (long)j * p.cs;
   const float* cd = p.coord + (long)b * p.nvox * 3;
   SoftState s;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(128) softargmax_finalize(const SoftParams p) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= p.B * p.J) return;
-  const bool sm = p.softmax != 0;
+  const bool sm = p.softmax == 1;
   SoftState s;
   st_init(s, sm);
   const float* src = p.partial + (long)gw * p.nch * 5;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(128) softargmax_finalize(const SoftParams p) {
   for (int o = 16; o > 0; o >>= 1) { const SoftState t = st_shfl_xor(s, o); st_merge(s, t, sm); }
   if (lane == 0) {
     float* k = p.keypoints + (long)gw * 3;
-    if (sm) { k[0] = s.sx / s.d; k[1] = s.sy / s.d; k[2] = s.sz / s.d; }
+    if (sm || p.softmax == 2) { k[0] = s.sx / s.d; k[1] = s.sy / s.d; k[2] = s.sz / s.d; }   // mode 2: ReLU mass-normalised
     else { k[0] = s.sx; k[1] = s.sy; k[2] = s.sz; }
     p.stats[gw * 2] = s.m;
     p.stats[gw * 2 + 1] = s.d;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256) softargmax_normalize_cl(const SoftParams 
   __shared__ float tile[8][32][33];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool sm = p.softmax != 0;
+  const bool sm = p.softmax == 1;
   const float* st = p.stats + (long)b * p.J * 2;
   for (long v0 = ((long)blockIdx.x * 8 + warp) * 32; v0 < p.nvox; v0 += (long)gridDim.x * 256) {
     const float* lg = p.logits + (long)b * p.bs + lane;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) softargmax_normalize_cl(const SoftParams 
 
 __global__ void __launch_bounds__(256) softargmax_normalize_generic(const SoftParams p) {
   const int j = blockIdx.y, b = blockIdx.z;
-  const bool sm = p.softmax != 0;
+  const bool sm = p.softmax == 1;
   const float mx = p.stats[((long)b * p.J + j) * 2], dn = p.stats[((long)b * p.J + j) * 2 + 1];
   const float* lg = p.logits + (long)b * p.bs + (long)j * p.cs;
   float* o = p.volumes + ((long)b * p.J + j) * p.nvox;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(128) softargmax_stream_merge(const StreamParam
   const int lane = threadIdx.x & 31;
   if (gw >= p.B * p.J) return;
   const int b = gw / p.J, j = gw % p.J;
-  const bool sm = p.softmax != 0;
+  const bool sm = p.softmax == 1;
   SoftState a;
   st_init(a, sm);
   for (int gg = lane; gg < p.G; gg += 32) {
@@ -523,9 +524,10 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
   p.B = B; p.J = J; p.nvox = nvox; p.mult = multiplier; p.softmax = softmax;
   cudaStream_t st = (cudaStream_t)stream;
   const bool cl = (chan_stride == 1 && J <= 32 && voxel_stride >= J);
+  LT_REQUIRE(softmax >= 0 && softmax <= 2, "softargmax3d: mode must be 0 (ReLU), 1 (softmax) or 2 (ReLU, mass-normalised coordinates)");
   // ---- streaming path ----
   static const int stream_mode = getenv("LT_SOFTARGMAX_FUSED") ? atoi(getenv("LT_SOFTARGMAX_FUSED")) : 1;
-  if (stream_mode && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 8 == 0 && batch_stride % 4 == 0 &&
+  if (stream_mode && softmax != 2 && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 8 == 0 && batch_stride % 4 == 0 &&
       nvox >= kStreamMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0 &&
       (!volumes_out || ((uintptr_t)volumes_out & 31) == 0)) {
     StreamParams f;

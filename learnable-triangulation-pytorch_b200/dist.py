@@ -116,13 +116,14 @@ class FeatureExchange:
         self.shape = (self.per, n_views, h, w, channels)
         self.buf = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
-        self.peers = [self.handle.get_buffer(r, self.shape, torch.float32) for r in range(plan.group_size)]
-        self.view_index = torch.tensor(plan.views, device=device)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.n_views = n_views
 
     def scatter(self, feats_local):
-        """feats_local: (B, V_local, h, w, C) -> rows of the owners' buffers (peer stores)."""
-        for owner, dst in enumerate(self.peers):
-            dst.index_copy_(1, self.view_index, feats_local[owner * self.per:(owner + 1) * self.per])
+        """feats_local: (B, V_local, h, w, C) -> rows of the owners' buffers: one launch of our own copy kernel whose float4
+        stores go straight into peer memory over NVLink (lt_feature_scatter_fwd)."""
+        from . import capi
+        capi.feature_scatter(feats_local, self.peer_ptrs, self.plan.view_rank, self.n_views)
 
     def barrier(self):
         self.handle.barrier()

@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import capi
-from .capi import FMT_F32, FMT_S32, CONV_SIMT, CONV_TC, CONV_TC1, CONV_TC_FOLD, RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU
+from .capi import FMT_F32, FMT_S32, CONV_SIMT, CONV_TC, CONV_TC1, CONV_TC_FOLD, CONV_TC_PAIR, RES_NONE, RES_BEFORE_RELU, RES_AFTER_RELU
 
 
 def _round_up(v, m):
@@ -47,7 +47,7 @@ class Act:
 
 class ConvPack:
     """One (phase of a) convolution, ready to launch: packed filter + folded scale/shift + geometry."""
-    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs", "w_fold")
+    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs", "w_fold", "w_pair")
 
 
 def _fold_bn(conv_bias, bn, cout, device):
@@ -98,6 +98,7 @@ class NativeEngine:
         self._graphs = {}
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
         self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
+        self.use_pair = os.environ.get("LT_TC_PAIR", "1") == "1"          # CTA-pair kernel for Cout % 128 == 0 layers
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
@@ -127,6 +128,7 @@ class NativeEngine:
         pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
         pk.kmacs = taps * cin * cout   # algorithmic MACs per output position
         pk.w_fold = None
+        pk.w_pair = None
         use_tc = (self.mode != "simt") and not force_simt and (max(stride) == 1 or self.tc_strided)
         scale, shift = _fold_bn(bias, bn, cout, dev)
         if use_tc:
@@ -137,6 +139,11 @@ class NativeEngine:
             packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
             capi.conv_tc_pack_weights(wp.contiguous(), packed, taps, cin_p, cout_p)
             pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = packed, cin_p, cout_p, self.tc_impl, FMT_S32
+            # wide layers: also pack for the CTA-pair kernel (cta_group::2, 256 x {128,256} tiles; csrc/conv_pair.cu)
+            if self.use_pair and self.mode == "tc" and cout_p % 128 == 0:
+                wq = torch.empty(capi.conv_pair_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
+                capi.conv_pair_pack_weights(wp.contiguous(), wq, taps, cin_p, cout_p)
+                pk.w_pair = wq
             # narrow cubic stride-1 layers (V2V at full resolution): also pack for the kw-folded persistent kernel
             if (self.use_fold and self.mode == "tc" and cin_p == 32 and cout <= 32 and k[0] == k[1] == k[2] and k[0] in (3, 7)
                     and tuple(pad) == (k[0] // 2,) * 3 and max(stride) == 1):
@@ -330,7 +337,9 @@ class NativeEngine:
         if (pk.w_fold is not None and x.W >= 16 and out.C == 32 and out_scale == (1, 1, 1) and (od, oh, ow) == (x.D, x.H, x.W)):
             impl, weight = CONV_TC_FOLD, pk.w_fold
             d.Cout = pk.cout
-        label = "conv_fold" if impl == CONV_TC_FOLD else ("conv_tc" if impl != CONV_SIMT else "conv_ffma")
+        elif pk.w_pair is not None and capi.conv_pair_eligible(d):
+            impl, weight = CONV_TC_PAIR, pk.w_pair
+        label = {CONV_TC_FOLD: "conv_fold", CONV_TC_PAIR: "conv_pair", CONV_SIMT: "conv_ffma"}.get(impl, "conv_tc")
         with self._timed(label, flops=2.0 * x.N * od * oh * ow * pk.kmacs,
                          desc="N%d %dx%dx%d Cin%d Cout%d k%d%d%d s%d" % (x.N, od, oh, ow, pk.cin, pk.cout, kd, kh, kw, sw)):
             capi.conv_nd(d, x.data, weight, pk.scale, pk.shift, None if residual is None else residual.data, out.data, impl)
@@ -684,7 +693,7 @@ class NativeEngine:
         return kp_all, features, volumes, coord
 
     # ------------------------------------------------------------------ algebraic model (config #5)
-    def algebraic_forward(self, images, proj, heatmap_multiplier, use_confidences):
+    def algebraic_forward(self, images, proj, heatmap_multiplier, use_confidences, heatmap_softmax=True):
         """AlgebraicTriangulationNet.forward (triangulation.py:149-200), device side.
 
         images (B, V, 3, H, W), proj (B, V, 3, 4) image-space projection matrices.
@@ -709,7 +718,8 @@ class NativeEngine:
         heat = torch.empty((B * V, J, h, w), dtype=torch.float32, device=dev)
         kp = torch.empty((B * V, J, 3), dtype=torch.float32, device=dev)
         ws = torch.empty(capi.softargmax3d_workspace_bytes(B * V, J, h * w) // 4 + 1, dtype=torch.float32, device=dev)
-        capi.softargmax3d(logits.data, h * w * logits.C, logits.C, 1, self._grid2d, heat, kp, ws, B * V, J, h * w, heatmap_multiplier, True)
+        capi.softargmax3d(logits.data, h * w * logits.C, logits.C, 1, self._grid2d, heat, kp, ws, B * V, J, h * w, heatmap_multiplier,
+                          1 if heatmap_softmax else 2)    # op.py:25-41: ReLU heat-maps, centre of mass / mass
         self.launches += 3
         kp2d = kp[:, :, :2].reshape(B, V, J, 2) * torch.tensor([W / w, H / h], device=dev, dtype=torch.float32)   # :181-184
         kp2d = kp2d.contiguous()

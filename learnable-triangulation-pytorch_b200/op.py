@@ -78,7 +78,7 @@ def integrate_tensor_3d_with_coordinates(volumes, coord_volumes, softmax=True, b
 
 def integrate_tensor_2d(heatmaps, softmax=True, backend=None):
     """Drop-in for reference op.py:11-47: (B, J, h, w) -> coordinates (B, J, 2) [x, y in pixels], normalised heatmaps."""
-    if _resolve_backend(backend, heatmaps) in ("torch", "hybrid") or not softmax:
+    if _resolve_backend(backend, heatmaps) in ("torch", "hybrid"):
         return torch_ops.integrate_tensor_2d(heatmaps, softmax)
     B, J, h, w = heatmaps.shape
     dev = heatmaps.device
@@ -88,5 +88,6 @@ def integrate_tensor_2d(heatmaps, softmax=True, backend=None):
     out = torch.empty_like(logits)
     kp = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
     ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, h * w) // 4 + 1, dtype=torch.float32, device=dev)
-    capi.softargmax3d(logits, J * h * w, 1, h * w, grid, out, kp, ws, B, J, h * w, 1.0, True)
+    # softmax=False: ReLU heat-maps, centre of mass divided by the mass (op.py:25-41) = mode 2 of lt_softargmax3d_fwd
+    capi.softargmax3d(logits, J * h * w, 1, h * w, grid, out, kp, ws, B, J, h * w, 1.0, 1 if softmax else 2)
     return kp[:, :, :2].contiguous(), out

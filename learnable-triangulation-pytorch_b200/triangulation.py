@@ -227,10 +227,9 @@ class AlgebraicTriangulationNet(_EngineOwner):
             raise RuntimeError("lt_b200 native backend needs CUDA tensors; construct the model with backend='torch' for CPU/autograd")
         if self.training or torch.is_grad_enabled():
             raise RuntimeError("lt_b200 native backend is inference-only: use model.eval() under torch.no_grad(), or backend='torch'")
-        if not self.heatmap_softmax:
-            raise NotImplementedError("heatmap_softmax=False (ReLU mass normalisation) is only available with backend='torch'")
-        return self.engine().algebraic_forward(images.float().contiguous(), proj_matricies.float().contiguous(),
-                                               self.heatmap_multiplier, self.use_confidences)
+        with torch.cuda.device(images.device):
+            return self.engine().algebraic_forward(images.float().contiguous(), proj_matricies.float().contiguous(),
+                                                   self.heatmap_multiplier, self.use_confidences, self.heatmap_softmax)
 
     def _forward_torch(self, images, proj_matricies):
         B, V = images.shape[:2]

@@ -18,7 +18,11 @@ class Recorder:
                 self.calls.append((name, a))
             return f
         monkeypatch.setattr(capi, "conv_fold_weight_bytes", lambda k, co: k * k * k * ((co + 15) // 16 * 16) * 64 * 2)
-        for name in ("conv_fold_pack_weights", "stem_s2d", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
+        monkeypatch.setattr(capi, "conv_pair_weight_bytes", lambda t, ci, co: t * (ci // 32) * ((co + 127) // 128 * 128) * 128)
+        # same shape rule as csrc/conv_pair.cu pair_plan (without its wave-count heuristics): staged epilogue + Cout % 128 == 0
+        monkeypatch.setattr(capi, "conv_pair_eligible", lambda d: d.Cout % 128 == 0 and d.FC % 32 == 0 and d.Cout <= d.FC and
+                            d.N * d.OD * d.OH * d.OW >= 128 * 40)
+        for name in ("conv_pair_pack_weights", "conv_fold_pack_weights", "stem_s2d", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
                      "s32_to_f32", "cl_to_cf", "conv_tc_pack_weights"):
             monkeypatch.setattr(capi, name, rec(name))
         monkeypatch.setattr(capi, "lib", lambda: None)
@@ -39,6 +43,10 @@ class Recorder:
         if impl == capi.CONV_TC_FOLD:
             assert d.Cin == 32 and d.FC == 32 and d.Cout <= 32 and d.IW >= 16 and d.KD == d.KH == d.KW and d.KW in (3, 7)
             assert w.numel() == d.KW ** 3 * ((d.Cout + 15) // 16 * 16) * 64
+        elif impl == capi.CONV_TC_PAIR:
+            assert d.in_format == capi.FMT_S32 and x.dtype == torch.float16 and d.Cin % 32 == 0 and d.Cout % 128 == 0
+            assert w.numel() == d.KD * d.KH * d.KW * (d.Cin // 32) * d.Cout * 64 and scale.numel() >= d.Cout
+            assert d.FC % 32 == 0 and d.Cout >= d.FC
         elif impl == capi.CONV_SIMT:
             assert d.in_format == capi.FMT_F32 and x.dtype == torch.float32
             cw = (d.Cout + 3) // 4 * 4
@@ -77,7 +85,7 @@ def test_engine_plan_is_consistent(monkeypatch, mode, layers):
     # V2V: front0 + 20 res blocks (2 convs each) + 4 skip convs (16->32, 32->64, 64->128 enc, none else) ...
     v2v = len(convs) - backbone
     assert v2v == 1 + 20 * 2 + 3 + 5 * 8 + 2 + 1, v2v
-    assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights")) + 2   # softargmax = 3 launches
+    assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights", "conv_pair_pack_weights")) + 2   # softargmax = 3 launches
     if mode == "tc":
         simt = [c for c in convs if c[1][0] == capi.CONV_SIMT]
         assert len(simt) == 0, "every conv runs on the tensor-core kernels"

@@ -222,6 +222,77 @@ def test_conv_fold_vs_torch(case, with_res):
         assert float(full[:, cout:].abs().max()) == 0.0
 
 
+PAIR_CASES = [
+    # (dims, cin, cout, k, stride, pad, spatial, batch, res_mode)  -- layers with Cout % 128 == 0 (csrc/conv_pair.cu)
+    (2, 256, 1024, 1, 1, 0, (24, 24), 9, "before"),     # 1x1 expand of a bottleneck: Nt = 256, 4 N tiles, odd M-tile count (41)
+    (2, 1024, 256, 1, 1, 0, (24, 24), 8, "none"),       # 1x1 reduce: 32 K chunks, one N tile
+    (2, 256, 256, 3, 1, 1, (24, 24), 8, "none"),        # 3x3: padding through TMA zero fill in both CTAs of a pair
+    (2, 128, 128, 3, 1, 1, (48, 48), 3, "none"),        # Nt = 128
+    (2, 128, 512, 1, 1, 0, (48, 48), 3, "before"),
+    (2, 64, 256, 1, 1, 0, (96, 96), 2, "before"),       # 2 K chunks per tile: epilogue-bound, many tiles per pair
+    (2, 256, 512, 1, 2, 0, (48, 48), 4, "none"),        # stride-2 downsample through TMA traversal strides
+    (2, 128, 128, 3, 2, 1, (48, 48), 16, "none"),
+    (2, 512, 2048, 1, 1, 0, (12, 12), 6, "before"),
+    (3, 128, 128, 3, 1, 1, (16, 16, 16), 2, "before"),  # V2V 16^3 level
+    (3, 64, 128, 3, 1, 1, (16, 16, 16), 4, "after"),
+    (2, 96, 384, 1, 1, 0, (40, 24), 5, "before"),       # CoutP = 384 = 3 x 128
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_pair_vs_torch(case):
+    """CTA-pair kernel (cta_group::2, M = 256 per pair, single accumulator) against the fp32 torch op."""
+    dims, cin, cout, k, stride, pad, spatial, N, res_mode = case
+    torch.manual_seed(cin + cout + k + N)
+    conv = (torch.nn.Conv2d if dims == 2 else torch.nn.Conv3d)(cin, cout, k, stride, pad, bias=(dims == 3)).eval()
+    bn = _bn_for(conv, 17)
+    x = torch.randn(N, cin, *spatial)
+    mode = {"none": capi.RES_NONE, "before": capi.RES_BEFORE_RELU, "after": capi.RES_AFTER_RELU}[res_mode]
+    with torch.no_grad():
+        y0 = bn(conv(x))
+        res = torch.randn_like(y0)
+        want = {"none": F.relu(y0), "before": F.relu(y0 + res), "after": F.relu(y0) + res}[res_mode]
+    e = _engine("tc")
+    pk = e._pack_conv(conv.to(DEV), bn.to(DEV))
+    assert pk.w_pair is not None
+    ra = act_from_nchw(res, capi.FMT_S32) if res_mode != "none" else None
+    launched = []
+    orig = capi.conv_nd
+    capi.conv_nd = lambda d, *a: (launched.append(a[-1]), orig(d, *a))[1]
+    try:
+        ya = e._conv(act_from_nchw(x, capi.FMT_S32), pk, relu=True, residual=ra, res_mode=mode)
+    finally:
+        capi.conv_nd = orig
+    torch.cuda.synchronize()
+    assert launched == [capi.CONV_TC_PAIR], "the CTA-pair kernel must have been selected"
+    got = act_to_nchw(ya, cout).cpu()
+    if dims == 2:
+        got = got.squeeze(2)
+    err = rel_err(got.numpy(), want.numpy())
+    print("conv_pair %s rel err %.2e" % (case, err))
+    assert err < TOL["tc"]
+
+
+def test_conv_pair_deconv_phases_vs_torch():
+    """k4 s2 p1 transposed conv 256 -> 256 (pose_resnet.py:266-291) as four stride-phase 2x2 convs on the CTA-pair kernel."""
+    torch.manual_seed(14)
+    e = _engine("tc")
+    dc = torch.nn.ConvTranspose2d(256, 256, 4, 2, 1, 0, bias=False).eval()
+    bn = _bn_for(dc, 2)
+    x = torch.randn(6, 256, 24, 24)
+    with torch.no_grad():
+        want = F.relu(bn(dc(x)))
+    launched = []
+    orig = capi.conv_nd
+    capi.conv_nd = lambda d, *a: (launched.append(a[-1]), orig(d, *a))[1]
+    try:
+        got = act_to_nchw(e._deconv2d(act_from_nchw(x, capi.FMT_S32), e._pack_deconv2d_k4s2(dc.to(DEV), bn.to(DEV)))).squeeze(2).cpu()
+    finally:
+        capi.conv_nd = orig
+    assert launched == [capi.CONV_TC_PAIR] * 4
+    assert rel_err(got.numpy(), want.numpy()) < TOL["tc"]
+
+
 def test_conv_tc_fp32_output_and_no_residual():
     torch.manual_seed(3)
     conv = torch.nn.Conv2d(256, 32, 1).eval()

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-2 GPU session script: STAGES selects what runs (space separated): tc ops forward hybrid rest bench benchfull smoke
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+O=gpurun_out
+T=${TAG:-r02a}
+STAGES=${STAGES:-"tc forward bench"}
+show='import sys,json; d=json.loads(sys.stdin.read()); print(round(d["value"],1), round(d["e2e"]["value"],1), round(d["ms_per_step"],3), d["step_breakdown_ms"], {k: round(d[k]["frac"],3) for k in d if k.startswith("roofline") and d[k]}, d["clocks"], d.get("parity"), {k: d[k] for k in d if k.startswith("torch_gpu")})'
+for s in $STAGES; do
+  case $s in
+    tc) timeout 900 python -m pytest tests/test_gpu_tc.py -q -m gpu -p no:cacheprovider --tb=short -x -s > $O/${T}_test_tc.log 2>&1; grep -E "conv_pair|passed|failed|Error|error" $O/${T}_test_tc.log | tail -40 ;;
+    ops) timeout 900 python -m pytest tests/test_gpu_ops.py -q -m gpu -p no:cacheprovider --tb=short > $O/${T}_test_ops.log 2>&1; tail -5 $O/${T}_test_ops.log ;;
+    forward) timeout 1500 python -m pytest tests/test_gpu_forward.py -q -m gpu -s -p no:cacheprovider --tb=short > $O/${T}_test_forward.log 2>&1; grep -E "rel err|config2|passed|failed|Error" $O/${T}_test_forward.log | tail -30 ;;
+    hybrid) timeout 900 python -m pytest tests/test_gpu_hybrid.py -q -m gpu -p no:cacheprovider --tb=short > $O/${T}_test_hybrid.log 2>&1; tail -5 $O/${T}_test_hybrid.log ;;
+    rest) timeout 1500 python -m pytest tests/test_gpu_algebraic.py tests/test_gpu_pipeline.py tests/test_gpu_variants.py -q -m gpu -p no:cacheprovider --tb=short > $O/${T}_test_rest.log 2>&1; tail -8 $O/${T}_test_rest.log ;;
+    all) timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short > $O/${T}_pytest_gpu.log 2>&1; tail -8 $O/${T}_pytest_gpu.log ;;
+    bench) LT_BENCH_TIMELINE=$O/${T}_timeline_tc.json timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-gpu 2> $O/${T}_bench_tc.err | tail -1 | tee $O/${T}_bench_tc.json | python -c "$show" ;;
+    benchfull) LT_BENCH_TIMELINE=$O/${T}_timeline_tc.json timeout 1200 python bench.py --steps 20 --warmup 3 2> $O/${T}_bench_tc.err | tail -1 | tee $O/${T}_bench_tc.json | python -c "$show" ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 1 --warmup 1 2>/dev/null | tail -1 | tee $O/${T}_bench_reference.json | cut -c1-300 ;;
+    smoke) timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -4 | tee $O/${T}_smoke.log ;;
+    nopair) LT_TC_PAIR=0 LT_BENCH_TIMELINE=$O/${T}_timeline_nopair.json timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-gpu 2> $O/${T}_bench_nopair.err | tail -1 | tee $O/${T}_bench_nopair.json | python -c "$show" ;;
+  esac
+  echo "== stage $s done"
+done
