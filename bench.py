@@ -477,7 +477,8 @@ def main_native(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # DRAM bytes per launch from the committed ncu launch list
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
-    kernel_names = {"conv_tc": "conv_tc_kernel", "conv_pair": "conv_pair_kernel", "conv_fold": "conv_fold_kernel", "conv_ffma": "conv_simt_kernel"}
+    kernel_names = {"conv_tc": "conv_tc_kernel", "conv_pair": "conv_pair_kernel", "conv_fold": "conv_fold_kernel", "conv_tail": "v2v_tail_kernel",
+                    "conv_ffma": "conv_simt_kernel"}
     tensor_kernels = [k for k in kernel_names if k in agg]
     conv_key = max(tensor_kernels, key=lambda k: agg[k][0]) if tensor_kernels else None
 

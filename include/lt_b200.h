@@ -186,12 +186,30 @@ int lt_conv_nd_fwd(const lt_conv_desc* desc, const void* in, const void* weight,
 size_t lt_conv_tc_weight_bytes(int taps, int Cin, int Cout);
 int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
 
+/* Weight preparation (once per parameter version, engine.prepare()).
+ * lt_conv_gather_weights_fwd: any framework filter layout -> canonical float32 [KD*KH*KW][CinP][CoutP] (zero padded); element
+ *   (td, th, tw, ci, co) is read from w[base + td*s_td + th*s_th + tw*s_tw + ci*s_ci + co*s_co] (nn.Conv: (Cout, Cin, k...);
+ *   nn.ConvTranspose: (Cin, Cout, k...); stride phases of a transposed conv: a tap sub-lattice walked with negative strides).
+ * lt_fold_bn_fwd: eval-mode BatchNorm (pose_resnet.py:30-31, v2v.py:12) + conv bias -> per-channel scale / shift [CP] (double
+ *   arithmetic, rounded once); mean == NULL: no BatchNorm. */
+int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, long s_th, long s_tw, long s_ci, long s_co, int KD, int KH, int KW,
+                               int Cin, int CinP, int Cout, int CoutP, float* out, void* stream);
+int lt_fold_bn_fwd(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
+                   int C, int CP, float* scale, float* shift, void* stream);
+
 /* CTA-pair weight packing: float32 [taps][Cin][Cout] (DEVICE) -> fp16 [taps][Cin/32][CoutP][32 hi | 32 lo] (128-byte rows),
  * CoutP = round_up(Cout, 128).  lt_conv_pair_eligible: 1 if LT_CONV_TC_PAIR covers this launch (shape / tiling heuristics),
  * else 0 (use LT_CONV_TC). */
 size_t lt_conv_pair_weight_bytes(int taps, int Cin, int Cout);
 int lt_conv_pair_pack_weights(const float* w_tap_ci_co, void* packed, int taps, int Cin, int Cout, void* stream);
 int lt_conv_pair_eligible(const lt_conv_desc* desc);
+
+/* Fused tail of the V2V network (v2v.py:154-160,168-169): back_layers[1], back_layers[2] (1x1x1 conv 32->32 + BN + ReLU each) and
+ * output_layer (1x1x1 conv 32->J + bias) as one kernel: x split-fp16 [rows][32 hi | 32 lo] -> logits float32 [rows][FC]
+ * (J <= FC <= 32, FC % 4 == 0; channels J..FC-1 are written as bias3 = 0).  w1/w2/w3: lt_conv_pair_pack_weights(taps 1, Cin 32)
+ * buffers; scale/shift: folded BatchNorm ([32] each); bias3 [32] zero padded. */
+int lt_v2v_tail_fwd(const void* x, const void* w1, const void* w2, const void* w3, const float* scale1, const float* shift1,
+                    const float* scale2, const float* shift2, const float* bias3, float* logits, long rows, int FC, void* stream);
 
 /* kw-folded weight packing: float32 [K^3][32][Cout] (DEVICE) -> split-fp16 [kd][kh][kw*NC + co][64], NC = round_up(Cout, 16). */
 size_t lt_conv_fold_weight_bytes(int K, int Cout);

@@ -58,9 +58,12 @@ SIGNATURES = {
     "lt_conv_nd_fwd": (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6 + [c_int, c_void_p]),
     "lt_conv_tc_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lt_conv_gather_weights_fwd": (c_int, [c_void_p] + [c_long] * 6 + [c_int] * 7 + [c_void_p, c_void_p]),
+    "lt_fold_bn_fwd": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lt_conv_pair_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_pair_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_conv_pair_eligible": (c_int, [ctypes.POINTER(ConvDesc)]),
+    "lt_v2v_tail_fwd": (c_int, [c_void_p] * 10 + [c_long, c_int, c_void_p]),
     "lt_conv_fold_weight_bytes": (c_size_t, [c_int, c_int]),
     "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
@@ -207,6 +210,17 @@ def conv_tc_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
     _check(lib().lt_conv_tc_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), taps, cin, cout, _stream()), "lt_conv_tc_pack_weights")
 
 
+def conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, out):
+    """w: the module's own filter tensor; strides = element strides of (td, th, tw, ci, co); out float32 [taps][cin_p][cout_p]."""
+    _check(lib().lt_conv_gather_weights_fwd(_ptr(w), base, *[int(v) for v in strides], k[0], k[1], k[2], cin, cin_p, cout, cout_p,
+                                            _ptr(out), _stream()), "lt_conv_gather_weights_fwd")
+
+
+def fold_bn(gamma, beta, mean, var, bias, eps, c, cp, scale, shift):
+    _check(lib().lt_fold_bn_fwd(_ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), _ptr(bias), float(eps), c, cp, _ptr(scale), _ptr(shift),
+                                _stream()), "lt_fold_bn_fwd")
+
+
 def conv_pair_weight_bytes(taps, cin, cout):
     return lib().lt_conv_pair_weight_bytes(taps, cin, cout)
 
@@ -217,6 +231,11 @@ def conv_pair_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
 
 def conv_pair_eligible(desc):
     return bool(lib().lt_conv_pair_eligible(ctypes.byref(desc)))
+
+
+def v2v_tail(x, w1, w2, w3, scale1, shift1, scale2, shift2, bias3, logits, rows, fc):
+    _check(lib().lt_v2v_tail_fwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(scale1), _ptr(shift1), _ptr(scale2), _ptr(shift2), _ptr(bias3),
+                                 _ptr(logits), rows, fc, _stream()), "lt_v2v_tail_fwd")
 
 
 def conv_fold_weight_bytes(k, cout):

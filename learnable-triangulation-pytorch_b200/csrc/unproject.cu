@@ -440,19 +440,19 @@ __device__ __forceinline__ const float4* q_at(const float4* base, unsigned idx) 
   return reinterpret_cast<const float4*>(r);
 }
 
-template <int MAXV, int FMT, bool EXACT, int MINB>   // EXACT: V == MAXV (no per-view predicates at all); MINB: min CTAs / SM
+template <int MAXV, int FMT, bool EXACT, int MINB, int CPL>   // EXACT: V == MAXV (no per-view predicates); MINB: min CTAs / SM; CPL: channels per lane (4 or 8)
 __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojParams p) {
   __shared__ float sP[MAXV * 12];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < p.V * 12; i += blockDim.x) sP[i] = p.proj[(long)b * p.V * 12 + i];
   __syncthreads();
-  constexpr int G = 8, C = 32, VPB = 32;
+  constexpr int C = 32, G = C / CPL, NQ = CPL / 4, VPB = 256 / G;
   const int sub = threadIdx.x & (G - 1);
-  const int slot = threadIdx.x >> 3;
+  const int slot = threadIdx.x / G;
   const int V = EXACT ? MAXV : p.V;
   const unsigned map_q = (unsigned)(p.h * p.w * (C / 4));   // float4 units per view map
-  // this lane's 4 channels of pixel 0 of view 0; tap offsets are 32-bit counts of float4 (one IMAD.WIDE per address)
-  const float4* fbase = reinterpret_cast<const float4*>(p.features + (long)b * V * p.h * p.w * C) + sub;
+  // this lane's CPL channels of pixel 0 of view 0; tap offsets are 32-bit counts of float4 (one IMAD.WIDE per address)
+  const float4* fbase = reinterpret_cast<const float4*>(p.features + (long)b * V * p.h * p.w * C) + sub * NQ;
   const float inv_h = 1.0f / (float)p.h, inv_w = 1.0f / (float)p.w;
   const float wm = (float)(p.w - 1), hm = (float)(p.h - 1);
   const int wi = p.w - 1, hi = p.h - 1;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojPar
     const long vox = live ? vbase + slot : p.nvox - 1;
     const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
     const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
-    float s[MAXV][4];
+    float s[MAXV][CPL];
 #pragma unroll
     for (int v0 = 0; v0 < MAXV; v0 += G) {
       // my share of the ray setup: view v0 + sub -> four clamped tap offsets and four weights with the mask folded in
@@ -505,22 +505,32 @@ __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojPar
         const float c0 = __shfl_sync(0xffffffffu, w0, j, G), c1 = __shfl_sync(0xffffffffu, w1, j, G);
         const float c2 = __shfl_sync(0xffffffffu, w2, j, G), c3 = __shfl_sync(0xffffffffu, w3, j, G);
         // views >= V carry offset 0 / weight 0: harmless loads of pixel 0
-        const float4 q0 = __ldg(q_at(fbase, a0)), q1 = __ldg(q_at(fbase, a1)), q2 = __ldg(q_at(fbase, a2)), q3 = __ldg(q_at(fbase, a3));
-        s[v][0] = fmaf(q3.x, c3, fmaf(q2.x, c2, fmaf(q1.x, c1, q0.x * c0)));
-        s[v][1] = fmaf(q3.y, c3, fmaf(q2.y, c2, fmaf(q1.y, c1, q0.y * c0)));
-        s[v][2] = fmaf(q3.z, c3, fmaf(q2.z, c2, fmaf(q1.z, c1, q0.z * c0)));
-        s[v][3] = fmaf(q3.w, c3, fmaf(q2.w, c2, fmaf(q1.w, c1, q0.w * c0)));
+        const float4* t0 = q_at(fbase, a0);
+        const float4* t1 = q_at(fbase, a1);
+        const float4* t2 = q_at(fbase, a2);
+        const float4* t3 = q_at(fbase, a3);
+#pragma unroll
+        for (int qd = 0; qd < NQ; ++qd) {
+          const float4 q0 = __ldg(t0 + qd), q1 = __ldg(t1 + qd), q2 = __ldg(t2 + qd), q3 = __ldg(t3 + qd);
+          s[v][qd * 4 + 0] = fmaf(q3.x, c3, fmaf(q2.x, c2, fmaf(q1.x, c1, q0.x * c0)));
+          s[v][qd * 4 + 1] = fmaf(q3.y, c3, fmaf(q2.y, c2, fmaf(q1.y, c1, q0.y * c0)));
+          s[v][qd * 4 + 2] = fmaf(q3.z, c3, fmaf(q2.z, c2, fmaf(q1.z, c1, q0.z * c0)));
+          s[v][qd * 4 + 3] = fmaf(q3.w, c3, fmaf(q2.w, c2, fmaf(q1.w, c1, q0.w * c0)));
+        }
       }
     }
     if constexpr (!EXACT) {
       // absent views must not take part in the view softmax: a large negative FINITE score (exp -> 0, s * 0 = -0)
 #pragma unroll
       for (int v = 0; v < MAXV; ++v)
-        if (v >= V) { s[v][0] = s[v][1] = s[v][2] = s[v][3] = -1.0e30f; }
-    }
-    float o[4];
+        if (v >= V) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < CPL; ++i) s[v][i] = -1.0e30f;
+        }
+    }
+    float o[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
       float m = s[0][i];
 #pragma unroll
       for (int v = 1; v < MAXV; ++v) m = fmaxf(m, s[v][i]);
@@ -531,10 +541,14 @@ __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojPar
       o[i] = num * rcp_approx(den);                  // den in [1, V]: no range scaling needed
     }
     if (!live) continue;
-    if constexpr (FMT == LT_FMT_F32) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((long)b * p.nvox + vox) * C + sub * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
-      store_s32x4(reinterpret_cast<sh_t*>(p.out) + ((long)b * p.nvox + vox) * 2 * C, sub * 4, make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+    for (int qd = 0; qd < NQ; ++qd) {
+      const float4 ov = make_float4(o[qd * 4], o[qd * 4 + 1], o[qd * 4 + 2], o[qd * 4 + 3]);
+      if constexpr (FMT == LT_FMT_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ((long)b * p.nvox + vox) * C + sub * CPL + qd * 4) = ov;
+      } else {
+        store_s32x4(reinterpret_cast<sh_t*>(p.out) + ((long)b * p.nvox + vox) * 2 * C, sub * CPL + qd * 4, ov);
+      }
     }
   }
 }
@@ -608,17 +622,27 @@ static int launch_unproject(const float* features, const float* proj, const floa
   const bool pow2q = (units & (units - 1)) == 0;
   static const int v2_mode = getenv("LT_UNPROJECT_V2") ? atoi(getenv("LT_UNPROJECT_V2")) : 1;
   if (v2_mode && C == 32 && agg == LT_AGG_SOFTMAX && partial == 0 && V <= 8 && (long)V * h * w * C < (1L << 30)) {
-    // register budget of the 4-view kernel (min CTAs/SM), measured on B200 at config #2 shapes: 4 -> 64 registers 0.292 ms
-    // (default), 5 -> 48 registers 0.299 ms, 6 -> 40 registers 0.344 ms, 1 -> 90 registers 0.377 ms
-    static const int lb = getenv("LT_UNPROJECT_LB") ? atoi(getenv("LT_UNPROJECT_LB")) : 4;
+    // variants (measured on B200 at config #2 shapes, see profiles/): 8 lanes x 4 channels per voxel at 4 CTAs/SM was the
+    // round-1 default (0.29-0.31 ms); 4 lanes x 8 channels halves the per-voxel ray / shuffle / address overhead
+    static const int cpl = getenv("LT_UNPROJECT_CPL") ? atoi(getenv("LT_UNPROJECT_CPL")) : 4;
+    static const int lb = getenv("LT_UNPROJECT_LB") ? atoi(getenv("LT_UNPROJECT_LB")) : 0;
+    if (cpl == 8) {
+      const int vpb8 = 64;
+      long blocks8 = (nvox + vpb8 - 1) / vpb8;
+      if (blocks8 > (long)sm_count() * 8) blocks8 = (long)sm_count() * 8;
+      grid.x = (unsigned)blocks8;
+    }
 #define LT_UNPROJ_V2(FMT)                                                                   \
-    if (V == 4 && lb == 6) unproject_v2_kernel<4, FMT, true, 6><<<grid, 256, 0, st>>>(p); \
-    else if (V == 4 && lb == 1) unproject_v2_kernel<4, FMT, true, 1><<<grid, 256, 0, st>>>(p); \
-    else if (V == 4 && lb == 5) unproject_v2_kernel<4, FMT, true, 5><<<grid, 256, 0, st>>>(p); \
-    else if (V == 4) unproject_v2_kernel<4, FMT, true, 4><<<grid, 256, 0, st>>>(p);        \
-    else if (V == 8) unproject_v2_kernel<8, FMT, true, 3><<<grid, 256, 0, st>>>(p);        \
-    else if (V < 4) unproject_v2_kernel<4, FMT, false, 5><<<grid, 256, 0, st>>>(p);        \
-    else unproject_v2_kernel<8, FMT, false, 3><<<grid, 256, 0, st>>>(p)
+    if (cpl == 8 && V == 4 && lb == 3) unproject_v2_kernel<4, FMT, true, 3, 8><<<grid, 256, 0, st>>>(p); \
+    else if (cpl == 8 && V == 4) unproject_v2_kernel<4, FMT, true, 2, 8><<<grid, 256, 0, st>>>(p); \
+    else if (cpl == 8 && V == 8) unproject_v2_kernel<8, FMT, true, 1, 8><<<grid, 256, 0, st>>>(p); \
+    else if (cpl == 8 && V < 4) unproject_v2_kernel<4, FMT, false, 2, 8><<<grid, 256, 0, st>>>(p); \
+    else if (cpl == 8) unproject_v2_kernel<8, FMT, false, 1, 8><<<grid, 256, 0, st>>>(p); \
+    else if (V == 4 && lb == 5) unproject_v2_kernel<4, FMT, true, 5, 4><<<grid, 256, 0, st>>>(p); \
+    else if (V == 4) unproject_v2_kernel<4, FMT, true, 4, 4><<<grid, 256, 0, st>>>(p);        \
+    else if (V == 8) unproject_v2_kernel<8, FMT, true, 3, 4><<<grid, 256, 0, st>>>(p);        \
+    else if (V < 4) unproject_v2_kernel<4, FMT, false, 5, 4><<<grid, 256, 0, st>>>(p);        \
+    else unproject_v2_kernel<8, FMT, false, 3, 4><<<grid, 256, 0, st>>>(p)
     if (out_format == LT_FMT_F32) { LT_UNPROJ_V2(LT_FMT_F32); } else { LT_UNPROJ_V2(LT_FMT_S32); }
 #undef LT_UNPROJ_V2
   } else if (vec4 && stored && pow2q && C <= 128) {

@@ -50,20 +50,9 @@ class ConvPack:
     __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs", "w_fold", "w_pair")
 
 
-def _fold_bn(conv_bias, bn, cout, device):
-    """BatchNorm (eval) + conv bias -> y = acc * scale + shift."""
-    if bn is not None:
-        inv = (bn.running_var.detach().double() + bn.eps).rsqrt()
-        g = bn.weight.detach().double() if bn.weight is not None else torch.ones(cout, dtype=torch.double, device=device)
-        b = bn.bias.detach().double() if bn.bias is not None else torch.zeros(cout, dtype=torch.double, device=device)
-        scale = g * inv
-        shift = b - bn.running_mean.detach().double() * scale
-        if conv_bias is not None:
-            shift = shift + conv_bias.detach().double() * scale
-    else:
-        scale = torch.ones(cout, dtype=torch.double, device=device)
-        shift = conv_bias.detach().double() if conv_bias is not None else torch.zeros(cout, dtype=torch.double, device=device)
-    return scale.float(), shift.float()
+def _f32(t):
+    """The module's own tensor as contiguous float32 (no copy for ordinary float32 parameters)."""
+    return None if t is None else t.detach().float().contiguous()
 
 
 class _Timed:
@@ -99,6 +88,7 @@ class NativeEngine:
         self.launches = 0          # kernels launched by the last eager forward (our own kernels only)
         self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
         self.use_pair = os.environ.get("LT_TC_PAIR", "1") == "1"          # CTA-pair kernel for Cout % 128 == 0 layers
+        self.use_tail = os.environ.get("LT_TC_TAIL", "1") == "1"          # fused back1 + back2 + output kernel
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
@@ -119,10 +109,13 @@ class NativeEngine:
         self._packs = None
         self._graphs = {}
 
-    def _pack(self, w_taps, bias, bn, k, stride, pad, force_simt=False, out_fmt=None):
-        """w_taps: float32 [taps][Cin][Cout] (device)."""
-        dev = w_taps.device
-        taps, cin, cout = w_taps.shape
+    def _pack(self, src, k, stride, pad, cin, cout, bias, bn, cin_pad=None, force_simt=False, out_fmt=None, force_pair=False):
+        """src = (filter tensor, base, (s_td, s_th, s_tw, s_ci, s_co)): where element (td, th, tw, ci, co) of this (phase of a)
+        convolution sits inside the module's own weight tensor.  Everything below is our own kernels: gather to the canonical
+        [tap][Cin][Cout] layout (lt_conv_gather_weights_fwd), operand packing, BatchNorm folding (lt_fold_bn_fwd)."""
+        w, base, strides = src
+        dev = w.device
+        taps = k[0] * k[1] * k[2]
         out_fmt = self.act_fmt if out_fmt is None else out_fmt
         pk = ConvPack()
         pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
@@ -130,65 +123,65 @@ class NativeEngine:
         pk.w_fold = None
         pk.w_pair = None
         use_tc = (self.mode != "simt") and not force_simt and (max(stride) == 1 or self.tc_strided)
-        scale, shift = _fold_bn(bias, bn, cout, dev)
         if use_tc:
-            cin_p = _round_up(cin, 32)
+            cin_p = _round_up(max(cin, cin_pad or 0), 32)
             cout_p = _round_up(cout, 32 if out_fmt == FMT_S32 else 16)
-            wp = torch.zeros((taps, cin_p, cout_p), dtype=torch.float32, device=dev)
-            wp[:, :cin, :cout] = w_taps
+        else:
+            cin_p = max(cin, cin_pad or 0)
+            cout_p = _round_up(cout, 4)
+        wp = torch.empty((taps, cin_p, cout_p), dtype=torch.float32, device=dev)
+        capi.conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, wp)
+        if use_tc:
             packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
-            capi.conv_tc_pack_weights(wp.contiguous(), packed, taps, cin_p, cout_p)
+            capi.conv_tc_pack_weights(wp, packed, taps, cin_p, cout_p)
             pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = packed, cin_p, cout_p, self.tc_impl, FMT_S32
             # wide layers: also pack for the CTA-pair kernel (cta_group::2, 256 x {128,256} tiles; csrc/conv_pair.cu)
-            if self.use_pair and self.mode == "tc" and cout_p % 128 == 0:
+            if self.mode == "tc" and ((self.use_pair and cout_p % 128 == 0) or force_pair):
                 wq = torch.empty(capi.conv_pair_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
-                capi.conv_pair_pack_weights(wp.contiguous(), wq, taps, cin_p, cout_p)
+                capi.conv_pair_pack_weights(wp, wq, taps, cin_p, cout_p)
                 pk.w_pair = wq
             # narrow cubic stride-1 layers (V2V at full resolution): also pack for the kw-folded persistent kernel
             if (self.use_fold and self.mode == "tc" and cin_p == 32 and cout <= 32 and k[0] == k[1] == k[2] and k[0] in (3, 7)
                     and tuple(pad) == (k[0] // 2,) * 3 and max(stride) == 1):
                 wf = torch.empty(capi.conv_fold_weight_bytes(k[0], cout) // 2, dtype=torch.float16, device=dev)
-                capi.conv_fold_pack_weights(wp[:, :, :cout].contiguous(), wf, k[0], cout)
+                wsrc = wp if cout_p == cout else wp[:, :, :cout].contiguous()
+                capi.conv_fold_pack_weights(wsrc, wf, k[0], cout)
                 pk.w_fold = wf
         else:
-            cout_p = _round_up(cout, 4)
-            wp = torch.zeros((taps, cin, cout_p), dtype=torch.float32, device=dev)
-            wp[:, :, :cout] = w_taps
-            pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = wp.contiguous(), cin, cout_p, CONV_SIMT, FMT_F32
-        pk.scale = torch.zeros(cout_p, dtype=torch.float32, device=dev)
-        pk.shift = torch.zeros(cout_p, dtype=torch.float32, device=dev)
-        pk.scale[:cout] = scale
-        pk.shift[:cout] = shift
+            pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = wp, cin_p, cout_p, CONV_SIMT, FMT_F32
+        pk.scale = torch.empty(cout_p, dtype=torch.float32, device=dev)
+        pk.shift = torch.empty(cout_p, dtype=torch.float32, device=dev)
+        if bn is not None:
+            capi.fold_bn(_f32(bn.weight), _f32(bn.bias), _f32(bn.running_mean), _f32(bn.running_var), _f32(bias), bn.eps, cout, cout_p,
+                         pk.scale, pk.shift)
+        else:
+            capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, cout_p, pk.scale, pk.shift)
         return pk
 
     def _pack_conv(self, conv, bn, cin_pad=None, **kw):
-        w = conv.weight.detach().float()
+        w = _f32(conv.weight)
+        cout, cin = w.shape[:2]
         if w.dim() == 4:   # (Cout, Cin, KH, KW)
             k = (1,) + tuple(conv.kernel_size)
             stride = (1,) + tuple(conv.stride)
             pad = (0,) + tuple(conv.padding)
-            wt = w.permute(2, 3, 1, 0).reshape(k[1] * k[2], w.shape[1], w.shape[0])
         else:              # (Cout, Cin, KD, KH, KW)
             k, stride, pad = tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
-            wt = w.permute(2, 3, 4, 1, 0).reshape(k[0] * k[1] * k[2], w.shape[1], w.shape[0])
-        if cin_pad is not None and cin_pad > wt.shape[1]:
-            wz = torch.zeros((wt.shape[0], cin_pad, wt.shape[2]), dtype=wt.dtype, device=wt.device)
-            wz[:, :wt.shape[1]] = wt
-            wt = wz
-        pk = self._pack(wt.contiguous(), conv.bias, bn, k, stride, pad, **kw)
-        pk.kmacs = pk.taps * w.shape[1] * w.shape[0]
-        return pk
+        T = k[0] * k[1] * k[2]
+        src = (w, 0, (k[1] * k[2], k[2], 1, T, cin * T))
+        return self._pack(src, k, stride, pad, cin, cout, conv.bias, bn, cin_pad=cin_pad, **kw)
 
     def _pack_stem_s2d(self, conv, bn):
         """7x7 stride-2 pad-3 conv == 4x4 stride-1 conv (front pad 2) over the 2x2 space-to-depth input.
 
         Input row 2*oy - 3 + ky = 2*(oy + a) + r with a = tap offset in {-2..1}, r = row parity:
         ky = 2a + r + 3 (taps with ky outside [0, 7) get zero weights).  Channel order (r*2 + s)*3 + c.
+        The re-indexing is not affine in the s2d channel, so this one (64 x 3 x 7 x 7) filter is rearranged on the host.
         """
-        w = conv.weight.detach().float()          # (64, 3, 7, 7)
+        w = conv.weight.detach().float().cpu()          # (64, 3, 7, 7)
         assert tuple(w.shape[1:]) == (3, 7, 7) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (3, 3)
         cout = w.shape[0]
-        wt = torch.zeros((4, 4, 32, cout), dtype=torch.float32, device=w.device)
+        wt = torch.zeros((4, 4, 32, cout), dtype=torch.float32)
         for ai, a in enumerate(range(-2, 2)):
             for bi, b in enumerate(range(-2, 2)):
                 for r in (0, 1):
@@ -197,35 +190,36 @@ class NativeEngine:
                         if 0 <= ky < 7 and 0 <= kx < 7:
                             c0 = (r * 2 + s) * 3
                             wt[ai, bi, c0:c0 + 3] = w[:, :, ky, kx].t()
-        pk = self._pack(wt.reshape(16, 32, cout).contiguous(), conv.bias, bn, (1, 4, 4), (1, 1, 1), (0, 2, 2))
+        wt = wt.to(conv.weight.device)                  # one H2D copy; canonical [tap][ci][co] already
+        pk = self._pack((wt, 0, (0, 4 * 32 * cout, 32 * cout, cout, 1)), (1, 4, 4), (1, 1, 1), (0, 2, 2), 32, cout, conv.bias, bn)
         pk.kmacs = 49 * 3 * cout
         return pk
 
     def _pack_deconv2d_k4s2(self, deconv, bn):
         """ConvTranspose2d(k=4, s=2, p=1) as four 2x2 stride-1 convs, one per output parity.
 
-        out[2m+py] takes ky in {3,1} (input rows m-1, m) for py=0 and {2,0} (rows m, m+1) for py=1.
+        out[2m+py] takes ky in {3,1} (input rows m-1, m) for py=0 and {2,0} (rows m, m+1) for py=1: tap i reads ky = 3 - py - 2i.
         """
-        w = deconv.weight.detach().float()  # (Cin, Cout, 4, 4)
+        w = _f32(deconv.weight)  # (Cin, Cout, 4, 4)
         assert tuple(deconv.kernel_size) == (4, 4) and tuple(deconv.stride) == (2, 2) and tuple(deconv.padding) == (1, 1)
+        cin, cout = w.shape[:2]
         phases = {}
-        sel = {0: [3, 1], 1: [2, 0]}
         for py in (0, 1):
             for px in (0, 1):
-                wt = w[:, :, sel[py], :][:, :, :, sel[px]]           # (Cin, Cout, 2, 2)
-                wt = wt.permute(2, 3, 0, 1).reshape(4, w.shape[0], w.shape[1]).contiguous()
-                phases[(py, px)] = self._pack(wt, deconv.bias, bn, (1, 2, 2), (1, 1, 1), (0, 1 - py, 1 - px))
+                src = (w, (3 - py) * 4 + (3 - px), (0, -8, -2, cout * 16, 16))
+                phases[(py, px)] = self._pack(src, (1, 2, 2), (1, 1, 1), (0, 1 - py, 1 - px), cin, cout, deconv.bias, bn)
         return phases
 
     def _pack_deconv3d_k2s2(self, deconv, bn):
         """ConvTranspose3d(k=2, s=2): eight independent 1x1x1 convs scattered to the output parities."""
-        w = deconv.weight.detach().float()  # (Cin, Cout, 2, 2, 2)
+        w = _f32(deconv.weight)  # (Cin, Cout, 2, 2, 2)
+        cin, cout = w.shape[:2]
         phases = {}
         for a in (0, 1):
             for b in (0, 1):
                 for c in (0, 1):
-                    wt = w[:, :, a, b, c].reshape(1, w.shape[0], w.shape[1]).contiguous()
-                    phases[(a, b, c)] = self._pack(wt, deconv.bias, bn, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+                    src = (w, a * 4 + b * 2 + c, (0, 0, 0, cout * 8, 8))
+                    phases[(a, b, c)] = self._pack(src, (1, 1, 1), (1, 1, 1), (0, 0, 0), cin, cout, deconv.bias, bn)
         return phases
 
     def prepare(self):
@@ -286,9 +280,11 @@ class NativeEngine:
                 P["up%d" % lvl] = self._pack_deconv3d_k2s2(up.block[0], up.block[1])
             pack_res("mid", ed.mid_res)
             pack_res("back0", v.back_layers[0])
-            P["back1"] = self._pack_conv(v.back_layers[1].block[0], v.back_layers[1].block[1])
-            P["back2"] = self._pack_conv(v.back_layers[2].block[0], v.back_layers[2].block[1])
-            P["output"] = self._pack_conv(v.output_layer, None, out_fmt=FMT_F32)
+            # the three point-wise layers of the tail are also packed for the fused tail kernel (csrc/conv_tail.cu)
+            tail = self.use_tail and self.mode == "tc"
+            P["back1"] = self._pack_conv(v.back_layers[1].block[0], v.back_layers[1].block[1], force_pair=tail)
+            P["back2"] = self._pack_conv(v.back_layers[2].block[0], v.back_layers[2].block[1], force_pair=tail)
+            P["output"] = self._pack_conv(v.output_layer, None, out_fmt=FMT_F32, force_pair=tail)
         self._packs, self._packs_version = P, ver
         self._graphs = {}
 
@@ -478,11 +474,22 @@ class NativeEngine:
             x = self._res3d(x, "dec%d" % lvl)
             x = self._deconv3d(x, P["up%d" % lvl], skips.pop(lvl))
         x = self._res3d(x, "back0")
+        out_c = _round_up(P["output"].cout, 4) if self.compact_logits else None
+        b1, b2, b3 = P["back1"], P["back2"], P["output"]
+        if (b1.w_pair is not None and b2.w_pair is not None and b3.w_pair is not None and x.fmt == FMT_S32 and x.C == 32 and out_c is not None
+                and b1.cin == b2.cin == b3.cin == 32 and b1.cout == b2.cout == 32 and b3.cout <= out_c <= 32):
+            # v2v.py:154-160,168-169 in one kernel: the two hidden activations never leave the SM
+            logits = Act(x.N, x.D, x.H, x.W, out_c, FMT_F32, x.data.device)
+            rows = x.pixels
+            with self._timed("conv_tail", flops=2.0 * rows * (b1.kmacs + b2.kmacs + b3.kmacs), nbytes=rows * (128 + 4 * out_c),
+                             desc="N%d %dx%dx%d 32->32->32->%d k111 fused" % (x.N, x.D, x.H, x.W, b3.cout)):
+                capi.v2v_tail(x.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.shift, logits.data, rows, out_c)
+            self.launches += 1
+            return logits
         x = self._conv(x, P["back1"], relu=True)
         x = self._conv(x, P["back2"], relu=True)
         # compact logits: 17 joints stored 20 wide (80-byte voxel rows) instead of the 32-wide N tile -> the soft-argmax
         # streams 37 % fewer bytes; the conv's TMA store clips the 12 padding channels
-        out_c = _round_up(P["output"].cout, 4) if self.compact_logits else None
         return self._conv(x, P["output"], relu=False, out_fmt=FMT_F32, out_c=out_c)
 
     def softargmax(self, logits, coord, J, multiplier, softmax):

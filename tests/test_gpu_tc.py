@@ -342,3 +342,30 @@ def test_conv_tc_vs_ffma_at_config2_sizes(case):
     err = rel_err(y_tc.cpu().numpy(), y_ff.cpu().numpy())
     print("conv_tc vs ffma %s rel err %.2e" % (case, err))
     assert err < TOL["tc"]
+
+
+@pytest.mark.parametrize("spatial,N", [((16, 16, 16), 2), ((5, 6, 7), 3), ((64, 64, 16), 1)])
+def test_v2v_tail_fused_vs_torch(spatial, N):
+    """back_layers[1], back_layers[2], output_layer (v2v.py:154-160,168-169) as one kernel (csrc/conv_tail.cu) vs the three torch ops;
+    row counts that are not a multiple of the 128-voxel tile included."""
+    torch.manual_seed(21)
+    c1, c2, c3 = torch.nn.Conv3d(32, 32, 1).eval(), torch.nn.Conv3d(32, 32, 1).eval(), torch.nn.Conv3d(32, 17, 1).eval()
+    bn1, bn2 = _bn_for(c1, 5), _bn_for(c2, 6)
+    x = torch.randn(N, 32, *spatial)
+    with torch.no_grad():
+        want = c3(F.relu(bn2(c2(F.relu(bn1(c1(x)))))))
+    e = _engine("tc")
+    e.use_tail = True
+    b1 = e._pack_conv(c1.to(DEV), bn1.to(DEV), force_pair=True)
+    b2 = e._pack_conv(c2.to(DEV), bn2.to(DEV), force_pair=True)
+    b3 = e._pack_conv(c3.to(DEV), None, out_fmt=capi.FMT_F32, force_pair=True)
+    xa = act_from_nchw(x, capi.FMT_S32)
+    rows = xa.pixels
+    logits = torch.full((rows, 20), 7.0, dtype=torch.float32, device=DEV)
+    capi.v2v_tail(xa.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.shift, logits, rows, 20)
+    torch.cuda.synchronize()
+    got = logits.view(N, *spatial, 20).permute(0, 4, 1, 2, 3).cpu()
+    err = rel_err(got[:, :17].numpy(), want.numpy())
+    print("v2v tail %s N=%d rel err %.2e" % (spatial, N, err))
+    assert err < TOL["tc"] * 2          # three chained layers
+    assert float(got[:, 17:].abs().max()) == 0.0

@@ -10,8 +10,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = [
-    ("unproject", {"LT_UNPROJECT_V2": "0"}), ("unproject", {"LT_UNPROJECT_LB": "5"}), ("unproject", {"LT_UNPROJECT_LB": "4"}),
-    ("unproject", {"LT_UNPROJECT_LB": "6"}), ("unproject", {"LT_UNPROJECT_LB": "1"}),
+    ("unproject", {"LT_UNPROJECT_V2": "0"}), ("unproject", {"LT_UNPROJECT_CPL": "4"}), ("unproject", {"LT_UNPROJECT_CPL": "4", "LT_UNPROJECT_LB": "5"}),
+    ("unproject", {"LT_UNPROJECT_CPL": "8"}), ("unproject", {"LT_UNPROJECT_CPL": "8", "LT_UNPROJECT_LB": "3"}),
     ("softargmax20", {"LT_SOFTARGMAX_FUSED": "0"}), ("softargmax20", {"LT_SOFTARGMAX_FUSED": "1"}),
     ("softargmax32", {"LT_SOFTARGMAX_FUSED": "0"}), ("softargmax32", {"LT_SOFTARGMAX_FUSED": "1"}),
 ]
@@ -61,7 +61,11 @@ if what == "unproject":
     out = torch.empty((B, nvox, 64), dtype=torch.float16, device=dev)
     pj = up(proj)
     nbytes = B * (nvox * 32 * 4 + V * h * h * 32 * 4 + nvox * 12)
-    print(timed(lambda: capi.unproject_aggregate(feats, pj, coord.view(B, nvox, 3), None, out, capi.FMT_S32, capi.AGG["softmax"]), nbytes))
+    res = timed(lambda: capi.unproject_aggregate(feats, pj, coord.view(B, nvox, 3), None, out, capi.FMT_S32, capi.AGG["softmax"]), nbytes)
+    f = torch.empty((B, nvox, 32), device=dev)
+    capi.s32_to_f32(out, f, B * nvox, 32)
+    print(res, " checksum: sum %.6f  sumsq %.6f  sample %s" % (float(f.double().sum()), float((f.double() ** 2).sum()),
+                                                               [round(float(x), 6) for x in f[3, 12345:12348, 7]]))
 else:
     vs = int(what[-2:])
     logits = torch.randn(B, nvox, vs, device=dev) * 3
