@@ -519,6 +519,8 @@ def main_native(args, rank, world, local_rank):
             extra["roofline_" + key] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                         "frac": ach / pk["hbm_gbs"], "ms_per_step": ms, "launches": cnt, "traffic": traffic.get(key),
                                         "peak_source": pk["src"] + " copy bandwidth"}
+    if traffic.get("_source") or traffic.get("source"):
+        traffic.setdefault("_source", traffic.get("source"))
     if traffic.get("_source"):
         extra["traffic_source"] = traffic["_source"]
     extra["step_breakdown_ms"] = {k: round(v[0], 3) for k, v in agg.items()}

@@ -56,6 +56,26 @@ enum lt_conv_impl {
 /* residual placement in the conv epilogue */
 enum lt_residual { LT_RES_NONE = 0, LT_RES_BEFORE_RELU = 1, LT_RES_AFTER_RELU = 2 };
 
+/* Kernel-selection options: the ONLY mutable process-wide state of the library besides its caches (encoded tensor maps,
+ * per-device function attributes).  Every field defaults to the measured-best path; the alternatives stay reachable for A/B
+ * measurements on the same box.  Set once before launching (lt_set_options is not synchronised against concurrent launches);
+ * no entry point reads the environment. */
+typedef struct lt_options {
+  int tc_persist;          /* conv_tc: persistent variant 0 = never, 1 = tiny-tile layers (default), 2 = whenever possible */
+  int tc_splitk;           /* conv_tc: split-K for grids below half the SMs (default 1) */
+  int tc_bres;             /* conv_tc: B-resident persistent variant for K-short 1x1 layers (default 1) */
+  int tc_direct_epilogue;  /* conv_tc: register epilogue with plain stores instead of the staged TMA epilogue (default 0) */
+  int fold_fast_issue;     /* conv_fold: unrolled uniform-register MMA issue loop (default 1) */
+  int fold_debug;          /* conv_fold: 0 = off; 1..3 = stage knock-outs of tools/fold_probe.py; 16 = wait counters to stderr */
+  int softargmax_stream;   /* soft-argmax: streaming TMA kernels for compact channels-last logits (default 1) */
+  int unproject_v2;        /* unprojection: production-shape kernel (default 1) */
+  int unproject_cpl;       /* unprojection v2: channels per lane, 4 or 8 */
+  int unproject_lb;        /* unprojection v2: min CTAs / SM override (0 = per-variant default) */
+} lt_options;
+void lt_default_options(lt_options* o);
+int lt_get_options(lt_options* o);
+int lt_set_options(const lt_options* o);
+
 int lt_version(void);
 const char* lt_last_error_string(void);
 

@@ -36,8 +36,20 @@ class ConvDesc(ctypes.Structure):
         "relu", "residual", "in_format", "out_format")] + [("workspace", c_void_p), ("workspace_bytes", c_size_t)]
 
 
+class Options(ctypes.Structure):
+    """Mirror of `struct lt_options` (include/lt_b200.h): kernel-selection switches, all defaulting to the measured-best path."""
+    _fields_ = [(n, c_int) for n in ("tc_persist", "tc_splitk", "tc_bres", "tc_direct_epilogue", "fold_fast_issue", "fold_debug",
+                                     "softargmax_stream", "unproject_v2", "unproject_cpl", "unproject_lb")]
+
+
+# The ONE place the environment is read (A/B tooling: tools/post_probe.py, tools/fold_probe.py): LT_OPT_<FIELD>=<int>
+OPTIONS_ENV_PREFIX = "LT_OPT_"
+
 # every symbol include/lt_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
+    "lt_default_options": (None, [ctypes.POINTER(Options)]),
+    "lt_get_options": (c_int, [ctypes.POINTER(Options)]),
+    "lt_set_options": (c_int, [ctypes.POINTER(Options)]),
     "lt_version": (c_int, []),
     "lt_last_error_string": (ctypes.c_char_p, []),
     "lt_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
@@ -99,7 +111,39 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        _apply_env_options(handle)
     return _lib
+
+
+def _apply_env_options(handle):
+    """LT_OPT_<FIELD> environment overrides -> lt_set_options, once at load (the C library itself never reads the environment)."""
+    o = Options()
+    handle.lt_default_options(ctypes.byref(o))
+    changed = False
+    for name, _ in Options._fields_:
+        v = os.environ.get(OPTIONS_ENV_PREFIX + name.upper())
+        if v is not None:
+            setattr(o, name, int(v))
+            changed = True
+    if changed and handle.lt_set_options(ctypes.byref(o)) != 0:
+        raise RuntimeError("lt_set_options failed: %s" % handle.lt_last_error_string().decode())
+
+
+def set_options(**kw):
+    """Explicit options API: capi.set_options(unproject_cpl=8, ...)."""
+    o = Options()
+    _check(lib().lt_get_options(ctypes.byref(o)), "lt_get_options")
+    for k, v in kw.items():
+        if k not in dict(Options._fields_):
+            raise KeyError("unknown lt_options field %r" % k)
+        setattr(o, k, int(v))
+    _check(lib().lt_set_options(ctypes.byref(o)), "lt_set_options")
+
+
+def get_options():
+    o = Options()
+    _check(lib().lt_get_options(ctypes.byref(o)), "lt_get_options")
+    return {n: getattr(o, n) for n, _ in Options._fields_}
 
 
 def _check(rc, what):
@@ -108,6 +152,8 @@ def _check(rc, what):
 
 
 def _stream():
+    """Stream of the CURRENT device: callers that work on another device wrap the call in `torch.cuda.device(...)`
+    (VolumetricTriangulationNet.forward does)."""
     return torch.cuda.current_stream().cuda_stream
 
 

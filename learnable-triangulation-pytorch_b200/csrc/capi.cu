@@ -17,6 +17,17 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static lt_options make_default_options() {
+  lt_options o;
+  o.tc_persist = 1; o.tc_splitk = 1; o.tc_bres = 1; o.tc_direct_epilogue = 0;
+  o.fold_fast_issue = 1; o.fold_debug = 0;
+  o.softargmax_stream = 1;
+  o.unproject_v2 = 1; o.unproject_cpl = 4; o.unproject_lb = 0;
+  return o;
+}
+static lt_options g_options = make_default_options();
+const lt_options& opts() { return g_options; }
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -43,7 +54,24 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
 
 }  // namespace lt
 
-extern "C" int lt_version(void) { return 100; }
+extern "C" int lt_version(void) { return 200; }
+
+extern "C" void lt_default_options(lt_options* o) {
+  if (o) *o = lt::make_default_options();
+}
+extern "C" int lt_get_options(lt_options* o) {
+  if (!o) return lt::fail(LT_ERR_INVALID, "lt_get_options: null pointer");
+  *o = lt::g_options;
+  return LT_OK;
+}
+extern "C" int lt_set_options(const lt_options* o) {
+  using namespace lt;
+  LT_REQUIRE(o, "lt_set_options: null pointer");
+  LT_REQUIRE(o->unproject_cpl == 4 || o->unproject_cpl == 8, "lt_set_options: unproject_cpl must be 4 or 8");
+  LT_REQUIRE(o->tc_persist >= 0 && o->tc_persist <= 2, "lt_set_options: tc_persist must be 0, 1 or 2");
+  g_options = *o;
+  return LT_OK;
+}
 
 extern "C" const char* lt_last_error_string(void) { return lt::err_buf(); }
 

@@ -24,7 +24,20 @@ int fail(int code, const char* fmt, ...);
     if (e__ != cudaSuccess) return ::lt::fail(LT_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+const lt_options& opts();   // process-wide kernel-selection options (capi.cu; lt_set_options)
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// One-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property): `first()` is true exactly once per device ordinal
+// for each DeviceOnce object, from whichever host thread gets there first.
+struct DeviceOnce {
+  unsigned long long done = 0;
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (__atomic_fetch_or(&done, bit, __ATOMIC_ACQ_REL) & bit) == 0;
+  }
+};
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 

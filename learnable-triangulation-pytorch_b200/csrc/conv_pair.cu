@@ -328,13 +328,10 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   x.off_bar = x.off_res + 32768;
   const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 6) * 8 + 16 + 1024;
   if (smem > 227 * 1024) return fail(LT_ERR_INVALID, "conv_pair: shared memory budget exceeded (%zu)", smem);
-  static thread_local int conf_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (conf_dev != dev) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conf_dev = dev;
   }
   conv_pair_kernel<<<plan.grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
   cudaError_t e = cudaGetLastError();

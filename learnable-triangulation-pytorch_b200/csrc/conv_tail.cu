@@ -234,13 +234,10 @@ extern "C" int lt_v2v_tail_fwd(const void* x, const void* w1, const void* w2, co
   TailParams p;
   p.scale1 = scale1; p.shift1 = shift1; p.scale2 = scale2; p.shift2 = shift2; p.bias3 = bias3;
   p.logits = logits; p.rows = rows; p.tiles = (rows + 127) / 128; p.FC = FC;
-  static thread_local int conf_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (conf_dev != dev) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(v2v_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem);
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "v2v_tail: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    conf_dev = dev;
   }
   long grid = 3L * sm_count();
   if (grid > p.tiles) grid = p.tiles;

@@ -500,10 +500,39 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached per host thread by their full argument list (base pointer, dims, strides, box, element strides,
+// swizzle, type): an eager forward re-encodes the same ~300 maps every step otherwise (cuTensorMapEncodeTiled costs ~1-2 us each;
+// graph replays never come here).  256-entry direct-mapped table, 64-bit FNV-1a key with full-argument verification.
+struct MapKey {
+  const void* base;
+  int rank, swizzle, f32;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5], es[5];
+};
+struct MapSlot {
+  bool used = false;
+  MapKey key;
+  CUtensorMap map;
+};
+
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box, const uint32_t* estrides, int swizzle128, int f32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.swizzle = swizzle128; key.f32 = f32;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; key.es[i] = estrides ? estrides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  uint64_t h = 1469598103934665603ull;
+  const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
+  for (size_t i = 0; i < sizeof(key); ++i) { h ^= kb[i]; h *= 1099511628211ull; }
+  static thread_local MapSlot cache[256];
+  MapSlot& slot = cache[(h ^ (h >> 29)) & 255];
+  if (slot.used && memcmp(&slot.key, &key, sizeof(key)) == 0) {
+    *map = slot.map;
+    return LT_OK;
+  }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estrides ? estrides[i] : 1; }
@@ -513,6 +542,9 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                   swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  slot.used = true;
+  slot.key = key;
+  slot.map = *map;
   return LT_OK;
 }
 
@@ -603,14 +635,13 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   p.tmem_cols = pow2_ceil(acc_cols) < 32 ? 32 : pow2_ceil(acc_cols);
   const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 3) * 8 + 16 + 1024;
   if (p.tma_epi && (size_t)stages * stage_bytes < 65536) return fail(LT_ERR_INVALID, "conv_tc: operand ring too small for the staged epilogue");
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = 227 * 1024;
   }
   const long m_tiles = (long)p.tw * p.th * p.td * p.tn;
-  static const int persist_mode = getenv("LT_TC_PERSIST") ? atoi(getenv("LT_TC_PERSIST")) : 1;
+  const int persist_mode = opts().tc_persist;
   // Measured on B200 (profiles/): two co-resident non-persistent CTAs already overlap epilogue and main loop for the
   // MMA-heavy layers and win there; the persistent variant wins when a tile carries almost no work (1x1x1 convs at 64^3:
   // 0.73 -> 0.41 ms for three launches), where CTA setup (TMEM alloc, barrier init, descriptor fetch) dominates.
@@ -641,11 +672,10 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     x.off_bar = x.off_res + 32768;
     const size_t psmem = (size_t)x.off_bar + (2 * pst + 7) * 8 + 16 + 1024;
     if (psmem > 227 * 1024) return fail(LT_ERR_INVALID, "conv_tc_persist: shared memory budget exceeded (%zu)", psmem);
-    static bool pconf = false;
-    if (!pconf) {
+    static DeviceOnce pconf;
+    if (pconf.first()) {
       cudaError_t e2 = cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
       if (e2 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
-      pconf = true;
     }
     const unsigned pgrid = bres ? (unsigned)(x.m_streams * n_tiles) : (unsigned)sm_count();
     conv_tc_persist_kernel<<<pgrid, 320, psmem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
@@ -655,7 +685,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   // split-K: a grid that cannot fill half the SMs is bound by the serial K loop of each CTA (27 taps x Cin/32 chunks of
   // weights streamed from HBM by ONE SM); spread the chunks over blockIdx.z instead
-  static const int splitk_mode = getenv("LT_TC_SPLITK") ? atoi(getenv("LT_TC_SPLITK")) : 1;
+  const int splitk_mode = opts().tc_splitk;
   int splits = 1;
   const long grid_ctas = m_tiles * n_tiles;
   if (splitk_mode && ws && p.terms != 0 && grid_ctas * 2 <= (long)sm_count() && nchunks_total >= 16) {
@@ -792,23 +822,21 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     const uint64_t dims[5] = {(uint64_t)d->Cin * 2, (uint64_t)d->IW, (uint64_t)d->IH, (uint64_t)d->ID, (uint64_t)d->N};
     const uint64_t str[4] = {rowb, rowb * d->IW, rowb * d->IW * d->IH, rowb * d->IW * d->IH * d->ID};
     // strided convs: TMA traversal strides; the box spans (b-1)*s+1 input positions and delivers b of them
-    static const int box_is_count = getenv("LT_TMA_STRIDE_MODE") && atoi(getenv("LT_TMA_STRIDE_MODE")) == 1;
     const uint32_t es[5] = {1, (uint32_t)d->sw, (uint32_t)d->sh, (uint32_t)d->sd, 1};
     uint32_t bx[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
-    if (!box_is_count)
-      for (int i = 1; i <= 3; ++i) bx[i] = (bx[i] - 1) * es[i] + 1;
+    for (int i = 1; i <= 3; ++i) bx[i] = (bx[i] - 1) * es[i] + 1;
     LT_REQUIRE(bx[1] <= 256 && bx[2] <= 256 && bx[3] <= 256, "conv_tc: strided box exceeds 256");
     int rc = make_map(&tmA, in, 5, dims, str, bx, es, 1);
     if (rc) return rc;
   }
   CUtensorMap tmOut = tmA, tmRes = tmA;
-  static const int direct_epi = getenv("LT_TC_EPILOGUE") && !strcmp(getenv("LT_TC_EPILOGUE"), "direct");
+  const int direct_epi = opts().tc_direct_epilogue;
   // float32 outputs may be narrower than the (single) padded N tile: the tensor map then has FC channels and the TMA
   // store clips the box at the tensor bound (80-byte voxel rows for the 17-joint logits instead of 128)
   const bool clipped_f32 = d->out_format == LT_FMT_F32 && d->residual == LT_RES_NONE && CoutP == Nt && d->FC % 4 == 0 && d->FC < CoutP;
   p.tma_epi = (!direct_epi && Nt % 32 == 0 && ((d->FC % 32 == 0 && CoutP <= d->FC) || clipped_f32)) ? 1 : 0;
   // B-resident persistent variant: 1x1-like layers (<= 8 K chunks) with more than one 128-wide N tile and enough M tiles
-  static const int bres_mode = getenv("LT_TC_BRES") ? atoi(getenv("LT_TC_BRES")) : 1;
+  const int bres_mode = opts().tc_bres;
   const long m_tiles_all = (long)p.tw * p.th * p.td * p.tn;
   int n_tiles = CoutP / Nt;
   if (bres_mode && terms != 0 && p.tma_epi && taps * CB <= 8 && Nt == 128 && CoutP >= 256 && CoutP / 64 <= sm_count() / 2 &&

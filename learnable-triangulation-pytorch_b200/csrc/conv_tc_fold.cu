@@ -386,10 +386,8 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.NF = p.K * p.NC;
   // x window: 16 rows keep 16-K+1 outputs per line, 32 rows keep 32-K+1; pick whichever computes fewer wasted rows
   // (64-wide volumes: K=3 -> 16 (80 rows per line vs 96), K=7 -> 32 (96 vs 112))
-  static const int wx_env = getenv("LT_FOLD_WX") ? atoi(getenv("LT_FOLD_WX")) : 0;
   p.WX = 16;
   if (p.W >= 32 && ceil_div(p.W, 32 - p.K + 1) * 32 < ceil_div(p.W, 16 - p.K + 1) * 16) p.WX = 32;
-  if ((wx_env == 16 || wx_env == 32) && p.W >= wx_env) p.WX = wx_env;
   p.wx_shift = p.WX == 32 ? 5 : 4;
   p.LINES = 128 / p.WX;
   p.OWt = p.WX - p.K + 1;
@@ -405,12 +403,12 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.stage_rows = p.LINES * p.OWt;
   p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
   p.scale = scale; p.shift = shift;
-  p.dbg = getenv("LT_FOLD_DBG") ? atoi(getenv("LT_FOLD_DBG")) : 0;
+  p.dbg = opts().fold_debug & 15;
   static unsigned long long* prof_buf = nullptr;
-  static const bool want_prof = getenv("LT_FOLD_PROF") != nullptr;
+  const bool want_prof = (opts().fold_debug & 16) != 0;
   if (want_prof && !prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long));
   p.prof = want_prof ? prof_buf : nullptr;
-  static const int fast_issue = getenv("LT_FOLD_FAST_ISSUE") ? atoi(getenv("LT_FOLD_FAST_ISSUE")) : 1;
+  const int fast_issue = opts().fold_fast_issue;
   p.fast_issue = (fast_issue && p.dbg == 0 && p.prof == nullptr) ? 1 : 0;
   if (want_prof) cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
   const int b_region = p.b_resident ? p.K * p.K * p.b_bytes : p.b_slots * p.b_bytes;
@@ -452,11 +450,10 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
       if (rc) return rc;
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(conv_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
   }
   long grid = p.tiles < sm_count() ? p.tiles : sm_count();
   conv_fold_kernel<<<(unsigned)grid, 320, smem, (cudaStream_t)stream>>>(tmA, tmB, tmOut, tmRes, p);

@@ -523,7 +523,7 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
   const bool cl = (chan_stride == 1 && J <= 32 && voxel_stride >= J);
   LT_REQUIRE(softmax >= 0 && softmax <= 2, "softargmax3d: mode must be 0 (ReLU), 1 (softmax) or 2 (ReLU, mass-normalised coordinates)");
   // ---- streaming path ----
-  static const int stream_mode = getenv("LT_SOFTARGMAX_FUSED") ? atoi(getenv("LT_SOFTARGMAX_FUSED")) : 1;
+  const int stream_mode = opts().softargmax_stream;
   if (stream_mode && softmax != 2 && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 8 == 0 && batch_stride % 4 == 0 &&
       nvox >= kStreamMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0 &&
       (!volumes_out || ((uintptr_t)volumes_out & 31) == 0)) {
@@ -538,16 +538,16 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
     f.mult = multiplier; f.softmax = softmax;
     LT_REQUIRE(f.T * f.vs * 4 <= kStreamLogitBytes && f.T * 12 <= kStreamCoordBytes, "softargmax stream: tile does not fit (vs=%d)", f.vs);
     LT_REQUIRE(f.total_tiles < (1L << 31), "softargmax stream: too many tiles");
-    static int max_ctas = 0;
-    if (!max_ctas) {
+    static DeviceOnce configured;
+    if (configured.first()) {
       cudaError_t e = cudaFuncSetAttribute(stream_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
       if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      max_ctas = 2 * sm_count();
-      if (max_ctas > kMaxStreamCtas) max_ctas = kMaxStreamCtas;
     }
+    int max_ctas = 2 * sm_count();
+    if (max_ctas > kMaxStreamCtas) max_ctas = kMaxStreamCtas;
     const int G = f.total_tiles < max_ctas ? (int)f.total_tiles : max_ctas;
     f.G = G;
     float* w = reinterpret_cast<float*>(workspace);

@@ -620,12 +620,11 @@ static int launch_unproject(const float* features, const float* proj, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const bool stored = V <= kMaxStoredViews;
   const bool pow2q = (units & (units - 1)) == 0;
-  static const int v2_mode = getenv("LT_UNPROJECT_V2") ? atoi(getenv("LT_UNPROJECT_V2")) : 1;
+  const int v2_mode = opts().unproject_v2;
   if (v2_mode && C == 32 && agg == LT_AGG_SOFTMAX && partial == 0 && V <= 8 && (long)V * h * w * C < (1L << 30)) {
     // variants (measured on B200 at config #2 shapes, see profiles/): 8 lanes x 4 channels per voxel at 4 CTAs/SM was the
     // round-1 default (0.29-0.31 ms); 4 lanes x 8 channels halves the per-voxel ray / shuffle / address overhead
-    static const int cpl = getenv("LT_UNPROJECT_CPL") ? atoi(getenv("LT_UNPROJECT_CPL")) : 4;
-    static const int lb = getenv("LT_UNPROJECT_LB") ? atoi(getenv("LT_UNPROJECT_LB")) : 0;
+    const int cpl = opts().unproject_cpl, lb = opts().unproject_lb;
     if (cpl == 8) {
       const int vpb8 = 64;
       long blocks8 = (nvox + vpb8 - 1) / vpb8;
@@ -651,23 +650,7 @@ static int launch_unproject(const float* features, const float* proj, const floa
     if (V <= 2) unproject_fast_kernel<GG, 2, CPL><<<grid, 256, 0, st>>>(p);                 \
     else if (V <= 4) unproject_fast_kernel<GG, 4, CPL><<<grid, 256, 0, st>>>(p);            \
     else unproject_fast_kernel<GG, 8, CPL><<<grid, 256, 0, st>>>(p)
-    // (measured on B200: the 8-channel-per-lane variant halves the per-lane ray/weight overhead but drops occupancy to
-    //  2 CTAs/SM and is 45 % slower at C = 32, so it is only used on request)
-    static const bool wide_lanes = getenv("LT_UNPROJECT_CPL8") != nullptr;
-    if (wide_lanes && C % 8 == 0) {
-      p.G = C / 8;
-      const int vpb8 = 256 / p.G;
-      long blocks8 = (nvox + vpb8 - 1) / vpb8;
-      if (blocks8 > (long)sm_count() * 8) blocks8 = (long)sm_count() * 8;
-      grid.x = (unsigned)blocks8;
-      switch (p.G) {
-        case 1: LT_UNPROJ_FAST(1, 8); break;
-        case 2: LT_UNPROJ_FAST(2, 8); break;
-        case 4: LT_UNPROJ_FAST(4, 8); break;
-        case 8: LT_UNPROJ_FAST(8, 8); break;
-        default: LT_UNPROJ_FAST(16, 8); break;
-      }
-    } else {
+    {
       switch (G) {
         case 1: LT_UNPROJ_FAST(1, 4); break;
         case 2: LT_UNPROJ_FAST(2, 4); break;

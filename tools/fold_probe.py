@@ -1,13 +1,13 @@
-"""Time one kw-folded conv (3^3 32->32 and 7^3 32->16 at 64^3, B=8) under the LT_FOLD_DBG knobs."""
+"""Time one kw-folded conv (3^3 32->32 and 7^3 32->16 at 64^3, B=8) under the lt_options.fold_debug settings (LT_OPT_FOLD_DEBUG)."""
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) == 1:
-    for dbg in ("0", "1", "2", "3", "0p"):   # "0p": production path with the in-kernel wait counters (LT_FOLD_PROF)
-        env = dict(os.environ, LT_FOLD_DBG=dbg[0])
+    for dbg in ("0", "1", "2", "3", "0p"):   # "0p": production path with the in-kernel wait counters (fold_debug = 16)
+        env = dict(os.environ, LT_OPT_FOLD_DEBUG=dbg[0])
         if dbg.endswith("p"):
-            env["LT_FOLD_PROF"] = "1"
+            env["LT_OPT_FOLD_DEBUG"] = "16"
         r = subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True)
-        print("LT_FOLD_DBG=" + dbg, r.stdout.strip())
+        print("fold_debug=" + dbg, r.stdout.strip())
         print("\n".join(sorted(set(l for l in r.stderr.strip().splitlines() if "fold prof" in l))[:8]))
     sys.exit(0)
 import torch

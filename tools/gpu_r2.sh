@@ -18,6 +18,15 @@ for s in $STAGES; do
     benchfull) LT_BENCH_TIMELINE=$O/${T}_timeline_tc.json timeout 1200 python bench.py --steps 20 --warmup 3 2> $O/${T}_bench_tc.err | tail -1 | tee $O/${T}_bench_tc.json | python -c "$show" ;;
     benchref) timeout 600 python bench.py --impl reference --steps 1 --warmup 1 2>/dev/null | tail -1 | tee $O/${T}_bench_reference.json | cut -c1-300 ;;
     smoke) timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -4 | tee $O/${T}_smoke.log ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/${T}_launches_tc.csv python tools/profile_step.py --mode tc --repeat 2 > $O/ncu_launches.log 2>&1; wc -l $O/${T}_launches_tc.csv ;;
+    ncufull)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:unproject -c 1 -f -o $O/${T}_prof_unproject python tools/profile_step.py --stage post --repeat 1 > $O/ncu_unproject.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"stream_|softargmax" -c 3 -f -o $O/${T}_prof_softargmax python tools/profile_step.py --stage v2v --repeat 1 > $O/ncu_softargmax.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_fold_kernel|v2v_tail" -c 3 -f -o $O/${T}_prof_conv_fold python tools/profile_step.py --stage v2v --repeat 1 > $O/ncu_conv_fold.log 2>&1
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_pair_kernel -s 40 -c 4 -f -o $O/${T}_prof_conv_pair python tools/profile_step.py --stage all --repeat 1 > $O/ncu_conv_pair.log 2>&1
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 20 -c 3 -f -o $O/${T}_prof_conv_tc python tools/profile_step.py --stage all --repeat 1 > $O/ncu_conv_tc.log 2>&1
+      ls -la $O/*.ncu-rep ;;
+    postprobe) timeout 600 python tools/post_probe.py 2>&1 | tee $O/${T}_post_probe.log | cut -c1-300 ;;
     nopair) LT_TC_PAIR=0 LT_BENCH_TIMELINE=$O/${T}_timeline_nopair.json timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-gpu 2> $O/${T}_bench_nopair.err | tail -1 | tee $O/${T}_bench_nopair.json | python -c "$show" ;;
   esac
   echo "== stage $s done"

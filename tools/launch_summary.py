@@ -2,7 +2,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
 tools/profile_step.py --repeat 2 into a per-kernel markdown table (second forward only: the first one also packs weights).
 
-    python tools/launch_summary.py launches.csv out.md "title"
+    python tools/launch_summary.py launches.csv out.md "title" [traffic.json]
 """
 import csv
 import re
@@ -50,6 +50,22 @@ def main():
               % (tot, sum(a[0] for a in agg.values()), foreign)]
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    if len(sys.argv) > 4:
+        # per-launch DRAM traffic (read + write bytes) per kernel family, for bench.py's `roofline*.traffic`
+        import json
+        fam = {}
+        for name, a in agg.items():
+            short = name.split("::")[-1].split("<")[0]
+            key = ("unproject" if "unproject" in short else "softargmax" if ("softargmax" in short or short.startswith("stream_")) else short)
+            f = fam.setdefault(key, [0, 0.0])
+            f[0] += a[0] if key not in ("unproject", "softargmax") else 0
+            f[1] += (a[2] + a[3]) * 1e6
+        traffic = {"_source": "%s (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one steady-state forward, config #2, B=8): %s"
+                   % (src.split("/")[-1], title),
+                   "unit": "bytes per launch (read + write); unproject / softargmax: all kernels of the stage together"}
+        for key, (cnt, nbytes) in fam.items():
+            traffic[key] = nbytes / max(cnt, 1)
+        json.dump(traffic, open(sys.argv[4], "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -10,10 +10,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = [
-    ("unproject", {"LT_UNPROJECT_V2": "0"}), ("unproject", {"LT_UNPROJECT_CPL": "4"}), ("unproject", {"LT_UNPROJECT_CPL": "4", "LT_UNPROJECT_LB": "5"}),
-    ("unproject", {"LT_UNPROJECT_CPL": "8"}), ("unproject", {"LT_UNPROJECT_CPL": "8", "LT_UNPROJECT_LB": "3"}),
-    ("softargmax20", {"LT_SOFTARGMAX_FUSED": "0"}), ("softargmax20", {"LT_SOFTARGMAX_FUSED": "1"}),
-    ("softargmax32", {"LT_SOFTARGMAX_FUSED": "0"}), ("softargmax32", {"LT_SOFTARGMAX_FUSED": "1"}),
+    ("unproject", {"LT_OPT_UNPROJECT_V2": "0"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_LB": "5"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "8"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3"}),
+    ("softargmax20", {"LT_OPT_SOFTARGMAX_STREAM": "0"}), ("softargmax20", {"LT_OPT_SOFTARGMAX_STREAM": "1"}),
+    ("softargmax32", {"LT_OPT_SOFTARGMAX_STREAM": "0"}), ("softargmax32", {"LT_OPT_SOFTARGMAX_STREAM": "1"}),
 ]
 
 if len(sys.argv) == 1:
