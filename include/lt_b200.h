@@ -211,11 +211,15 @@ int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, in
  *   (td, th, tw, ci, co) is read from w[base + td*s_td + th*s_th + tw*s_tw + ci*s_ci + co*s_co] (nn.Conv: (Cout, Cin, k...);
  *   nn.ConvTranspose: (Cin, Cout, k...); stride phases of a transposed conv: a tap sub-lattice walked with negative strides).
  * lt_fold_bn_fwd: eval-mode BatchNorm (pose_resnet.py:30-31, v2v.py:12) + conv bias -> per-channel scale / shift [CP] (double
- *   arithmetic, rounded once); mean == NULL: no BatchNorm. */
+ *   arithmetic, rounded once); mean == NULL: no BatchNorm.
+ * lt_absmax_fwd: float bit pattern of max|w| over n elements.  Passed (optionally, else NULL) to the two calls above it selects the
+ *   power-of-two filter pre-scale S = 2^(9 - floor(log2 max|w|)) of the tensor-core path: the gathered filter is multiplied by S,
+ *   the folded scale by 1 / S (exact), so that the unscaled low halves of the split-fp16 weights stay normal numbers. */
+int lt_absmax_fwd(const float* w, long n, unsigned int* out_bits, void* stream);
 int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, long s_th, long s_tw, long s_ci, long s_co, int KD, int KH, int KW,
-                               int Cin, int CinP, int Cout, int CoutP, float* out, void* stream);
+                               int Cin, int CinP, int Cout, int CoutP, const unsigned int* absmax_bits, float* out, void* stream);
 int lt_fold_bn_fwd(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
-                   int C, int CP, float* scale, float* shift, void* stream);
+                   int C, int CP, const unsigned int* absmax_bits, float* scale, float* shift, void* stream);
 
 /* CTA-pair weight packing: float32 [taps][Cin][Cout] (DEVICE) -> fp16 [taps][Cin/32][CoutP][32 hi | 32 lo] (128-byte rows),
  * CoutP = round_up(Cout, 128).  lt_conv_pair_eligible: 1 if LT_CONV_TC_PAIR covers this launch (shape / tiling heuristics),

@@ -70,8 +70,9 @@ SIGNATURES = {
     "lt_conv_nd_fwd": (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6 + [c_int, c_void_p]),
     "lt_conv_tc_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "lt_conv_gather_weights_fwd": (c_int, [c_void_p] + [c_long] * 6 + [c_int] * 7 + [c_void_p, c_void_p]),
-    "lt_fold_bn_fwd": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "lt_absmax_fwd": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
+    "lt_conv_gather_weights_fwd": (c_int, [c_void_p] + [c_long] * 6 + [c_int] * 7 + [c_void_p, c_void_p, c_void_p]),
+    "lt_fold_bn_fwd": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lt_conv_pair_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_pair_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_conv_pair_eligible": (c_int, [ctypes.POINTER(ConvDesc)]),
@@ -256,15 +257,20 @@ def conv_tc_pack_weights(w_tap_ci_co, packed, taps, cin, cout):
     _check(lib().lt_conv_tc_pack_weights(_ptr(w_tap_ci_co), _ptr(packed), taps, cin, cout, _stream()), "lt_conv_tc_pack_weights")
 
 
-def conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, out):
+def absmax(w, out_bits):
+    """out_bits: int32[1] device tensor receiving the float bit pattern of max|w|."""
+    _check(lib().lt_absmax_fwd(_ptr(w), w.numel(), _ptr(out_bits), _stream()), "lt_absmax_fwd")
+
+
+def conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, out, absmax_bits=None):
     """w: the module's own filter tensor; strides = element strides of (td, th, tw, ci, co); out float32 [taps][cin_p][cout_p]."""
     _check(lib().lt_conv_gather_weights_fwd(_ptr(w), base, *[int(v) for v in strides], k[0], k[1], k[2], cin, cin_p, cout, cout_p,
-                                            _ptr(out), _stream()), "lt_conv_gather_weights_fwd")
+                                            _ptr(absmax_bits), _ptr(out), _stream()), "lt_conv_gather_weights_fwd")
 
 
-def fold_bn(gamma, beta, mean, var, bias, eps, c, cp, scale, shift):
-    _check(lib().lt_fold_bn_fwd(_ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), _ptr(bias), float(eps), c, cp, _ptr(scale), _ptr(shift),
-                                _stream()), "lt_fold_bn_fwd")
+def fold_bn(gamma, beta, mean, var, bias, eps, c, cp, scale, shift, absmax_bits=None):
+    _check(lib().lt_fold_bn_fwd(_ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), _ptr(bias), float(eps), c, cp, _ptr(absmax_bits),
+                                _ptr(scale), _ptr(shift), _stream()), "lt_fold_bn_fwd")
 
 
 def conv_pair_weight_bytes(taps, cin, cout):

@@ -85,6 +85,19 @@ __device__ __forceinline__ float4 load_s32x4(const sh_t* row, int c) {
   return make_float4(join_s32(h[0], l[0]), join_s32(h[1], l[1]), join_s32(h[2], l[2]), join_s32(h[3], l[3]));
 }
 
+// Power-of-two pre-scale of a layer's filter (tensor-core path): S = 2^(9 - floor(log2 max|w|)) puts max|w| * S into
+// [512, 1024), so that the UNSCALED low parts of every weight down to 2^-13 of the largest stay normal fp16 numbers (full
+// ~22-bit operands); Kaiming-sized filters (|w| ~ 0.03) would otherwise keep only ~2^-20 relative precision, which a
+// 152-layer trunk amplifies to ~1.5e-4 at the features (measured, profiles/r02_precision.md).  1 / S is folded into the
+// epilogue scale (exact).  absmax_bits: the float bit pattern of max|w| (lt_absmax_fwd), or null for "no scaling".
+__device__ __forceinline__ float weight_pow2_scale(const unsigned* absmax_bits) {
+  if (!absmax_bits) return 1.0f;
+  const unsigned b = *absmax_bits;
+  const int e = (int)(b >> 23) - 127;     // floor(log2(max)) for normal floats
+  if (b == 0u || e < -100 || e > 100) return 1.0f;
+  return exp2f((float)(9 - e));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

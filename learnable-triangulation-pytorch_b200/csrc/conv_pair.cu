@@ -34,6 +34,7 @@ struct PairExtra {
   long m_tiles, m_pairs, total_tiles;
   int stage_bytes, off_out, off_res, off_bar;
   int b_rows;   // weight rows per chunk = CoutP
+  int res_bufs; // residual staging buffers (power of two): 16 KB blocks requested this many blocks ahead
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -91,6 +92,7 @@ __device__ __forceinline__ uint32_t make_idesc_f16_m256(int n) {
 }
 
 constexpr int kPairEpiWarps = 8;
+constexpr int kMaxResBufs = 4;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -99,13 +101,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* out_stage = smem + x.off_out;   // 2 x 16 KB
-  uint8_t* res_stage = smem + x.off_res;   // 2 x 16 KB
+  uint8_t* res_stage = smem + x.off_res;   // res_bufs x 16 KB
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + x.off_bar);
   uint64_t* empty = full + p.stages;
   uint64_t* acc_full = empty + p.stages;   // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint64_t* res_full = acc_empty + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = acc_empty + 2;      // [kMaxResBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kMaxResBufs);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -114,7 +116,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kPairEpiWarps); mbar_init(&res_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kPairEpiWarps); }
+    for (int i = 0; i < kMaxResBufs; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
@@ -206,17 +209,21 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
     const long my_tiles = (x.total_tiles > pair_idx) ? (x.total_tiles - 1 - pair_idx) / n_pairs + 1 : 0;
     const long total_blocks = my_tiles * nblk;
+    // The residual tiles stream through RB 16 KB buffers indexed by a block counter that runs across tiles: block c lives in
+    // buffer c % RB and is requested RB blocks ahead (a K-short 1x1 expand layer reads as many residual bytes as operand bytes:
+    // with two buffers its epilogue ran at the latency of one TMA round trip per block)
+    const int RB = x.res_bufs, rb_shift = (RB == 4) ? 2 : 1;
     auto issue_res = [&](long c) {   // leader thread only: residual block c of this CTA's tile sequence
       const long tile_c = pair_idx + (c / nblk) * n_pairs;
       const int blk = (int)(c % nblk);
       int a0, a1, a2, a3, an;
       decode(tile_c, a0, a1, a2, a3, an);
-      const int buf = (int)(c & 1);
+      const int buf = (int)(c & (RB - 1));
       mbar_expect_tx(&res_full[buf], 16384u);
       tma_load_5d(res_stage + buf * 16384, &tmRes, &res_full[buf], an * esz + blk * 32 * esz, a0, a1, a2, a3);
     };
     if (leader && has_res)
-      for (long c = 0; c < 2 && c < total_blocks; ++c) issue_res(c);
+      for (long c = 0; c < RB && c < total_blocks; ++c) issue_res(c);
     uint32_t it = 0;
     long c = 0;
     for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
@@ -228,7 +235,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.Nt;
       for (int i = 0; i < nblk; ++i, ++c) {
-        const int buf = (int)(c & 1);
+        const int buf = (int)(c & 1);              // output staging buffer
+        const int rbuf = (int)(c & (RB - 1));      // residual staging buffer
         float v[16], r[16];
         {
           uint32_t t1[16];
@@ -243,19 +251,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
         if (has_res) {
-          mbar_wait(&res_full[buf], (uint32_t)((c >> 1) & 1));
-          epi_load16(smem_u32(res_stage + buf * 16384), row, half, p.out_format, r);
+          mbar_wait(&res_full[rbuf], (uint32_t)((c >> rb_shift) & 1));
+          epi_load16(smem_u32(res_stage + rbuf * 16384), row, half, p.out_format, r);
         }
         epi_activate16(v, r, p.residual, p.relu);
         if (leader) bulk_wait_read<1>();      // the store that last read out_stage[buf] (two blocks ago) is done with it
-        epi_bar_sync();                       // also: every thread has finished reading res_stage[buf]
+        epi_bar_sync();                       // also: every thread has finished reading res_stage[rbuf]
         epi_store16(smem_u32(out_stage + buf * 16384), row, half, p.out_format, v);
         fence_proxy_async();
         epi_bar_sync();
         if (leader) {
           tma_store_5d(&tmOut, out_stage + buf * 16384, cbase + i * 32 * esz, ow0, oh0, od0, nb0);
           bulk_commit();
-          if (has_res && c + 2 < total_blocks) issue_res(c + 2);
+          if (has_res && c + RB < total_blocks) issue_res(c + RB);
         }
       }
     }
@@ -294,15 +302,18 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
     if (t < best) { best = t; best_nt = nt; }
   }
   if (!best_nt) return false;
-  // tiny grids (deep V2V levels): the split-K path of the one-CTA kernel spreads the K loop over the SMs instead
-  if (m_pairs * (CoutP / best_nt) * 4 < P && nchunks >= 16) return false;
-  (void)d;
+  // small grids: latency-bound; the one-CTA kernel has the cheaper prologue and a split-K path that spreads the K loop over
+  // the SMs (measured: 2x2 taps 2048 -> 256 at 12x12 = 36 pair tiles with 256 chunks each: 70 us here, 59 us there)
+  const long best_tiles = m_pairs * (CoutP / best_nt);
+  if (best_tiles * 4 < P || (best_tiles * 2 <= P && nchunks >= 64)) return false;
   plan->Nt = best_nt;
   plan->n_tiles = CoutP / best_nt;
   plan->m_tiles = m_tiles;
   plan->m_pairs = m_pairs;
   const int stage_bytes = kATileBytes + best_nt * 64;
-  int stages = (227 * 1024 - 1024 - 65536 - 512) / stage_bytes;
+  // shared memory: operand ring + 2 output staging tiles + (residual layers) 4 residual staging tiles, 16 KB each
+  plan->res_bufs = d->residual != LT_RES_NONE ? kMaxResBufs : 0;
+  int stages = (227 * 1024 - 1024 - 32768 - plan->res_bufs * 16384 - 512) / stage_bytes;
   if (stages > 8) stages = 8;
   plan->stages = stages;
   const long tiles = m_pairs * plan->n_tiles;
@@ -325,8 +336,9 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   const int ring = plan.stages * x.stage_bytes;
   x.off_out = (ring + 1023) & ~1023;
   x.off_res = x.off_out + 32768;
-  x.off_bar = x.off_res + 32768;
-  const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 6) * 8 + 16 + 1024;
+  x.off_bar = x.off_res + plan.res_bufs * 16384;
+  x.res_bufs = plan.res_bufs ? plan.res_bufs : 2;
+  const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 4 + kMaxResBufs) * 8 + 16 + 1024;
   if (smem > 227 * 1024) return fail(LT_ERR_INVALID, "conv_pair: shared memory budget exceeded (%zu)", smem);
   static DeviceOnce configured;
   if (configured.first()) {

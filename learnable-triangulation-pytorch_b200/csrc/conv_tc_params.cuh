@@ -38,6 +38,7 @@ struct PairPlan {
   long m_tiles;      // 128-position M tiles
   long m_pairs;      // ceil(m_tiles / 2)
   int stages;        // operand ring depth
+  int res_bufs;      // residual staging tiles (0 without a residual)
   unsigned grid;     // CTAs (2 per pair)
 };
 bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* plan);   // false: shape not covered by the pair kernel

@@ -199,25 +199,34 @@ static inline unsigned grid_for(long total, int per_block = 256) {
 // Element (td, th, tw, ci, co) of the source filter sits at w[base + td*s_td + th*s_th + tw*s_tw + ci*s_ci + co*s_co]: plain convs
 // (Cout, Cin, KD, KH, KW), transposed convs (Cin, Cout, ...) and their stride phases (a sub-lattice of taps walked with negative
 // strides) are all affine maps, so ONE kernel replaces the permute / slice / pad / contiguous chain.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ w, long n, unsigned* __restrict__ out_bits) {
+  float m = 0.0f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0f && m < INFINITY) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
 __global__ void __launch_bounds__(256) gather_weights_kernel(const float* __restrict__ w, long base, long s_td, long s_th, long s_tw, long s_ci,
                                                              long s_co, int KH, int KW, int Cin, int CinP, int Cout, int CoutP, long total,
-                                                             float* __restrict__ out) {
+                                                             const unsigned* __restrict__ absmax_bits, float* __restrict__ out) {
+  const float S = weight_pow2_scale(absmax_bits);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int co = (int)(i % CoutP);
     long r = i / CoutP;
     const int ci = (int)(r % CinP);
     const int tap = (int)(r / CinP);
     const int tw = tap % KW, th = (tap / KW) % KH, td = tap / (KW * KH);
-    out[i] = (ci < Cin && co < Cout) ? w[base + td * s_td + th * s_th + tw * s_tw + ci * s_ci + co * s_co] : 0.0f;
+    out[i] = (ci < Cin && co < Cout) ? w[base + td * s_td + th * s_th + tw * s_tw + ci * s_ci + co * s_co] * S : 0.0f;
   }
 }
 
 // y = acc * scale + shift with scale = gamma / sqrt(var + eps), shift = beta - mean * scale (+ conv_bias * scale); double arithmetic,
 // rounded once.  Any of gamma / beta / bias may be null; mean == null means "no BatchNorm" (scale 1, shift = bias).
 __global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias, double eps,
-                               int C, int CP, float* scale, float* shift) {
+                               int C, int CP, const unsigned* absmax_bits, float* scale, float* shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= CP) return;
+  const double inv_s = 1.0 / (double)weight_pow2_scale(absmax_bits);   // the packed filter carries S: acc = S * sum x w
   double sc = 0.0, sh = 0.0;
   if (c < C) {
     if (mean) {
@@ -229,7 +238,7 @@ __global__ void fold_bn_kernel(const float* gamma, const float* beta, const floa
       sh = bias ? (double)bias[c] : 0.0;
     }
   }
-  scale[c] = (float)sc;
+  scale[c] = (float)(sc * inv_s);
   shift[c] = (float)sh;
 }
 
@@ -249,24 +258,37 @@ __global__ void __launch_bounds__(256) feature_scatter_kernel(const float* __res
 
 }  // namespace lt
 
+extern "C" int lt_absmax_fwd(const float* w, long n, unsigned int* out_bits, void* stream) {
+  using namespace lt;
+  LT_REQUIRE(w && out_bits && n > 0, "absmax: bad arguments");
+  cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(unsigned int), (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(LT_ERR_CUDA, "absmax: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  long blocks = (n + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, n, out_bits);
+  LT_CHECK_LAUNCH("absmax_kernel");
+  return LT_OK;
+}
+
 extern "C" int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, long s_th, long s_tw, long s_ci, long s_co, int KD, int KH,
-                                          int KW, int Cin, int CinP, int Cout, int CoutP, float* out, void* stream) {
+                                          int KW, int Cin, int CinP, int Cout, int CoutP, const unsigned int* absmax_bits, float* out,
+                                          void* stream) {
   using namespace lt;
   LT_REQUIRE(w && out && KD > 0 && KH > 0 && KW > 0 && Cin > 0 && Cout > 0 && CinP >= Cin && CoutP >= Cout, "conv_gather_weights: bad arguments");
   const long total = (long)KD * KH * KW * CinP * CoutP;
   long blocks = (total + 255) / 256;
   if (blocks > 4096) blocks = 4096;
   gather_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, base, s_td, s_th, s_tw, s_ci, s_co, KH, KW, Cin, CinP, Cout, CoutP,
-                                                                              total, out);
+                                                                              total, absmax_bits, out);
   LT_CHECK_LAUNCH("gather_weights_kernel");
   return LT_OK;
 }
 
 extern "C" int lt_fold_bn_fwd(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
-                              int C, int CP, float* scale, float* shift, void* stream) {
+                              int C, int CP, const unsigned int* absmax_bits, float* scale, float* shift, void* stream) {
   using namespace lt;
   LT_REQUIRE(scale && shift && C > 0 && CP >= C && (!mean || var), "fold_bn: bad arguments");
-  fold_bn_kernel<<<ceil_div(CP, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, (double)eps, C, CP, scale, shift);
+  fold_bn_kernel<<<ceil_div(CP, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, (double)eps, C, CP, absmax_bits, scale, shift);
   LT_CHECK_LAUNCH("fold_bn_kernel");
   return LT_OK;
 }

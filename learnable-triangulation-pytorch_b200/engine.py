@@ -89,6 +89,7 @@ class NativeEngine:
         self.use_fold = os.environ.get("LT_TC_FOLD", "1") == "1"          # kw-folded kernel for Cin=32 cubic layers
         self.use_pair = os.environ.get("LT_TC_PAIR", "1") == "1"          # CTA-pair kernel for Cout % 128 == 0 layers
         self.use_tail = os.environ.get("LT_TC_TAIL", "1") == "1"          # fused back1 + back2 + output kernel
+        self.weight_prescale = os.environ.get("LT_TC_WSCALE", "1") == "1"   # power-of-two filter pre-scale (common.cuh)
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
@@ -130,7 +131,12 @@ class NativeEngine:
             cin_p = max(cin, cin_pad or 0)
             cout_p = _round_up(cout, 4)
         wp = torch.empty((taps, cin_p, cout_p), dtype=torch.float32, device=dev)
-        capi.conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, wp)
+        amax = None
+        if use_tc and self.weight_prescale:
+            # power-of-two pre-scale of the whole filter tensor (all phases of a transposed conv share it): common.cuh
+            amax = torch.empty(1, dtype=torch.int32, device=dev)
+            capi.absmax(w, amax)
+        capi.conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, wp, amax)
         if use_tc:
             packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
             capi.conv_tc_pack_weights(wp, packed, taps, cin_p, cout_p)
@@ -153,9 +159,9 @@ class NativeEngine:
         pk.shift = torch.empty(cout_p, dtype=torch.float32, device=dev)
         if bn is not None:
             capi.fold_bn(_f32(bn.weight), _f32(bn.bias), _f32(bn.running_mean), _f32(bn.running_var), _f32(bias), bn.eps, cout, cout_p,
-                         pk.scale, pk.shift)
+                         pk.scale, pk.shift, amax)
         else:
-            capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, cout_p, pk.scale, pk.shift)
+            capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, cout_p, pk.scale, pk.shift, amax)
         return pk
 
     def _pack_conv(self, conv, bn, cin_pad=None, **kw):

@@ -22,7 +22,7 @@ class Recorder:
         # same shape rule as csrc/conv_pair.cu pair_plan (without its wave-count heuristics): staged epilogue + Cout % 128 == 0
         monkeypatch.setattr(capi, "conv_pair_eligible", lambda d: d.Cout % 128 == 0 and d.FC % 32 == 0 and d.Cout <= d.FC and
                             d.N * d.OD * d.OH * d.OW >= 128 * 40)
-        for name in ("v2v_tail", "conv_gather_weights", "fold_bn", "conv_pair_pack_weights", "conv_fold_pack_weights", "stem_s2d", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
+        for name in ("v2v_tail", "absmax", "conv_gather_weights", "fold_bn", "conv_pair_pack_weights", "conv_fold_pack_weights", "stem_s2d", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
                      "s32_to_f32", "cl_to_cf", "conv_tc_pack_weights"):
             monkeypatch.setattr(capi, name, rec(name))
         monkeypatch.setattr(capi, "lib", lambda: None)
@@ -87,7 +87,7 @@ def test_engine_plan_is_consistent(monkeypatch, mode, layers):
     tail = sum(1 for c in rec.calls if c[0] == "v2v_tail")      # tc mode: back1 + back2 + output fused into one launch
     assert tail == (1 if mode == "tc" else 0)
     assert v2v == 1 + 20 * 2 + 3 + 5 * 8 + (0 if tail else 2 + 1), v2v
-    assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights", "conv_pair_pack_weights", "conv_gather_weights", "fold_bn")) + 2   # softargmax = 3 launches
+    assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights", "conv_pair_pack_weights", "conv_gather_weights", "fold_bn", "absmax")) + 2   # softargmax = 3 launches
     if mode == "tc":
         simt = [c for c in convs if c[1][0] == capi.CONV_SIMT]
         assert len(simt) == 0, "every conv runs on the tensor-core kernels"
