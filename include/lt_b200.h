@@ -190,6 +190,12 @@ typedef struct lt_conv_desc {
   int relu;                  /* apply max(x,0) */
   int residual;              /* lt_residual; residual tensor has the output tensor's shape/format */
   int in_format, out_format; /* lt_format */
+  int ogd, ogh, ogw;         /* output groups (0 or 1 = none): with G = ogd*ogh*ogw > 1 the Cout output channels are G blocks of
+                                Cout/G channels, block g = (a*ogh + b)*ogw + c being written (and its residual read) at the output
+                                offset (ood + a, ooh + b, oow + c) with channel index 0..Cout/G-1 (FC == Cout/G).  A k2 s2
+                                transposed conv (v2v.py:54-66) is ONE 1x1x1 GEMM this way: N = 8 x Cout, osd=osh=osw=2, ogd=ogh=ogw=2;
+                                scale/shift carry Cout entries (the per-channel values repeated G times).  LT_CONV_TC / _PAIR only */
+  int reserved0;             /* set to 0 (keeps the pointer below 8-byte aligned without implicit padding) */
   void* workspace;           /* optional device scratch for split-K (layers with fewer M x N tiles than half the SMs:
                                 the K loop is spread over more CTAs and summed in a fixed order); NULL = never split */
   size_t workspace_bytes;    /* size of workspace; a split is only used when its partial tiles fit */
@@ -217,7 +223,8 @@ int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, in
  *   the folded scale by 1 / S (exact), so that the unscaled low halves of the split-fp16 weights stay normal numbers. */
 int lt_absmax_fwd(const float* w, long n, unsigned int* out_bits, void* stream);
 int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, long s_th, long s_tw, long s_ci, long s_co, int KD, int KH, int KW,
-                               int Cin, int CinP, int Cout, int CoutP, const unsigned int* absmax_bits, float* out, void* stream);
+                               int Cin, int CinP, int Cout, int CoutP, const unsigned int* absmax_bits, float* out, int out_ld,
+                               int out_col0, void* stream);   /* out row length (0 = CoutP) and first column: column blocks of a wider filter */
 int lt_fold_bn_fwd(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
                    int C, int CP, const unsigned int* absmax_bits, float* scale, float* shift, void* stream);
 
@@ -231,9 +238,11 @@ int lt_conv_pair_eligible(const lt_conv_desc* desc);
 /* Fused tail of the V2V network (v2v.py:154-160,168-169): back_layers[1], back_layers[2] (1x1x1 conv 32->32 + BN + ReLU each) and
  * output_layer (1x1x1 conv 32->J + bias) as one kernel: x split-fp16 [rows][32 hi | 32 lo] -> logits float32 [rows][FC]
  * (J <= FC <= 32, FC % 4 == 0; channels J..FC-1 are written as bias3 = 0).  w1/w2/w3: lt_conv_pair_pack_weights(taps 1, Cin 32)
- * buffers; scale/shift: folded BatchNorm ([32] each); bias3 [32] zero padded. */
+ * buffers; scale/shift: folded BatchNorm ([32] each); scale3 / bias3 [32]: output affine (lt_fold_bn_fwd without BatchNorm: the
+ * inverse filter pre-scale and the bias, zero padded). */
 int lt_v2v_tail_fwd(const void* x, const void* w1, const void* w2, const void* w3, const float* scale1, const float* shift1,
-                    const float* scale2, const float* shift2, const float* bias3, float* logits, long rows, int FC, void* stream);
+                    const float* scale2, const float* shift2, const float* scale3, const float* bias3, float* logits, long rows, int FC,
+                    void* stream);
 
 /* kw-folded weight packing: float32 [K^3][32][Cout] (DEVICE) -> split-fp16 [kd][kh][kw*NC + co][64], NC = round_up(Cout, 16). */
 size_t lt_conv_fold_weight_bytes(int K, int Cout);

@@ -33,7 +33,7 @@ class ConvDesc(ctypes.Structure):
         "FD", "FH", "FW", "FC",
         "osd", "osh", "osw",
         "ood", "ooh", "oow",
-        "relu", "residual", "in_format", "out_format")] + [("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+        "relu", "residual", "in_format", "out_format", "ogd", "ogh", "ogw", "reserved0")] + [("workspace", c_void_p), ("workspace_bytes", c_size_t)]
 
 
 class Options(ctypes.Structure):
@@ -71,12 +71,12 @@ SIGNATURES = {
     "lt_conv_tc_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_absmax_fwd": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
-    "lt_conv_gather_weights_fwd": (c_int, [c_void_p] + [c_long] * 6 + [c_int] * 7 + [c_void_p, c_void_p, c_void_p]),
+    "lt_conv_gather_weights_fwd": (c_int, [c_void_p] + [c_long] * 6 + [c_int] * 7 + [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_fold_bn_fwd": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lt_conv_pair_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_pair_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_conv_pair_eligible": (c_int, [ctypes.POINTER(ConvDesc)]),
-    "lt_v2v_tail_fwd": (c_int, [c_void_p] * 10 + [c_long, c_int, c_void_p]),
+    "lt_v2v_tail_fwd": (c_int, [c_void_p] * 11 + [c_long, c_int, c_void_p]),
     "lt_conv_fold_weight_bytes": (c_size_t, [c_int, c_int]),
     "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
@@ -262,10 +262,11 @@ def absmax(w, out_bits):
     _check(lib().lt_absmax_fwd(_ptr(w), w.numel(), _ptr(out_bits), _stream()), "lt_absmax_fwd")
 
 
-def conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, out, absmax_bits=None):
-    """w: the module's own filter tensor; strides = element strides of (td, th, tw, ci, co); out float32 [taps][cin_p][cout_p]."""
+def conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, out, absmax_bits=None, out_ld=0, out_col0=0):
+    """w: the module's own filter tensor; strides = element strides of (td, th, tw, ci, co); out float32 [taps][cin_p][out_ld],
+    columns [out_col0, out_col0 + cout_p) are written."""
     _check(lib().lt_conv_gather_weights_fwd(_ptr(w), base, *[int(v) for v in strides], k[0], k[1], k[2], cin, cin_p, cout, cout_p,
-                                            _ptr(absmax_bits), _ptr(out), _stream()), "lt_conv_gather_weights_fwd")
+                                            _ptr(absmax_bits), _ptr(out), out_ld, out_col0, _stream()), "lt_conv_gather_weights_fwd")
 
 
 def fold_bn(gamma, beta, mean, var, bias, eps, c, cp, scale, shift, absmax_bits=None):
@@ -285,8 +286,8 @@ def conv_pair_eligible(desc):
     return bool(lib().lt_conv_pair_eligible(ctypes.byref(desc)))
 
 
-def v2v_tail(x, w1, w2, w3, scale1, shift1, scale2, shift2, bias3, logits, rows, fc):
-    _check(lib().lt_v2v_tail_fwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(scale1), _ptr(shift1), _ptr(scale2), _ptr(shift2), _ptr(bias3),
+def v2v_tail(x, w1, w2, w3, scale1, shift1, scale2, shift2, scale3, bias3, logits, rows, fc):
+    _check(lib().lt_v2v_tail_fwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(scale1), _ptr(shift1), _ptr(scale2), _ptr(shift2), _ptr(scale3), _ptr(bias3),
                                  _ptr(logits), rows, fc, _stream()), "lt_v2v_tail_fwd")
 
 

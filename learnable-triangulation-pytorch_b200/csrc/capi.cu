@@ -94,9 +94,12 @@ extern "C" int lt_conv_nd_fwd(const lt_conv_desc* d, const void* in, const void*
   LT_REQUIRE(d->OD > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0, "conv_nd: bad output dims");
   LT_REQUIRE(d->KD > 0 && d->KH > 0 && d->KW > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0, "conv_nd: bad filter/stride");
   LT_REQUIRE(d->osd > 0 && d->osh > 0 && d->osw > 0, "conv_nd: bad output scale");
-  LT_REQUIRE((d->OD - 1) * d->osd + d->ood < d->FD && (d->OH - 1) * d->osh + d->ooh < d->FH &&
-                 (d->OW - 1) * d->osw + d->oow < d->FW && d->ood >= 0 && d->ooh >= 0 && d->oow >= 0,
+  const int gd = d->ogd > 1 ? d->ogd : 1, gh = d->ogh > 1 ? d->ogh : 1, gw = d->ogw > 1 ? d->ogw : 1;
+  LT_REQUIRE((d->OD - 1) * d->osd + d->ood + gd - 1 < d->FD && (d->OH - 1) * d->osh + d->ooh + gh - 1 < d->FH &&
+                 (d->OW - 1) * d->osw + d->oow + gw - 1 < d->FW && d->ood >= 0 && d->ooh >= 0 && d->oow >= 0,
              "conv_nd: output mapping exceeds the output tensor");
+  LT_REQUIRE(gd * gh * gw == 1 || impl == LT_CONV_TC || impl == LT_CONV_TC1 || impl == LT_CONV_TC_PAIR,
+             "conv_nd: grouped output (ogd/ogh/ogw) is only implemented by the tensor-core kernels");
   LT_REQUIRE(d->residual == LT_RES_NONE || residual, "conv_nd: residual requested but pointer is null");
   LT_REQUIRE(d->residual >= LT_RES_NONE && d->residual <= LT_RES_AFTER_RELU, "conv_nd: bad residual mode");
   if (impl == LT_CONV_SIMT) return conv_simt_fwd(d, in, weight, scale, shift, residual, out, stream);

@@ -96,7 +96,7 @@ constexpr int kMaxResBufs = 4;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const TcParams p,
+                 const __grid_constant__ OutMaps tmOut, const __grid_constant__ OutMaps tmRes, const TcParams p,
                  const PairExtra x) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -120,7 +120,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < kMaxResBufs; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut.m[0]); }
   if (warp == 1) tmem_alloc2(tmem_slot, 512u);
   tc_fence_before();
   __syncthreads();
@@ -219,8 +219,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int a0, a1, a2, a3, an;
       decode(tile_c, a0, a1, a2, a3, an);
       const int buf = (int)(c & (RB - 1));
+      int ch = an + blk * 32, mi = 0;
+      if (p.n_maps > 1) { mi = ch / p.oc; ch -= mi * p.oc; }
       mbar_expect_tx(&res_full[buf], 16384u);
-      tma_load_5d(res_stage + buf * 16384, &tmRes, &res_full[buf], an * esz + blk * 32 * esz, a0, a1, a2, a3);
+      tma_load_5d(res_stage + buf * 16384, &tmRes.m[mi], &res_full[buf], ch * esz, a0, a1, a2, a3);
     };
     if (leader && has_res)
       for (long c = 0; c < RB && c < total_blocks; ++c) issue_res(c);
@@ -230,7 +232,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int ow0, oh0, od0, nb0, n0;
       decode(tile, ow0, oh0, od0, nb0, n0);
       const uint32_t as = it & 1u;
-      const int cbase = n0 * esz;
       mbar_wait(&acc_full[as], (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.Nt;
@@ -261,7 +262,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async();
         epi_bar_sync();
         if (leader) {
-          tma_store_5d(&tmOut, out_stage + buf * 16384, cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+          int ch = n0 + i * 32, mi = 0;
+          if (p.n_maps > 1) { mi = ch / p.oc; ch -= mi * p.oc; }
+          tma_store_5d(&tmOut.m[mi], out_stage + buf * 16384, ch * esz, ow0, oh0, od0, nb0);
           bulk_commit();
           if (has_res && c + RB < total_blocks) issue_res(c + RB);
         }
@@ -321,7 +324,7 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
   return true;
 }
 
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes, TcParams& p,
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmOut, const OutMaps& tmRes, TcParams& p,
                 const PairPlan& plan, int CoutP, cudaStream_t st) {
   PairExtra x;
   p.Nt = plan.Nt;

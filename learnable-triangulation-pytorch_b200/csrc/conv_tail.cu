@@ -20,7 +20,7 @@ namespace lt {
 struct TailParams {
   const float* scale1; const float* shift1;   // [32] folded BN of back_layers[1]
   const float* scale2; const float* shift2;   // [32] back_layers[2]
-  const float* bias3;                         // [32] output bias (zero padded)
+  const float* scale3; const float* bias3;    // [32] output layer: 1 / (filter pre-scale) and bias (zero padded)
   float* logits;                              // [rows][FC]
   long rows;
   long tiles;
@@ -177,16 +177,18 @@ __global__ void __launch_bounds__(kTailThreads, 3) v2v_tail_kernel(const __grid_
           float* dst = p.logits + vox * p.FC;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale3 + j));
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias3 + j));
-            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(t0[j]) + b.x, __uint_as_float(t0[j + 1]) + b.y,
-                                                             __uint_as_float(t0[j + 2]) + b.z, __uint_as_float(t0[j + 3]) + b.w);
+            *reinterpret_cast<float4*>(dst + j) = make_float4(fmaf(__uint_as_float(t0[j]), a.x, b.x), fmaf(__uint_as_float(t0[j + 1]), a.y, b.y),
+                                                             fmaf(__uint_as_float(t0[j + 2]), a.z, b.z), fmaf(__uint_as_float(t0[j + 3]), a.w, b.w));
           }
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (16 + j < p.FC) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.scale3 + 16 + j));
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias3 + 16 + j));
-              *reinterpret_cast<float4*>(dst + 16 + j) = make_float4(__uint_as_float(t1[j]) + b.x, __uint_as_float(t1[j + 1]) + b.y,
-                                                                    __uint_as_float(t1[j + 2]) + b.z, __uint_as_float(t1[j + 3]) + b.w);
+              *reinterpret_cast<float4*>(dst + 16 + j) = make_float4(fmaf(__uint_as_float(t1[j]), a.x, b.x), fmaf(__uint_as_float(t1[j + 1]), a.y, b.y),
+                                                                    fmaf(__uint_as_float(t1[j + 2]), a.z, b.z), fmaf(__uint_as_float(t1[j + 3]), a.w, b.w));
             }
           }
         }
@@ -208,12 +210,13 @@ __global__ void __launch_bounds__(kTailThreads, 3) v2v_tail_kernel(const __grid_
 using namespace lt;
 
 // x: split-fp16 rows [rows][32 hi | 32 lo]; w1/w2/w3: lt_conv_pair_pack_weights(taps = 1, Cin = 32, Cout = 32 / 32 / J) buffers
-// (rows padded to 128; the first 32 are used); scale/shift: folded BN of the two hidden layers; bias3 [32] (zero padded);
+// (rows padded to 128; the first 32 are used); scale/shift: folded BN of the two hidden layers; scale3 / bias3 [32]: output affine
+// (scale3 = 1 / filter pre-scale, bias zero padded);
 // logits float32 [rows][FC], FC % 4 == 0, J <= FC <= 32.
 extern "C" int lt_v2v_tail_fwd(const void* x, const void* w1, const void* w2, const void* w3, const float* scale1, const float* shift1,
-                               const float* scale2, const float* shift2, const float* bias3, float* logits, long rows, int FC,
-                               void* stream) {
-  LT_REQUIRE(x && w1 && w2 && w3 && scale1 && shift1 && scale2 && shift2 && bias3 && logits, "v2v_tail: null pointer");
+                               const float* scale2, const float* shift2, const float* scale3, const float* bias3, float* logits, long rows,
+                               int FC, void* stream) {
+  LT_REQUIRE(x && w1 && w2 && w3 && scale1 && shift1 && scale2 && shift2 && scale3 && bias3 && logits, "v2v_tail: null pointer");
   LT_REQUIRE(rows > 0 && rows < (1L << 31) && FC % 4 == 0 && FC >= 4 && FC <= 32, "v2v_tail: bad sizes (rows=%ld FC=%d)", rows, FC);
   CUtensorMap tmX, tmW[3];
   {
@@ -232,7 +235,7 @@ extern "C" int lt_v2v_tail_fwd(const void* x, const void* w1, const void* w2, co
     if (rc) return rc;
   }
   TailParams p;
-  p.scale1 = scale1; p.shift1 = shift1; p.scale2 = scale2; p.shift2 = shift2; p.bias3 = bias3;
+  p.scale1 = scale1; p.shift1 = shift1; p.scale2 = scale2; p.shift2 = shift2; p.scale3 = scale3; p.bias3 = bias3;
   p.logits = logits; p.rows = rows; p.tiles = (rows + 127) / 128; p.FC = FC;
   static DeviceOnce configured;
   if (configured.first()) {

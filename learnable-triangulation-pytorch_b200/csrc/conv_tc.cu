@@ -28,8 +28,8 @@ namespace lt {
 
 __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
-                                                      const __grid_constant__ CUtensorMap tmOut,
-                                                      const __grid_constant__ CUtensorMap tmRes, const TcParams p) {
+                                                      const __grid_constant__ OutMaps tmOut,
+                                                      const __grid_constant__ OutMaps tmRes, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.Nt * 128;
@@ -175,11 +175,17 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
       const bool leader = threadIdx.x == 64;
       const int nblk = p.Nt >> 5;
       const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;   // tensor-map elements per channel
-      const int cbase = n0 * esz;
+      // 32-channel block i of this N tile -> (output map, channel inside it): grouped outputs put block g*oc.. into map g
+      auto blk_map = [&](int i, int& mi, int& ch) {
+        ch = n0 + i * 32; mi = 0;
+        if (p.n_maps > 1) { mi = ch / p.oc; ch -= mi * p.oc; }
+      };
       if (leader && p.residual != LT_RES_NONE) {
         for (int i = 0; i < 2 && i < nblk; ++i) {
+          int mi, ch;
+          blk_map(i, mi, ch);
           mbar_expect_tx(&res_full[i], 16384u);
-          tma_load_5d(res_stage + i * 16384, &tmRes, &res_full[i], cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+          tma_load_5d(res_stage + i * 16384, &tmRes.m[mi], &res_full[i], ch * esz, ow0, oh0, od0, nb0);
         }
       }
       for (int i = 0; i < nblk; ++i) {
@@ -206,11 +212,14 @@ __global__ void __launch_bounds__(320) conv_tc_kernel(const __grid_constant__ CU
         fence_proxy_async();
         epi_bar_sync();
         if (leader) {
-          tma_store_5d(&tmOut, out_stage + buf * 16384, cbase + i * 32 * esz, ow0, oh0, od0, nb0);
+          int mi, ch;
+          blk_map(i, mi, ch);
+          tma_store_5d(&tmOut.m[mi], out_stage + buf * 16384, ch * esz, ow0, oh0, od0, nb0);
           bulk_commit();
           if (p.residual != LT_RES_NONE && i + 2 < nblk) {
+            blk_map(i + 2, mi, ch);
             mbar_expect_tx(&res_full[buf], 16384u);
-            tma_load_5d(res_stage + buf * 16384, &tmRes, &res_full[buf], cbase + (i + 2) * 32 * esz, ow0, oh0, od0, nb0);
+            tma_load_5d(res_stage + buf * 16384, &tmRes.m[mi], &res_full[buf], ch * esz, ow0, oh0, od0, nb0);
           }
         }
       }
@@ -609,6 +618,18 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, lo
 
 // Tensor map over the output (or residual) tensor as seen by this launch: the stride-phase mapping
 // (out coordinate = o * os + oo) becomes a base offset plus scaled strides; box = one 32-channel block of an M tile.
+static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* d, const TcParams& p);
+// one map per output group: group g = (a * ogh + b) * ogw + c adds (a, b, c) to the output offset (ood, ooh, oow)
+static int make_out_maps(OutMaps* maps, const void* base, const lt_conv_desc* d, const TcParams& p) {
+  const int gh = d->ogh > 1 ? d->ogh : 1, gw = d->ogw > 1 ? d->ogw : 1;
+  for (int g = 0; g < p.n_maps; ++g) {
+    lt_conv_desc dg = *d;
+    dg.ood += g / (gh * gw); dg.ooh += (g / gw) % gh; dg.oow += g % gw;
+    int rc = make_out_map(&maps->m[g], base, &dg, p);
+    if (rc) return rc;
+  }
+  return LT_OK;
+}
 static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* d, const TcParams& p) {
   const uint64_t rowb = (uint64_t)d->FC * 4;   // 4 bytes per channel in both formats
   const uint8_t* b0 = reinterpret_cast<const uint8_t*>(base) +
@@ -620,7 +641,7 @@ static int make_out_map(CUtensorMap* map, const void* base, const lt_conv_desc* 
   return make_map(map, b0, 5, dims, str, bx, nullptr, 1, f32);
 }
 
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmOut, const OutMaps& tmRes,
                      TcParams& p, int n_tiles, cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0) {
   p.splits = 1; p.ws = nullptr; p.ws_ld = 0;
   const int stage_bytes = kATileBytes + p.Nt * 128;
@@ -651,7 +672,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // the same A tiles -- the per-SM L2 ingest, not the tensor pipe, bounds them
   const long bres_bytes = (long)nchunks_total * p.Nt * 128;
   const bool bres = p.bres != 0;
-  if (bres || ((persist_mode == 2 || (persist_mode == 1 && tiny_tiles)) && p.tma_epi && p.terms != 0 && m_tiles * n_tiles > (long)sm_count())) {
+  if (p.n_maps == 1 && (bres || ((persist_mode == 2 || (persist_mode == 1 && tiny_tiles)) && p.tma_epi && p.terms != 0 && m_tiles * n_tiles > (long)sm_count()))) {
     // persistent variant: one CTA per SM, deep operand ring + dedicated epilogue staging, two TMEM accumulator stages
     TcPersistExtra x;
     x.n_tiles = n_tiles;
@@ -678,7 +699,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
       if (e2 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
     }
     const unsigned pgrid = bres ? (unsigned)(x.m_streams * n_tiles) : (unsigned)sm_count();
-    conv_tc_persist_kernel<<<pgrid, 320, psmem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
+    conv_tc_persist_kernel<<<pgrid, 320, psmem, st>>>(tmA, tmB, tmOut.m[0], tmRes.m[0], p, x);
     cudaError_t e3 = cudaGetLastError();
     if (e3 != cudaSuccess) return fail(LT_ERR_CUDA, "conv_tc_persist_kernel: %s", cudaGetErrorString(e3));
     return LT_OK;
@@ -688,7 +709,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const int splitk_mode = opts().tc_splitk;
   int splits = 1;
   const long grid_ctas = m_tiles * n_tiles;
-  if (splitk_mode && ws && p.terms != 0 && grid_ctas * 2 <= (long)sm_count() && nchunks_total >= 16) {
+  if (splitk_mode && ws && p.terms != 0 && p.n_maps == 1 && grid_ctas * 2 <= (long)sm_count() && nchunks_total >= 16) {
     splits = (int)((long)sm_count() / grid_ctas);
     if (splits > nchunks_total / 4) splits = nchunks_total / 4;
     const size_t per_split = (size_t)m_tiles * 128 * (size_t)n_tiles * p.Nt * sizeof(float);
@@ -713,6 +734,11 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   return LT_OK;
 }
 
+static int out_groups(const lt_conv_desc* d) {
+  const int g = (d->ogd > 1 ? d->ogd : 1) * (d->ogh > 1 ? d->ogh : 1) * (d->ogw > 1 ? d->ogw : 1);
+  return g;
+}
+
 // fills the geometry / epilogue part of the launch parameters (M-tile box, taps, output mapping)
 static void fill_params(const lt_conv_desc* d, TcParams& p, int CB, int CoutP, int Nt, int terms, const float* scale, const float* shift,
                         const void* residual, void* out) {
@@ -730,6 +756,8 @@ static void fill_params(const lt_conv_desc* d, TcParams& p, int CB, int CoutP, i
   p.relu = d->relu; p.residual = d->residual; p.out_format = d->out_format;
   p.scale = scale; p.shift = shift; p.res = residual; p.out = out;
   p.splits = 1; p.ws = nullptr; p.ws_ld = 0; p.stages = 0; p.tmem_cols = 0; p.tma_epi = 0;
+  p.n_maps = out_groups(d);
+  p.oc = p.n_maps > 1 ? d->Cout / p.n_maps : CoutP;
 }
 
 static int make_in_map(CUtensorMap* tmA, const lt_conv_desc* d, const TcParams& p, const void* in) {
@@ -745,6 +773,10 @@ static int make_in_map(CUtensorMap* tmA, const lt_conv_desc* d, const TcParams& 
 }
 
 static bool staged_epilogue_ok(const lt_conv_desc* d, int CoutP, int Nt) {
+  const int G = out_groups(d);
+  if (G > 1)    // grouped output: every 32-channel block must fall into one group, and fill the group's channels exactly
+    return Nt % 32 == 0 && d->Cout % G == 0 && (d->Cout / G) % 32 == 0 && d->Cout / G == d->FC && CoutP == d->Cout && G <= kMaxOutMaps &&
+           d->out_format == LT_FMT_S32;
   // float32 outputs may be narrower than the (single) padded N tile: the tensor map then has FC channels and the TMA
   // store clips the box at the tensor bound (80-byte voxel rows for the 17-joint logits instead of 128)
   const bool clipped_f32 = d->out_format == LT_FMT_F32 && d->residual == LT_RES_NONE && CoutP == Nt && d->FC % 4 == 0 && d->FC < CoutP;
@@ -769,7 +801,8 @@ int conv_pair_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   }
   if (probe_only) return 0;
   p.Nt = plan.Nt;
-  CUtensorMap tmA, tmB, tmOut, tmRes;
+  CUtensorMap tmA, tmB;
+  OutMaps tmOut, tmRes;
   int rc = make_in_map(&tmA, d, p, in);
   if (rc) return rc;
   {
@@ -780,11 +813,11 @@ int conv_pair_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
     rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 1);
     if (rc) return rc;
   }
-  rc = make_out_map(&tmOut, out, d, p);
+  rc = make_out_maps(&tmOut, out, d, p);
   if (rc) return rc;
   tmRes = tmOut;
   if (d->residual != LT_RES_NONE) {
-    rc = make_out_map(&tmRes, residual, d, p);
+    rc = make_out_maps(&tmRes, residual, d, p);
     if (rc) return rc;
   }
   return launch_pair(tmA, tmB, tmOut, tmRes, p, plan, CoutP, (cudaStream_t)stream);
@@ -815,6 +848,8 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
   p.osd = d->osd; p.osh = d->osh; p.osw = d->osw; p.ood = d->ood; p.ooh = d->ooh; p.oow = d->oow;
   p.relu = d->relu; p.residual = d->residual; p.out_format = d->out_format;
   p.scale = scale; p.shift = shift; p.res = residual; p.out = out;
+  p.n_maps = out_groups(d);
+  p.oc = p.n_maps > 1 ? d->Cout / p.n_maps : CoutP;
 
   CUtensorMap tmA, tmB;
   {
@@ -829,17 +864,22 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     int rc = make_map(&tmA, in, 5, dims, str, bx, es, 1);
     if (rc) return rc;
   }
-  CUtensorMap tmOut = tmA, tmRes = tmA;
+  OutMaps tmOut, tmRes;
+  tmOut.m[0] = tmA; tmRes.m[0] = tmA;
   const int direct_epi = opts().tc_direct_epilogue;
   // float32 outputs may be narrower than the (single) padded N tile: the tensor map then has FC channels and the TMA
   // store clips the box at the tensor bound (80-byte voxel rows for the 17-joint logits instead of 128)
   const bool clipped_f32 = d->out_format == LT_FMT_F32 && d->residual == LT_RES_NONE && CoutP == Nt && d->FC % 4 == 0 && d->FC < CoutP;
   p.tma_epi = (!direct_epi && Nt % 32 == 0 && ((d->FC % 32 == 0 && CoutP <= d->FC) || clipped_f32)) ? 1 : 0;
+  if (p.n_maps > 1) {
+    LT_REQUIRE(staged_epilogue_ok(d, CoutP, Nt), "conv_tc: grouped output needs split-fp16 output, Cout / groups == FC, a multiple of 32");
+    p.tma_epi = 1;
+  }
   // B-resident persistent variant: 1x1-like layers (<= 8 K chunks) with more than one 128-wide N tile and enough M tiles
   const int bres_mode = opts().tc_bres;
   const long m_tiles_all = (long)p.tw * p.th * p.td * p.tn;
   int n_tiles = CoutP / Nt;
-  if (bres_mode && terms != 0 && p.tma_epi && taps * CB <= 8 && Nt == 128 && CoutP >= 256 && CoutP / 64 <= sm_count() / 2 &&
+  if (bres_mode && p.n_maps == 1 && terms != 0 && p.tma_epi && taps * CB <= 8 && Nt == 128 && CoutP >= 256 && CoutP / 64 <= sm_count() / 2 &&
       m_tiles_all >= 2L * (sm_count() / (CoutP / 64))) {
     p.bres = 1;
     p.Nt = 64;
@@ -854,10 +894,10 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
     if (rc) return rc;
   }
   if (p.tma_epi) {
-    int rc = make_out_map(&tmOut, out, d, p);
+    int rc = make_out_maps(&tmOut, out, d, p);
     if (rc) return rc;
     if (d->residual != LT_RES_NONE) {
-      rc = make_out_map(&tmRes, residual, d, p);
+      rc = make_out_maps(&tmRes, residual, d, p);
       if (rc) return rc;
     }
   }
@@ -955,5 +995,8 @@ extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M
     if (rc) return rc;
   }
   p.tma_epi = 0;
-  return launch_tc(tmA, tmB, tmA, tmA, p, N / Nt, (cudaStream_t)stream);
+  p.n_maps = 1; p.oc = N;
+  OutMaps dummy;
+  dummy.m[0] = tmA;
+  return launch_tc(tmA, tmB, dummy, dummy, p, N / Nt, (cudaStream_t)stream);
 }

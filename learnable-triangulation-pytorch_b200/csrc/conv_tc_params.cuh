@@ -27,7 +27,14 @@ struct TcParams {
   int splits, ws_ld;
   float* ws;
   int bres;   // host-side request: B-resident persistent variant (Nt = 64 sub-tiles of the 128-wide packed weight tiles)
+  // grouped output (lt_conv_desc.ogd/ogh/ogw): output channel block g of `oc` channels goes to output map g (its own phase offset)
+  int oc, n_maps;
 };
+
+// Output / residual tensor maps of a launch: one per output group (k2 s2 transposed conv as ONE GEMM with N = 8 x Cout: group g
+// is the phase (a, b, c) of the output lattice); plain convs use m[0] only.
+constexpr int kMaxOutMaps = 8;
+struct OutMaps { CUtensorMap m[kMaxOutMaps]; };
 
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 fp16
 
@@ -42,7 +49,7 @@ struct PairPlan {
   unsigned grid;     // CTAs (2 per pair)
 };
 bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* plan);   // false: shape not covered by the pair kernel
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes, TcParams& p,
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& tmOut, const OutMaps& tmRes, TcParams& p,
                 const PairPlan& plan, int CoutP, cudaStream_t st);
 
 }  // namespace lt

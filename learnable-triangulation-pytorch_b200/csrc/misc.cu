@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ w
 
 __global__ void __launch_bounds__(256) gather_weights_kernel(const float* __restrict__ w, long base, long s_td, long s_th, long s_tw, long s_ci,
                                                              long s_co, int KH, int KW, int Cin, int CinP, int Cout, int CoutP, long total,
-                                                             const unsigned* __restrict__ absmax_bits, float* __restrict__ out) {
+                                                             const unsigned* __restrict__ absmax_bits, float* __restrict__ out, int out_ld,
+                                                             int out_col0) {
   const float S = weight_pow2_scale(absmax_bits);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int co = (int)(i % CoutP);
@@ -216,7 +217,8 @@ __global__ void __launch_bounds__(256) gather_weights_kernel(const float* __rest
     const int ci = (int)(r % CinP);
     const int tap = (int)(r / CinP);
     const int tw = tap % KW, th = (tap / KW) % KH, td = tap / (KW * KH);
-    out[i] = (ci < Cin && co < Cout) ? w[base + td * s_td + th * s_th + tw * s_tw + ci * s_ci + co * s_co] * S : 0.0f;
+    out[((long)tap * CinP + ci) * out_ld + out_col0 + co] =
+        (ci < Cin && co < Cout) ? w[base + td * s_td + th * s_th + tw * s_tw + ci * s_ci + co * s_co] * S : 0.0f;
   }
 }
 
@@ -272,14 +274,16 @@ extern "C" int lt_absmax_fwd(const float* w, long n, unsigned int* out_bits, voi
 
 extern "C" int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, long s_th, long s_tw, long s_ci, long s_co, int KD, int KH,
                                           int KW, int Cin, int CinP, int Cout, int CoutP, const unsigned int* absmax_bits, float* out,
-                                          void* stream) {
+                                          int out_ld, int out_col0, void* stream) {
   using namespace lt;
   LT_REQUIRE(w && out && KD > 0 && KH > 0 && KW > 0 && Cin > 0 && Cout > 0 && CinP >= Cin && CoutP >= Cout, "conv_gather_weights: bad arguments");
+  if (out_ld <= 0) out_ld = CoutP;
+  LT_REQUIRE(out_col0 >= 0 && out_col0 + CoutP <= out_ld, "conv_gather_weights: column block [%d, %d) exceeds the row length %d", out_col0, out_col0 + CoutP, out_ld);
   const long total = (long)KD * KH * KW * CinP * CoutP;
   long blocks = (total + 255) / 256;
   if (blocks > 4096) blocks = 4096;
   gather_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, base, s_td, s_th, s_tw, s_ci, s_co, KH, KW, Cin, CinP, Cout, CoutP,
-                                                                              total, absmax_bits, out);
+                                                                              total, absmax_bits, out, out_ld, out_col0);
   LT_CHECK_LAUNCH("gather_weights_kernel");
   return LT_OK;
 }

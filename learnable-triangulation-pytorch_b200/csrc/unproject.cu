@@ -440,6 +440,14 @@ __device__ __forceinline__ const float4* q_at(const float4* base, unsigned idx) 
   return reinterpret_cast<const float4*>(r);
 }
 
+// 256-bit read-only load (sm_100): two adjacent float4 of a channels-last pixel row in ONE request, so that four lanes cover a
+// voxel's 128-byte tap with one L1 wavefront (two 128-bit loads per lane would touch every line twice)
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 template <int MAXV, int FMT, bool EXACT, int MINB, int CPL>   // EXACT: V == MAXV (no per-view predicates); MINB: min CTAs / SM; CPL: channels per lane (4 or 8)
 __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojParams p) {
   __shared__ float sP[MAXV * 12];
@@ -509,13 +517,23 @@ __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojPar
         const float4* t1 = q_at(fbase, a1);
         const float4* t2 = q_at(fbase, a2);
         const float4* t3 = q_at(fbase, a3);
-#pragma unroll
-        for (int qd = 0; qd < NQ; ++qd) {
-          const float4 q0 = __ldg(t0 + qd), q1 = __ldg(t1 + qd), q2 = __ldg(t2 + qd), q3 = __ldg(t3 + qd);
-          s[v][qd * 4 + 0] = fmaf(q3.x, c3, fmaf(q2.x, c2, fmaf(q1.x, c1, q0.x * c0)));
-          s[v][qd * 4 + 1] = fmaf(q3.y, c3, fmaf(q2.y, c2, fmaf(q1.y, c1, q0.y * c0)));
-          s[v][qd * 4 + 2] = fmaf(q3.z, c3, fmaf(q2.z, c2, fmaf(q1.z, c1, q0.z * c0)));
-          s[v][qd * 4 + 3] = fmaf(q3.w, c3, fmaf(q2.w, c2, fmaf(q1.w, c1, q0.w * c0)));
+        if constexpr (NQ == 2) {
+          float4 q0, q1, q2, q3, r0, r1, r2, r3;
+          ldg256(t0, q0, r0); ldg256(t1, q1, r1); ldg256(t2, q2, r2); ldg256(t3, q3, r3);
+          s[v][0] = fmaf(q3.x, c3, fmaf(q2.x, c2, fmaf(q1.x, c1, q0.x * c0)));
+          s[v][1] = fmaf(q3.y, c3, fmaf(q2.y, c2, fmaf(q1.y, c1, q0.y * c0)));
+          s[v][2] = fmaf(q3.z, c3, fmaf(q2.z, c2, fmaf(q1.z, c1, q0.z * c0)));
+          s[v][3] = fmaf(q3.w, c3, fmaf(q2.w, c2, fmaf(q1.w, c1, q0.w * c0)));
+          s[v][4] = fmaf(r3.x, c3, fmaf(r2.x, c2, fmaf(r1.x, c1, r0.x * c0)));
+          s[v][5] = fmaf(r3.y, c3, fmaf(r2.y, c2, fmaf(r1.y, c1, r0.y * c0)));
+          s[v][6] = fmaf(r3.z, c3, fmaf(r2.z, c2, fmaf(r1.z, c1, r0.z * c0)));
+          s[v][7] = fmaf(r3.w, c3, fmaf(r2.w, c2, fmaf(r1.w, c1, r0.w * c0)));
+        } else {
+          const float4 q0 = __ldg(t0), q1 = __ldg(t1), q2 = __ldg(t2), q3 = __ldg(t3);
+          s[v][0] = fmaf(q3.x, c3, fmaf(q2.x, c2, fmaf(q1.x, c1, q0.x * c0)));
+          s[v][1] = fmaf(q3.y, c3, fmaf(q2.y, c2, fmaf(q1.y, c1, q0.y * c0)));
+          s[v][2] = fmaf(q3.z, c3, fmaf(q2.z, c2, fmaf(q1.z, c1, q0.z * c0)));
+          s[v][3] = fmaf(q3.w, c3, fmaf(q2.w, c2, fmaf(q1.w, c1, q0.w * c0)));
         }
       }
     }

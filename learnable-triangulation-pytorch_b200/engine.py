@@ -47,7 +47,7 @@ class Act:
 
 class ConvPack:
     """One (phase of a) convolution, ready to launch: packed filter + folded scale/shift + geometry."""
-    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs", "w_fold", "w_pair")
+    __slots__ = ("w", "scale", "shift", "taps", "k", "stride", "pad", "cin", "cout", "cout_p", "impl", "in_fmt", "kmacs", "w_fold", "w_pair", "groups")
 
 
 def _f32(t):
@@ -90,6 +90,7 @@ class NativeEngine:
         self.use_pair = os.environ.get("LT_TC_PAIR", "1") == "1"          # CTA-pair kernel for Cout % 128 == 0 layers
         self.use_tail = os.environ.get("LT_TC_TAIL", "1") == "1"          # fused back1 + back2 + output kernel
         self.weight_prescale = os.environ.get("LT_TC_WSCALE", "1") == "1"   # power-of-two filter pre-scale (common.cuh)
+        self.merge_deconv3d = os.environ.get("LT_TC_MERGE_DECONV", "1") == "1"   # k2 s2 transposed conv as one GEMM
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
@@ -114,29 +115,35 @@ class NativeEngine:
         """src = (filter tensor, base, (s_td, s_th, s_tw, s_ci, s_co)): where element (td, th, tw, ci, co) of this (phase of a)
         convolution sits inside the module's own weight tensor.  Everything below is our own kernels: gather to the canonical
         [tap][Cin][Cout] layout (lt_conv_gather_weights_fwd), operand packing, BatchNorm folding (lt_fold_bn_fwd)."""
-        w, base, strides = src
+        # a list of sources = column blocks of ONE wider filter (k2 s2 transposed conv: 8 phases side by side along N)
+        srcs = src if isinstance(src, list) else [src]
+        G = len(srcs)
+        w = srcs[0][0]
         dev = w.device
         taps = k[0] * k[1] * k[2]
         out_fmt = self.act_fmt if out_fmt is None else out_fmt
         pk = ConvPack()
-        pk.taps, pk.k, pk.stride, pk.pad, pk.cout = taps, k, stride, pad, cout
-        pk.kmacs = taps * cin * cout   # algorithmic MACs per output position
+        pk.taps, pk.k, pk.stride, pk.pad, pk.cout, pk.groups = taps, k, stride, pad, G * cout, G
+        pk.kmacs = taps * cin * cout * G   # algorithmic MACs per output position
         pk.w_fold = None
         pk.w_pair = None
         use_tc = (self.mode != "simt") and not force_simt and (max(stride) == 1 or self.tc_strided)
+        assert G == 1 or (use_tc and cout % 32 == 0), "column blocks need the tensor-core path and 32-channel multiples"
         if use_tc:
             cin_p = _round_up(max(cin, cin_pad or 0), 32)
-            cout_p = _round_up(cout, 32 if out_fmt == FMT_S32 else 16)
+            cout_p = _round_up(G * cout, 32 if out_fmt == FMT_S32 else 16)
         else:
             cin_p = max(cin, cin_pad or 0)
             cout_p = _round_up(cout, 4)
+        blk_p = cout if G > 1 else cout_p
         wp = torch.empty((taps, cin_p, cout_p), dtype=torch.float32, device=dev)
         amax = None
         if use_tc and self.weight_prescale:
             # power-of-two pre-scale of the whole filter tensor (all phases of a transposed conv share it): common.cuh
             amax = torch.empty(1, dtype=torch.int32, device=dev)
             capi.absmax(w, amax)
-        capi.conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, wp, amax)
+        for g, (wg, base, strides) in enumerate(srcs):
+            capi.conv_gather_weights(wg, base, strides, k, cin, cin_p, cout, blk_p, wp, amax, out_ld=cout_p, out_col0=g * cout)
         if use_tc:
             packed = torch.empty(capi.conv_tc_weight_bytes(taps, cin_p, cout_p) // 2, dtype=torch.float16, device=dev)
             capi.conv_tc_pack_weights(wp, packed, taps, cin_p, cout_p)
@@ -157,11 +164,13 @@ class NativeEngine:
             pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = wp, cin_p, cout_p, CONV_SIMT, FMT_F32
         pk.scale = torch.empty(cout_p, dtype=torch.float32, device=dev)
         pk.shift = torch.empty(cout_p, dtype=torch.float32, device=dev)
-        if bn is not None:
-            capi.fold_bn(_f32(bn.weight), _f32(bn.bias), _f32(bn.running_mean), _f32(bn.running_var), _f32(bias), bn.eps, cout, cout_p,
-                         pk.scale, pk.shift, amax)
-        else:
-            capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, cout_p, pk.scale, pk.shift, amax)
+        for g in range(G):     # the per-channel affine repeats for every column block
+            sc, sh = pk.scale[g * cout:g * cout + blk_p], pk.shift[g * cout:g * cout + blk_p]
+            if bn is not None:
+                capi.fold_bn(_f32(bn.weight), _f32(bn.bias), _f32(bn.running_mean), _f32(bn.running_var), _f32(bias), bn.eps, cout, blk_p,
+                             sc, sh, amax)
+            else:
+                capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, blk_p, sc, sh, amax)
         return pk
 
     def _pack_conv(self, conv, bn, cin_pad=None, **kw):
@@ -217,9 +226,16 @@ class NativeEngine:
         return phases
 
     def _pack_deconv3d_k2s2(self, deconv, bn):
-        """ConvTranspose3d(k=2, s=2): eight independent 1x1x1 convs scattered to the output parities."""
+        """ConvTranspose3d(k=2, s=2): eight independent 1x1x1 convs scattered to the output parities.
+
+        Tensor-core modes with Cout % 32 == 0: ONE 1x1x1 GEMM with N = 8 x Cout (the phases side by side along N, the epilogue
+        writing each 32-channel block to its phase of the output lattice: lt_conv_desc.ogd/ogh/ogw) -- the input is read once
+        instead of eight times and a level costs one launch instead of eight."""
         w = _f32(deconv.weight)  # (Cin, Cout, 2, 2, 2)
         cin, cout = w.shape[:2]
+        if self.mode != "simt" and cout % 32 == 0 and self.merge_deconv3d:
+            srcs = [(w, a * 4 + b * 2 + c, (0, 0, 0, cout * 8, 8)) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+            return self._pack(srcs, (1, 1, 1), (1, 1, 1), (0, 0, 0), cin, cout, deconv.bias, bn)
         phases = {}
         for a in (0, 1):
             for b in (0, 1):
@@ -304,7 +320,7 @@ class NativeEngine:
         return y
 
     def _conv(self, x, pk, relu, residual=None, res_mode=RES_NONE, out=None, out_scale=(1, 1, 1), out_off=(0, 0, 0),
-              out_dims=None, out_fmt=None, out_c=None):
+              out_dims=None, out_fmt=None, out_c=None, out_groups=(1, 1, 1)):
         """Launch one conv. `out` (with out_scale/out_off) lets transposed-conv phases share an output tensor.
 
         out_c: channel stride of a float32 output narrower than the padded N tile (the TMA store clips the padding)."""
@@ -330,7 +346,8 @@ class NativeEngine:
                           KD=kd, KH=kh, KW=kw, sd=sd, sh=sh, sw=sw, pd=pd, ph=ph, pw=pw,
                           FD=out.D, FH=out.H, FW=out.W, FC=out.C,
                           osd=out_scale[0], osh=out_scale[1], osw=out_scale[2], ood=out_off[0], ooh=out_off[1], oow=out_off[2],
-                          relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt)
+                          relu=int(relu), residual=res_mode, in_format=x.fmt, out_format=out.fmt,
+                          ogd=out_groups[0], ogh=out_groups[1], ogw=out_groups[2])
         if residual is not None:
             assert residual.fmt == out.fmt and residual.C == out.C
         ws = self._splitk_workspace(x.data.device)
@@ -377,6 +394,10 @@ class NativeEngine:
         return out
 
     def _deconv3d(self, x, phases, skip):
+        if isinstance(phases, ConvPack):      # merged: one GEMM, eight output groups
+            out = Act(x.N, 2 * x.D, 2 * x.H, 2 * x.W, phases.cout // 8, self.act_fmt, x.data.device)
+            return self._conv(x, phases, relu=True, residual=skip, res_mode=RES_AFTER_RELU, out=out, out_scale=(2, 2, 2),
+                              out_dims=(x.D, x.H, x.W), out_groups=(2, 2, 2))
         c = next(iter(phases.values())).cout
         out = Act(x.N, 2 * x.D, 2 * x.H, 2 * x.W, c, self.act_fmt, x.data.device)
         for (a, b, cc), pk in phases.items():
@@ -489,7 +510,7 @@ class NativeEngine:
             rows = x.pixels
             with self._timed("conv_tail", flops=2.0 * rows * (b1.kmacs + b2.kmacs + b3.kmacs), nbytes=rows * (128 + 4 * out_c),
                              desc="N%d %dx%dx%d 32->32->32->%d k111 fused" % (x.N, x.D, x.H, x.W, b3.cout)):
-                capi.v2v_tail(x.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.shift, logits.data, rows, out_c)
+                capi.v2v_tail(x.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.scale, b3.shift, logits.data, rows, out_c)
             self.launches += 1
             return logits
         x = self._conv(x, P["back1"], relu=True)

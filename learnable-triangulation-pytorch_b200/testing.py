@@ -134,7 +134,9 @@ def randomize_weights(model, seed=0, calib_size=64, calib_views=2, feat_gain=4.0
     hook = model_cpu.volume_net.output_layer.register_forward_hook(lambda m, i, o: grabbed.update(logits=o))
     top_training = model_cpu.training
     model_cpu.training = False                               # theta = 0; only the BatchNorms are in train mode
+    backend, model_cpu.backend = getattr(model_cpu, "backend", "torch"), "torch"    # CPU calibration: torch ops whatever the backend
     model_cpu._forward_torch(images, batch)
+    model_cpu.backend = backend
     model_cpu.training = top_training
     hook.remove()
     logits = grabbed["logits"]

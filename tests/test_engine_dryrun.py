@@ -86,7 +86,8 @@ def test_engine_plan_is_consistent(monkeypatch, mode, layers):
     v2v = len(convs) - backbone
     tail = sum(1 for c in rec.calls if c[0] == "v2v_tail")      # tc mode: back1 + back2 + output fused into one launch
     assert tail == (1 if mode == "tc" else 0)
-    assert v2v == 1 + 20 * 2 + 3 + 5 * 8 + (0 if tail else 2 + 1), v2v
+    up = 5 * (1 if mode == "tc" else 8)     # tc: each k2 s2 transposed conv is one grouped-output GEMM; simt: eight phase convs
+    assert v2v == 1 + 20 * 2 + 3 + up + (0 if tail else 2 + 1), v2v
     assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights", "conv_pair_pack_weights", "conv_gather_weights", "fold_bn", "absmax")) + 2   # softargmax = 3 launches
     if mode == "tc":
         simt = [c for c in convs if c[1][0] == capi.CONV_SIMT]

@@ -38,18 +38,23 @@ def _worker(rank, world, port, ret):
             kp_single = model(images.to(dev), None, batch)[0]
             plan = lt_dist.make_plan(world, rank, V)
             pg = lt_dist.new_view_groups(plan)
-            proj, base, position, step, rots, _ = model._host_geometry(batch, B, (S, S), (S // 4, S // 4))
+            from lt_b200.triangulation import backbone_map_size
+            proj, base, position, step, rots, _ = model._host_geometry(batch, B, (S, S), (backbone_map_size(S),) * 2)
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
             vs = plan.views
             errs = {}
             for coll in ("all_reduce", "reduce_scatter", "p2p", "features"):
-                try:
-                    kp = model.engine().forward_view_sharded(images[:, vs].contiguous().to(dev), up(proj[:, vs]), up(position), up(base),
-                                                             up(step), up(rots.reshape(B, 9)), plan, pg, coll, proj_all=up(proj))[0]
-                    torch.cuda.synchronize()
-                    errs[coll] = float((kp - kp_single).abs().max())
-                except Exception as e:   # report, do not hang the other rank
-                    errs[coll] = "ERROR: %r" % (e,)
+                for graph in (False, True):      # graph: stages 1 and 3 replayed as CUDA graphs around the eager exchange
+                    key = coll + ("+graph" if graph else "")
+                    try:
+                        for _ in range(2 if graph else 1):   # second call replays the captured graphs
+                            kp = model.engine().forward_view_sharded(images[:, vs].contiguous().to(dev), up(proj[:, vs]), up(position), up(base),
+                                                                     up(step), up(rots.reshape(B, 9)), plan, pg, coll, proj_all=up(proj),
+                                                                     use_graph=graph)[0]
+                        torch.cuda.synchronize()
+                        errs[key] = float((kp - kp_single).abs().max())
+                    except Exception as e:   # report, do not hang the other rank
+                        errs[key] = "ERROR: %r" % (e,)
         ret[rank] = errs
     finally:
         dist.destroy_process_group()

@@ -226,7 +226,7 @@ PAIR_CASES = [
     # (dims, cin, cout, k, stride, pad, spatial, batch, res_mode)  -- layers with Cout % 128 == 0 (csrc/conv_pair.cu)
     (2, 256, 1024, 1, 1, 0, (24, 24), 9, "before"),     # 1x1 expand of a bottleneck: Nt = 256, 4 N tiles, odd M-tile count (41)
     (2, 1024, 256, 1, 1, 0, (24, 24), 8, "none"),       # 1x1 reduce: 32 K chunks, one N tile
-    (2, 256, 256, 3, 1, 1, (24, 24), 8, "none"),        # 3x3: padding through TMA zero fill in both CTAs of a pair
+    (2, 256, 256, 3, 1, 1, (24, 24), 32, "none"),       # 3x3: padding through TMA zero fill in both CTAs of a pair
     (2, 128, 128, 3, 1, 1, (48, 48), 3, "none"),        # Nt = 128
     (2, 128, 512, 1, 1, 0, (48, 48), 3, "before"),
     (2, 64, 256, 1, 1, 0, (96, 96), 2, "before"),       # 2 K chunks per tile: epilogue-bound, many tiles per pair
@@ -291,6 +291,34 @@ def test_conv_pair_deconv_phases_vs_torch():
         capi.conv_nd = orig
     assert launched == [capi.CONV_TC_PAIR] * 4
     assert rel_err(got.numpy(), want.numpy()) < TOL["tc"]
+
+
+@pytest.mark.parametrize("cin,cout,spatial,N", [(64, 32, (32, 32, 32), 2), (128, 64, (16, 16, 16), 4), (128, 128, (8, 8, 8), 2), (128, 128, (2, 2, 2), 8)])
+def test_deconv3d_merged_single_gemm_vs_torch(cin, cout, spatial, N):
+    """ConvTranspose3d(k=2, s=2) + BN + ReLU + skip (v2v.py:54-66, :118-137) as ONE GEMM with N = 8 x Cout and grouped output
+    (lt_conv_desc.ogd/ogh/ogw): large levels on the CTA-pair kernel, small ones on the one-CTA kernel."""
+    torch.manual_seed(cin + cout + spatial[0])
+    e = _engine("tc")
+    dc = torch.nn.ConvTranspose3d(cin, cout, 2, 2).eval()
+    bn = _bn_for(dc, 3)
+    x = torch.randn(N, cin, *spatial)
+    skip = torch.randn(N, cout, *[2 * v for v in spatial])
+    with torch.no_grad():
+        want = F.relu(bn(dc(x))) + skip
+    pk = e._pack_deconv3d_k2s2(dc.to(DEV), bn.to(DEV))
+    assert not isinstance(pk, dict) and pk.groups == 8
+    launched = []
+    orig = capi.conv_nd
+    capi.conv_nd = lambda d, *a: (launched.append(a[-1]), orig(d, *a))[1]
+    try:
+        got = act_to_nchw(e._deconv3d(act_from_nchw(x, capi.FMT_S32), pk, act_from_nchw(skip, capi.FMT_S32))).cpu()
+    finally:
+        capi.conv_nd = orig
+    torch.cuda.synchronize()
+    assert len(launched) == 1
+    err = rel_err(got.numpy(), want.numpy())
+    print("deconv3d merged %d->%d %s N=%d impl=%d rel err %.2e" % (cin, cout, spatial, N, launched[0], err))
+    assert err < TOL["tc"]
 
 
 def test_conv_tc_fp32_output_and_no_residual():
@@ -362,7 +390,7 @@ def test_v2v_tail_fused_vs_torch(spatial, N):
     xa = act_from_nchw(x, capi.FMT_S32)
     rows = xa.pixels
     logits = torch.full((rows, 20), 7.0, dtype=torch.float32, device=DEV)
-    capi.v2v_tail(xa.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.shift, logits, rows, 20)
+    capi.v2v_tail(xa.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.scale, b3.shift, logits, rows, 20)
     torch.cuda.synchronize()
     got = logits.view(N, *spatial, 20).permute(0, 4, 1, 2, 3).cpu()
     err = rel_err(got[:, :17].numpy(), want.numpy())

@@ -27,6 +27,10 @@ for s in $STAGES; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 20 -c 3 -f -o $O/${T}_prof_conv_tc python tools/profile_step.py --stage all --repeat 1 > $O/ncu_conv_tc.log 2>&1
       ls -la $O/*.ncu-rep ;;
     trainstep) timeout 900 python tools/train_step_bench.py --batch 4 --steps 4 2>&1 | tail -1 | tee $O/${T}_train_step.json | cut -c1-600 ;;
+    convprobe) timeout 600 python tools/conv_probe.py 2>&1 | tee $O/${T}_conv_probe.log | cut -c1-700 ;;
+    ncupair)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_pair_kernel -s 44 -c 3 -f -o $O/${T}_prof_conv_pair python tools/profile_step.py --stage all --repeat 1 > $O/ncu_conv_pair.log 2>&1
+      ls -la $O/*.ncu-rep ;;
     postprobe) timeout 600 python tools/post_probe.py 2>&1 | tee $O/${T}_post_probe.log | cut -c1-300 ;;
     nopair) LT_TC_PAIR=0 LT_BENCH_TIMELINE=$O/${T}_timeline_nopair.json timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-gpu 2> $O/${T}_bench_nopair.err | tail -1 | tee $O/${T}_bench_nopair.json | python -c "$show" ;;
   esac

@@ -29,6 +29,8 @@ ap.add_argument("--steps", type=int, default=5)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
+torch.backends.cudnn.allow_tf32 = False          # true fp32 convolutions in both arms
+torch.backends.cuda.matmul.allow_tf32 = False
 
 images, batch = testing.make_batch(a.batch, a.views, image_size=a.image, seed=0)
 images = images.to(dev)
