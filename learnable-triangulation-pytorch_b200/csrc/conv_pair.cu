@@ -35,6 +35,7 @@ struct PairExtra {
   int stage_bytes, off_out, off_res, off_bar;
   int b_rows;   // weight rows per chunk = CoutP
   int res_bufs; // residual staging buffers (power of two): 16 KB blocks requested this many blocks ahead
+  int direct_out;   // split-fp16 output rows are stored straight from registers
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -89,6 +90,12 @@ __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, 
 // kind::f16 instruction descriptor for the pair: D = f32, A = B = fp16, K-major, M = 256, N = n
 __device__ __forceinline__ uint32_t make_idesc_f16_m256(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// 32 contiguous bytes (16 fp16 values of one voxel row) in one request
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
 constexpr int kPairEpiWarps = 8;
@@ -235,6 +242,61 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&acc_full[as], (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.Nt;
+      if (x.direct_out) {
+        // ---- direct epilogue (split-fp16 outputs): this thread's voxel row goes from registers to global memory as 2 x 32
+        // bytes per 32-channel block (high halves, low halves).  No staging tile, no TMA store: the TMA queue of the SM is
+        // FIFO, so a store issued here would wait behind every operand load the producer has already queued (up to 160 KB,
+        // ~3000 cycles) and throttle the epilogue of K-short layers to one block per queue latency (measured: 1x1 256 -> 1024
+        // with residual at 24x24: 60 us staged).  Residual tiles still arrive by TMA, four blocks ahead.
+        int r_ = row;
+        const int dw = r_ % p.bw; r_ /= p.bw;
+        const int dh = r_ % p.bh; r_ /= p.bh;
+        const int dd = r_ % p.bd; r_ /= p.bd;
+        const int ow = ow0 + dw, oh = oh0 + dh, od = od0 + dd, nb = nb0 + r_;
+        const bool valid = ow < p.OW && oh < p.OH && od < p.OD && nb < p.N;
+        const long opix = (((long)nb * p.FD + (od * p.osd + p.ood)) * p.FH + (oh * p.osh + p.ooh)) * p.FW + (ow * p.osw + p.oow);
+        for (int i = 0; i < nblk; ++i, ++c) {
+          const int rbuf = (int)(c & (RB - 1));
+          float v[16], r[16];
+          {
+            uint32_t t1[16];
+            tmem_ld16(tlane + (uint32_t)(i * 32 + half * 16), t1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
+          }
+          if (i == nblk - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(acc_empty0 + as * 8u);
+          }
+          epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
+          if (has_res) {
+            mbar_wait(&res_full[rbuf], (uint32_t)((c >> rb_shift) & 1));
+            epi_load16(smem_u32(res_stage + rbuf * 16384), row, half, LT_FMT_S32, r);
+          }
+          epi_activate16(v, r, p.residual, p.relu);
+          if (has_res) {
+            epi_bar_sync();                     // every thread has read res_stage[rbuf]: it may be refilled
+            if (leader && c + RB < total_blocks) issue_res(c + RB);
+          }
+          if (valid) {
+            int ch = n0 + i * 32;
+            long pix = opix;
+            if (p.n_maps > 1) {
+              const int mi = ch / p.oc;
+              ch -= mi * p.oc;
+              pix += ((long)(mi / (p.gh * p.gw)) * p.FH + (mi / p.gw) % p.gh) * p.FW + mi % p.gw;
+            }
+            uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + (pix * p.FC + ch) * 4 + half * 32;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_s32x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            stg256(dst, hi);
+            stg256(dst + 64, lo);
+          }
+        }
+        continue;
+      }
       for (int i = 0; i < nblk; ++i, ++c) {
         const int buf = (int)(c & 1);              // output staging buffer
         const int rbuf = (int)(c & (RB - 1));      // residual staging buffer
@@ -316,7 +378,8 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
   const int stage_bytes = kATileBytes + best_nt * 64;
   // shared memory: operand ring + 2 output staging tiles + (residual layers) 4 residual staging tiles, 16 KB each
   plan->res_bufs = d->residual != LT_RES_NONE ? kMaxResBufs : 0;
-  int stages = (227 * 1024 - 1024 - 32768 - plan->res_bufs * 16384 - 512) / stage_bytes;
+  plan->direct_out = (d->out_format == LT_FMT_S32 && opts().pair_direct_out) ? 1 : 0;
+  int stages = (227 * 1024 - 1024 - (plan->direct_out ? 0 : 32768) - plan->res_bufs * 16384 - 512) / stage_bytes;
   if (stages > 8) stages = 8;
   plan->stages = stages;
   const long tiles = m_pairs * plan->n_tiles;
@@ -338,7 +401,8 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& t
   x.b_rows = CoutP;
   const int ring = plan.stages * x.stage_bytes;
   x.off_out = (ring + 1023) & ~1023;
-  x.off_res = x.off_out + 32768;
+  x.direct_out = plan.direct_out;
+  x.off_res = x.off_out + (plan.direct_out ? 0 : 32768);
   x.off_bar = x.off_res + plan.res_bufs * 16384;
   x.res_bufs = plan.res_bufs ? plan.res_bufs : 2;
   const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 4 + kMaxResBufs) * 8 + 16 + 1024;

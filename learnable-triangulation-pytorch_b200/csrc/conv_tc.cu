@@ -758,6 +758,7 @@ static void fill_params(const lt_conv_desc* d, TcParams& p, int CB, int CoutP, i
   p.splits = 1; p.ws = nullptr; p.ws_ld = 0; p.stages = 0; p.tmem_cols = 0; p.tma_epi = 0;
   p.n_maps = out_groups(d);
   p.oc = p.n_maps > 1 ? d->Cout / p.n_maps : CoutP;
+  p.gh = d->ogh > 1 ? d->ogh : 1; p.gw = d->ogw > 1 ? d->ogw : 1;
 }
 
 static int make_in_map(CUtensorMap* tmA, const lt_conv_desc* d, const TcParams& p, const void* in) {
@@ -850,6 +851,7 @@ int conv_tc_fwd_terms(const lt_conv_desc* d, const void* in, const void* weight,
   p.scale = scale; p.shift = shift; p.res = residual; p.out = out;
   p.n_maps = out_groups(d);
   p.oc = p.n_maps > 1 ? d->Cout / p.n_maps : CoutP;
+  p.gh = d->ogh > 1 ? d->ogh : 1; p.gw = d->ogw > 1 ? d->ogw : 1;
 
   CUtensorMap tmA, tmB;
   {
@@ -995,7 +997,7 @@ extern "C" int lt_tc_gemm_selftest(const void* a, const void* b, float* d, int M
     if (rc) return rc;
   }
   p.tma_epi = 0;
-  p.n_maps = 1; p.oc = N;
+  p.n_maps = 1; p.oc = N; p.gh = p.gw = 1;
   OutMaps dummy;
   dummy.m[0] = tmA;
   return launch_tc(tmA, tmB, dummy, dummy, p, N / Nt, (cudaStream_t)stream);

@@ -29,6 +29,7 @@ struct TcParams {
   int bres;   // host-side request: B-resident persistent variant (Nt = 64 sub-tiles of the 128-wide packed weight tiles)
   // grouped output (lt_conv_desc.ogd/ogh/ogw): output channel block g of `oc` channels goes to output map g (its own phase offset)
   int oc, n_maps;
+  int gh, gw;    // output group grid (group g -> offset (g / (gh*gw), (g / gw) % gh, g % gw)); 1, 1 without groups
 };
 
 // Output / residual tensor maps of a launch: one per output group (k2 s2 transposed conv as ONE GEMM with N = 8 x Cout: group g
@@ -46,6 +47,7 @@ struct PairPlan {
   long m_pairs;      // ceil(m_tiles / 2)
   int stages;        // operand ring depth
   int res_bufs;      // residual staging tiles (0 without a residual)
+  int direct_out;    // split-fp16 outputs: the epilogue stores rows straight from registers (no staging tile, no TMA store)
   unsigned grid;     // CTAs (2 per pair)
 };
 bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* plan);   // false: shape not covered by the pair kernel

@@ -34,6 +34,9 @@ struct UnprojParams {
   // partial == 2 ("push"): sample b's partial goes to peer[b / samples_per_owner] (P2P store over NVLink) at slot src_rank
   float* peer[8];
   int samples_per_owner, src_rank;
+  // v2 kernel: cubic volumes (nvox = n^3, n % brick == 0) are walked brick by brick (brick^3 voxels at a time per CTA) so that
+  // the 2x2 tap cells of a CTA's consecutive voxels overlap in every view and are served by L1 instead of the 64 B/clk L2 port
+  int brick_n, brick;
 };
 
 struct Taps {
@@ -284,9 +287,27 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
   const int wm = p.w - 1, hm = p.h - 1;
 
   // block-uniform trip count: the width-G shuffles below need every lane of the warp present
-  for (long vbase = (long)blockIdx.x * VPB; vbase < p.nvox; vbase += (long)gridDim.x * VPB) {
-    const bool live = vbase + slot < p.nvox;
-    const long vox = live ? vbase + slot : p.nvox - 1;
+  // work items: VPB consecutive voxels (linear order), or -- brick mode -- VPB voxels of one brick^3 block (z fastest)
+  const int bs = p.brick, bpd = p.brick_n > 0 ? p.brick_n / bs : 0;            // brick side, bricks per dimension
+  const int bvol = bs * bs * bs;
+  const int ipb = p.brick_n > 0 ? bvol / VPB : 1;             // items per brick: a CTA finishes a brick before taking the next
+  const long n_outer = p.brick_n > 0 ? (long)bpd * bpd * bpd : (p.nvox + VPB - 1) / VPB;
+  for (long outer = blockIdx.x; outer < n_outer; outer += gridDim.x)
+  for (int inner = 0; inner < ipb; ++inner) {
+    const long item = outer * ipb + inner;
+    long vox;
+    bool live;
+    if (p.brick_n > 0) {
+      const long brick = outer;
+      const int w = inner * VPB + slot;                        // voxel inside the brick
+      const int bz = (int)(brick % bpd), by = (int)((brick / bpd) % bpd), bx = (int)(brick / ((long)bpd * bpd));
+      const int dz = w % bs, dy = (w / bs) % bs, dx = w / (bs * bs);
+      vox = ((long)(bx * bs + dx) * p.brick_n + (by * bs + dy)) * p.brick_n + (bz * bs + dz);
+      live = true;
+    } else {
+      live = item * VPB + slot < p.nvox;
+      vox = live ? item * VPB + slot : p.nvox - 1;
+    }
     const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
     const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
     float s[MAXV][CPL];
@@ -465,9 +486,27 @@ __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojPar
   const float wm = (float)(p.w - 1), hm = (float)(p.h - 1);
   const int wi = p.w - 1, hi = p.h - 1;
 
-  for (long vbase = (long)blockIdx.x * VPB; vbase < p.nvox; vbase += (long)gridDim.x * VPB) {
-    const bool live = vbase + slot < p.nvox;
-    const long vox = live ? vbase + slot : p.nvox - 1;
+  // work items: VPB consecutive voxels (linear order), or -- brick mode -- VPB voxels of one brick^3 block (z fastest)
+  const int bs = p.brick, bpd = p.brick_n > 0 ? p.brick_n / bs : 0;            // brick side, bricks per dimension
+  const int bvol = bs * bs * bs;
+  const int ipb = p.brick_n > 0 ? bvol / VPB : 1;             // items per brick: a CTA finishes a brick before taking the next
+  const long n_outer = p.brick_n > 0 ? (long)bpd * bpd * bpd : (p.nvox + VPB - 1) / VPB;
+  for (long outer = blockIdx.x; outer < n_outer; outer += gridDim.x)
+  for (int inner = 0; inner < ipb; ++inner) {
+    const long item = outer * ipb + inner;
+    long vox;
+    bool live;
+    if (p.brick_n > 0) {
+      const long brick = outer;
+      const int w = inner * VPB + slot;                        // voxel inside the brick
+      const int bz = (int)(brick % bpd), by = (int)((brick / bpd) % bpd), bx = (int)(brick / ((long)bpd * bpd));
+      const int dz = w % bs, dy = (w / bs) % bs, dx = w / (bs * bs);
+      vox = ((long)(bx * bs + dx) * p.brick_n + (by * bs + dy)) * p.brick_n + (bz * bs + dz);
+      live = true;
+    } else {
+      live = item * VPB + slot < p.nvox;
+      vox = live ? item * VPB + slot : p.nvox - 1;
+    }
     const float* cp = p.coord + ((long)b * p.nvox + vox) * 3;
     const float X = __ldg(cp), Y = __ldg(cp + 1), Z = __ldg(cp + 2);
     float s[MAXV][CPL];
@@ -619,6 +658,7 @@ static int launch_unproject(const float* features, const float* proj, const floa
   LT_REQUIRE(B <= 65535, "unproject: batch too large");
   UnprojParams p{features, proj, coord, conf, out, B, V, C, h, w, nvox, agg, out_format, 1, partial};
   p.samples_per_owner = 1; p.src_rank = src_rank;
+  p.brick_n = 0; p.brick = 8;
   for (int i = 0; i < 8; ++i) p.peer[i] = (peers && i < n_peers) ? peers[i] : nullptr;
   if (partial == 2) {
     LT_REQUIRE(peers && n_peers >= 1 && n_peers <= 8 && B % n_peers == 0, "unproject_push: need 1..8 peers dividing the batch");
@@ -643,7 +683,17 @@ static int launch_unproject(const float* features, const float* proj, const floa
     // variants (measured on B200 at config #2 shapes, see profiles/): 8 lanes x 4 channels per voxel at 4 CTAs/SM was the
     // round-1 default (0.29-0.31 ms); 4 lanes x 8 channels halves the per-voxel ray / shuffle / address overhead
     const int cpl = opts().unproject_cpl, lb = opts().unproject_lb;
-    if (cpl == 8) {
+    {
+      // brick walk for cubic volumes (the coordinate volume of the reference is n x n x n, triangulation.py:306-311)
+      long n = (long)llround(cbrt((double)nvox));
+      const int bs = opts().unproject_brick;
+      if (bs > 0 && n * n * n == nvox && n % bs == 0 && (bs * bs * bs) % (256 / (32 / cpl)) == 0) {
+        p.brick_n = (int)n; p.brick = bs;
+        const long nbricks = (n / bs) * (n / bs) * (n / bs);
+        grid.x = (unsigned)(nbricks < (long)sm_count() * 8 ? nbricks : (long)sm_count() * 8);
+      }
+    }
+    if (cpl == 8 && p.brick_n == 0) {
       const int vpb8 = 64;
       long blocks8 = (nvox + vpb8 - 1) / vpb8;
       if (blocks8 > (long)sm_count() * 8) blocks8 = (long)sm_count() * 8;

@@ -233,7 +233,7 @@ PAIR_CASES = [
     (2, 256, 512, 1, 2, 0, (48, 48), 4, "none"),        # stride-2 downsample through TMA traversal strides
     (2, 128, 128, 3, 2, 1, (48, 48), 16, "none"),
     (2, 512, 2048, 1, 1, 0, (12, 12), 6, "before"),
-    (3, 128, 128, 3, 1, 1, (16, 16, 16), 2, "before"),  # V2V 16^3 level
+    (3, 128, 128, 3, 1, 1, (16, 16, 16), 8, "before"),  # V2V 16^3 level
     (3, 64, 128, 3, 1, 1, (16, 16, 16), 4, "after"),
     (2, 96, 384, 1, 1, 0, (40, 24), 5, "before"),       # CoutP = 384 = 3 x 128
 ]

@@ -11,7 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = [
     ("unproject", {"LT_OPT_UNPROJECT_V2": "0"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_LB": "5"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "0"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "4"}),
     ("unproject", {"LT_OPT_UNPROJECT_CPL": "8"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3", "LT_OPT_UNPROJECT_BRICK": "4"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3", "LT_OPT_UNPROJECT_BRICK": "0"}),
     ("softargmax20", {"LT_OPT_SOFTARGMAX_STREAM": "0"}), ("softargmax20", {"LT_OPT_SOFTARGMAX_STREAM": "1"}),
     ("softargmax32", {"LT_OPT_SOFTARGMAX_STREAM": "0"}), ("softargmax32", {"LT_OPT_SOFTARGMAX_STREAM": "1"}),
 ]
