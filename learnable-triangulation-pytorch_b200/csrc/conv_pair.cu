@@ -36,6 +36,7 @@ struct PairExtra {
   int b_rows;   // weight rows per chunk = CoutP
   int res_bufs; // residual staging buffers (power of two): 16 KB blocks requested this many blocks ahead
   int direct_out;   // split-fp16 output rows are stored straight from registers
+  unsigned long long* prof;   // optional [16] cycle counters (lt_options.pair_prof): time each role spends waiting, summed over CTAs
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -98,6 +99,13 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
                ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
+
 constexpr int kPairEpiWarps = 8;
 constexpr int kMaxResBufs = 4;
 
@@ -120,6 +128,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const int nchunks = p.KD * p.KH * p.KW * p.CB;
   const int stage_bytes = x.stage_bytes;
+  const bool prof_on = x.prof != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -149,6 +158,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ================= TMA producer (both CTAs: own activation tile + own half of the weight tile) =================
     uint32_t rs = 0, rph = 0;
+    unsigned long long w_empty = 0;
+    const long long t_start = prof_on ? clock64() : 0;
     const uint32_t full0 = map_to_cta(smem_u32(&full[0]), 0);   // leader's full[] in cluster address space
     const int b_half = p.Nt >> 1;
     for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs) {
@@ -158,7 +169,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int brow0 = n0 + (int)rank * b_half;
       int cb = 0, kw = 0, kh = 0, kd = 0;
       for (int q = 0; q < nchunks; ++q) {
-        mbar_wait(&empty[rs], rph ^ 1u);
+        mbar_wait_t(&empty[rs], rph ^ 1u, w_empty, prof_on);
         uint8_t* a_dst = smem + (size_t)rs * stage_bytes;
         if (elect_one()) {
           if (rank == 0) mbar_expect_tx(&full[rs], 2u * (uint32_t)stage_bytes);
@@ -171,21 +182,24 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1u; }
       }
     }
+    if (prof_on && lane == 0) { atomicAdd(&x.prof[0 + 8 * rank], w_empty); atomicAdd(&x.prof[1 + 8 * rank], (unsigned long long)(clock64() - t_start)); }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only; M = 256 spans both CTAs) =================
     if (rank == 0) {
       const uint32_t idesc = make_idesc_f16_m256(p.Nt);
       uint32_t rs = 0, rph = 0, it = 0;
+      unsigned long long w_acc = 0, w_full = 0;
+      const long long t_start = prof_on ? clock64() : 0;
       const uint64_t ad0 = make_sw128_desc(smem_u32(smem));
       const uint64_t bd0 = make_sw128_desc(smem_u32(smem) + kATileBytes);
       const uint64_t sdelta = (uint64_t)(stage_bytes >> 4);
       for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
         const uint32_t as = it & 1u;
-        mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+        mbar_wait_t(&acc_empty[as], ((it >> 1) & 1u) ^ 1u, w_acc, prof_on);
         tc_fence_after();
         const uint32_t d = tmem_base + as * (uint32_t)p.Nt;
         for (int q = 0; q < nchunks; ++q) {
-          mbar_wait(&full[rs], rph);
+          mbar_wait_t(&full[rs], rph, w_full, prof_on);
           tc_fence_after();
           const uint64_t ad = ad0 + sdelta * rs, bd = bd0 + sdelta * rs;
           if (elect_one()) {
@@ -203,6 +217,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1u; }
         }
       }
+      if (prof_on && lane == 0) { atomicAdd(&x.prof[2], w_acc); atomicAdd(&x.prof[3], w_full); atomicAdd(&x.prof[4], (unsigned long long)(clock64() - t_start)); }
     }
   } else {
     // ================= epilogue (warps 2..9 of both CTAs; each CTA drains its own 128 TMEM lanes) =================
@@ -235,11 +250,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (long c = 0; c < RB && c < total_blocks; ++c) issue_res(c);
     uint32_t it = 0;
     long c = 0;
+    unsigned long long w_accf = 0, w_res = 0;
+    const long long t_start = prof_on ? clock64() : 0;
     for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
       int ow0, oh0, od0, nb0, n0;
       decode(tile, ow0, oh0, od0, nb0, n0);
       const uint32_t as = it & 1u;
-      mbar_wait(&acc_full[as], (it >> 1) & 1u);
+      mbar_wait_t(&acc_full[as], (it >> 1) & 1u, w_accf, prof_on);
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.Nt;
       if (x.direct_out) {
@@ -271,7 +288,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
           if (has_res) {
-            mbar_wait(&res_full[rbuf], (uint32_t)((c >> rb_shift) & 1));
+            mbar_wait_t(&res_full[rbuf], (uint32_t)((c >> rb_shift) & 1), w_res, prof_on);
             epi_load16(smem_u32(res_stage + rbuf * 16384), row, half, LT_FMT_S32, r);
           }
           epi_activate16(v, r, p.residual, p.relu);
@@ -333,6 +350,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (leader) bulk_wait<0>();
+    if (prof_on && threadIdx.x == 64) { atomicAdd(&x.prof[5 + 8 * rank], w_accf); atomicAdd(&x.prof[6 + 8 * rank], w_res); atomicAdd(&x.prof[7 + 8 * rank], (unsigned long long)(clock64() - t_start)); }
   }
 
   tc_fence_before();
@@ -359,6 +377,7 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
   int best_nt = 0;
   for (int nt = 256; nt >= 128; nt >>= 1) {
     if (CoutP % nt) continue;
+    if (opts().pair_nt != 0 && opts().pair_nt != nt && CoutP % opts().pair_nt == 0) continue;   // A/B override
     const long tiles = m_pairs * (CoutP / nt);
     const double waves = (double)((tiles + P - 1) / P);
     const double per_chunk = fmax(fmax(3.0 * nt, (16384.0 + nt * 64.0) / 50.0), 450.0);
@@ -381,6 +400,7 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
   plan->direct_out = (d->out_format == LT_FMT_S32 && opts().pair_direct_out) ? 1 : 0;
   int stages = (227 * 1024 - 1024 - (plan->direct_out ? 0 : 32768) - plan->res_bufs * 16384 - 512) / stage_bytes;
   if (stages > 8) stages = 8;
+  if (opts().pair_stages >= 2 && opts().pair_stages < stages) stages = opts().pair_stages;       // A/B override
   plan->stages = stages;
   const long tiles = m_pairs * plan->n_tiles;
   plan->grid = 2u * (unsigned)(tiles < P ? tiles : P);
@@ -412,9 +432,26 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& t
     cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
+  x.prof = nullptr;
+  static unsigned long long* prof_buf = nullptr;
+  const bool want_prof = opts().pair_prof != 0;
+  if (want_prof) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), st);
+    x.prof = prof_buf;
+  }
   conv_pair_kernel<<<plan.grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_pair_kernel: %s", cudaGetErrorString(e));
+  if (want_prof) {   // debug only: synchronises
+    unsigned long long h[16];
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const double g = (double)(plan.grid / 2);
+    fprintf(stderr, "[pair prof Nt=%d chunks=%d tiles/pair=%.1f stages=%d] leader: producer wait empty %.0f of %.0f | mma wait acc_empty %.0f full %.0f of %.0f | "
+            "epi wait acc_full %.0f res %.0f of %.0f || peer: producer wait empty %.0f of %.0f | epi wait acc_full %.0f res %.0f of %.0f (cycles per CTA)\n",
+            p.Nt, p.KD * p.KH * p.KW * p.CB, (double)x.total_tiles / g, p.stages, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g,
+            h[7] / g, h[8] / g, h[9] / g, h[13] / g, h[14] / g, h[15] / g);
+  }
   return LT_OK;
 }
 

@@ -38,6 +38,20 @@ def test_conv_desc_layout_matches_header():
     assert ctypes.sizeof(capi.ConvDesc) == sum(ctypes.sizeof(c) for _, c in fields)   # 32 ints, then 8-byte aligned
 
 
+def test_options_layout_matches_header():
+    """capi.Options mirrors `struct lt_options` field by field (all ints), and the defaults come from the library."""
+    header = open(os.path.join(ROOT, "include", "lt_b200.h")).read()
+    body = header[header.index("typedef struct lt_options {"):header.index("} lt_options;")]
+    fields = []
+    for line in body.splitlines()[1:]:
+        line = line.split("/*")[0].strip()
+        if line.startswith("int "):
+            fields += [f.strip() for f in line[4:].rstrip(";").split(",")]
+    assert fields == [f[0] for f in capi.Options._fields_]
+    o = capi.get_options()
+    assert o["tc_splitk"] == 1 and o["unproject_cpl"] in (4, 8) and o["pair_prof"] == 0
+
+
 def test_stack_projections_equals_per_camera_path():
     cams = testing.make_cameras(3, image_size=384)
     cameras = [[testing.Camera(c.R, c.t, c.K) for _ in range(2)] for c in cams]

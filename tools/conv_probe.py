@@ -51,16 +51,33 @@ for cin, cout, k, stride, side, N in CASES:
     out = Act(N, 1, out_side, out_side, cout, capi.FMT_S32, DEV)
     flops = 2.0 * N * out_side * out_side * cin * cout * k * k
     mb_min = (x.data.numel() + out.data.numel()) * 2 / 1e6
-    line = "cin %4d cout %4d k%d s%d %3dx%-3d N%-3d:" % (cin, cout, k, stride, side, side, N)
-    for use_pair in (True, False):
+    print("cin %4d cout %4d k%d s%d %3dx%-3d N%-3d  [in+out %.0f MB, %.1f GFLOP]" % (cin, cout, k, stride, side, side, N, mb_min, flops / 1e9), flush=True)
+    variants = [("pair direct-store ", True, dict(pair_direct_out=1)), ("pair staged+TMA   ", True, dict(pair_direct_out=0)),
+                ("pair Nt=128        ", True, dict(pair_direct_out=1, pair_nt=128)), ("pair ring depth 2  ", True, dict(pair_direct_out=1, pair_stages=2)),
+                ("one-CTA kernel    ", False, dict())]
+    for name, use_pair, o in variants:
+        capi.set_options(pair_direct_out=1, pair_nt=0, pair_stages=0, pair_prof=0)
+        capi.set_options(**o)
         e = _engine("tc")
         e.use_pair = use_pair
         pk = e._pack_conv(conv, bn)
+        line = "   %s:" % name
         for with_res in (False, True):
             r, mode = (res, capi.RES_BEFORE_RELU) if with_res else (None, capi.RES_NONE)
             fn = lambda: e._conv(x, pk, relu=True, residual=r, res_mode=mode, out=out)   # noqa: E731
             for do_flush in (False, True):
                 us = timed(fn, do_flush)
-                line += "  %s%s%s %6.1f us (%4.0f TF/s alg)" % ("pair" if use_pair else "old ", "+res" if with_res else "    ",
-                                                                " flushed" if do_flush else " warm   ", us, flops / us / 1e6)
-    print(line + "   [in+out %.0f MB%s]" % (mb_min, ""), flush=True)
+                line += "  %s%s %6.1f us (%4.0f TF/s)" % ("+res" if with_res else "    ", " flushed" if do_flush else " warm   ", us, flops / us / 1e6)
+        print(line, flush=True)
+        if use_pair and os.environ.get("CONV_PROBE_PROF", "1") == "1":
+            capi.set_options(pair_prof=1)
+            for with_res in (False, True):
+                r, mode = (res, capi.RES_BEFORE_RELU) if with_res else (None, capi.RES_NONE)
+                flush.zero_()
+                torch.cuda.synchronize()
+                sys.stderr.write("      %s %s: " % (name, "+res" if with_res else "no res"))
+                sys.stderr.flush()
+                e._conv(x, pk, relu=True, residual=r, res_mode=mode, out=out)
+                torch.cuda.synchronize()
+            capi.set_options(pair_prof=0)
+capi.set_options(pair_direct_out=1, pair_nt=0, pair_stages=0, pair_prof=0)

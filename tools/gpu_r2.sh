@@ -27,7 +27,7 @@ for s in $STAGES; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 20 -c 3 -f -o $O/${T}_prof_conv_tc python tools/profile_step.py --stage all --repeat 1 > $O/ncu_conv_tc.log 2>&1
       ls -la $O/*.ncu-rep ;;
     trainstep) timeout 900 python tools/train_step_bench.py --batch 4 --steps 4 2>&1 | tail -1 | tee $O/${T}_train_step.json | cut -c1-600 ;;
-    convprobe) timeout 600 python tools/conv_probe.py 2>&1 | tee $O/${T}_conv_probe.log | cut -c1-700 ;;
+    convprobe) timeout 600 python tools/conv_probe.py ${PROBE_CASES} 2>&1 | tee $O/${T}_conv_probe.log | cut -c1-900 ;;
     ncupair)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_pair_kernel -s 44 -c 3 -f -o $O/${T}_prof_conv_pair python tools/profile_step.py --stage all --repeat 1 > $O/ncu_conv_pair.log 2>&1
       ls -la $O/*.ncu-rep ;;
