@@ -106,10 +106,15 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsi
   acc += (unsigned long long)(clock64() - t0);
 }
 
-constexpr int kPairEpiWarps = 8;
+constexpr int kPairEpiWarps = 8;       // per group
+constexpr int kPairThreads = 64 + 2 * kPairEpiWarps * 32;   // producer + MMA warp + two epilogue groups of 8 warps
+__device__ __forceinline__ void epi_bar_sync_g(int grp) {
+  if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
 constexpr int kMaxResBufs = 4;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ OutMaps tmOut, const __grid_constant__ OutMaps tmRes, const TcParams p,
                  const PairExtra x) {
@@ -132,7 +137,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kPairEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kPairEpiWarps * (x.direct_out ? 2 : 1)); }
     for (int i = 0; i < kMaxResBufs; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
@@ -220,11 +225,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (prof_on && lane == 0) { atomicAdd(&x.prof[2], w_acc); atomicAdd(&x.prof[3], w_full); atomicAdd(&x.prof[4], (unsigned long long)(clock64() - t_start)); }
     }
   } else {
-    // ================= epilogue (warps 2..9 of both CTAs; each CTA drains its own 128 TMEM lanes) =================
+    // ================= epilogue (both CTAs; each CTA drains its own 128 TMEM lanes) =================
+    // Two groups of 8 warps (2..9, 10..17).  Direct-store mode: group g takes the 32-channel blocks i = g, g + 2, ... of a tile
+    // (measured with one group: ~1700 cycles per block of dependent tcgen05.ld -> FFMA -> cvt -> store work at two warps per
+    // scheduler = 13.6k cycles per 256-wide tile against a 6-10k cycle main loop of a K = 256 layer: epilogue-bound).
+    // Staged mode (float32 outputs): group 0 only.
+    const int grp = (warp - 2) >> 3;
+    if (grp == 1 && !x.direct_out) goto teardown;
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = ((warp - 2) >> 2) & 1;
     const int row = quad * 32 + lane;
-    const bool leader = threadIdx.x == 64;
+    const bool leader = threadIdx.x == 64 + grp * 256;
+    const int gstep = x.direct_out ? 2 : 1;
     const int nblk = p.Nt >> 5;
     const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
     const bool has_res = p.residual != LT_RES_NONE;
@@ -247,7 +259,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_load_5d(res_stage + buf * 16384, &tmRes.m[mi], &res_full[buf], ch * esz, a0, a1, a2, a3);
     };
     if (leader && has_res)
-      for (long c = 0; c < RB && c < total_blocks; ++c) issue_res(c);
+      for (long c = grp; c < RB && c < total_blocks; c += gstep) issue_res(c);
     uint32_t it = 0;
     long c = 0;
     unsigned long long w_accf = 0, w_res = 0;
@@ -272,8 +284,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ow = ow0 + dw, oh = oh0 + dh, od = od0 + dd, nb = nb0 + r_;
         const bool valid = ow < p.OW && oh < p.OH && od < p.OD && nb < p.N;
         const long opix = (((long)nb * p.FD + (od * p.osd + p.ood)) * p.FH + (oh * p.osh + p.ooh)) * p.FW + (ow * p.osw + p.oow);
-        for (int i = 0; i < nblk; ++i, ++c) {
-          const int rbuf = (int)(c & (RB - 1));
+        for (int i = grp; i < nblk; i += 2) {
+          const long cb = c + i;                 // block counter across this CTA's tiles
+          const int rbuf = (int)(cb & (RB - 1));
           float v[16], r[16];
           {
             uint32_t t1[16];
@@ -281,20 +294,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
           }
-          if (i == nblk - 1) {
+          if (i + 2 >= nblk) {                   // this group's last block of the tile: its part of the accumulator is drained
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty0 + as * 8u);
           }
           epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
           if (has_res) {
-            mbar_wait_t(&res_full[rbuf], (uint32_t)((c >> rb_shift) & 1), w_res, prof_on);
+            mbar_wait_t(&res_full[rbuf], (uint32_t)((cb >> rb_shift) & 1), w_res, prof_on);
             epi_load16(smem_u32(res_stage + rbuf * 16384), row, half, LT_FMT_S32, r);
           }
           epi_activate16(v, r, p.residual, p.relu);
           if (has_res) {
-            epi_bar_sync();                     // every thread has read res_stage[rbuf]: it may be refilled
-            if (leader && c + RB < total_blocks) issue_res(c + RB);
+            epi_bar_sync_g(grp);                // every thread of the group has read res_stage[rbuf]: it may be refilled
+            if (leader && cb + RB < total_blocks) issue_res(cb + RB);
           }
           if (valid) {
             int ch = n0 + i * 32;
@@ -312,6 +325,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             stg256(dst + 64, lo);
           }
         }
+        c += nblk;
         continue;
       }
       for (int i = 0; i < nblk; ++i, ++c) {
@@ -353,6 +367,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (prof_on && threadIdx.x == 64) { atomicAdd(&x.prof[5 + 8 * rank], w_accf); atomicAdd(&x.prof[6 + 8 * rank], w_res); atomicAdd(&x.prof[7 + 8 * rank], (unsigned long long)(clock64() - t_start)); }
   }
 
+teardown:
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();      // the peer may still read this CTA's operand half / signal its barriers until here
@@ -440,7 +455,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& t
     cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), st);
     x.prof = prof_buf;
   }
-  conv_pair_kernel<<<plan.grid, 320, smem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
+  conv_pair_kernel<<<plan.grid, kPairThreads, smem, st>>>(tmA, tmB, tmOut, tmRes, p, x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_pair_kernel: %s", cudaGetErrorString(e));
   if (want_prof) {   // debug only: synchronises
