@@ -75,6 +75,9 @@ typedef struct lt_options {
   int pair_nt, pair_stages; /* conv_pair A/B overrides: N tile (0 = heuristic, 128, 256), operand ring depth cap (0 = as many as fit) */
   int pair_prof;           /* conv_pair: 1 = per-role wait counters to stderr after every launch (debug; synchronises) */
   int pair_direct_out;     /* conv_pair: split-fp16 outputs stored from registers (1, default) or staged + TMA store (0) */
+  int fold_pair;           /* conv_fold: CTA-pair variant (cta_group::2, each CTA fetches half of every weight operand) (1, default) */
+  int fold_fullw;          /* conv_fold: full-width M tiles (W in {16, 32, 64}: every MMA row is an output position, the kw shift crosses
+                              warps through shared memory) (1, default) or 16/32-position x windows with K-1 wasted rows each (0) */
 } lt_options;
 void lt_default_options(lt_options* o);
 int lt_get_options(lt_options* o);

@@ -27,6 +27,8 @@ static lt_options make_default_options() {
   o.pair_nt = 0; o.pair_stages = 0;
   o.pair_prof = 0;
   o.pair_direct_out = 1;
+  o.fold_pair = 1;
+  o.fold_fullw = 1;
   return o;
 }
 static lt_options g_options = make_default_options();

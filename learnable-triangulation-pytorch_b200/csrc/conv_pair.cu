@@ -25,7 +25,16 @@
 //   empty[s]      per CTA; tcgen05.commit multicast from the leader frees the slot in both CTAs
 //   acc_full[a]   per CTA; commit multicast when a tile's last MMA has completed
 //   acc_empty[a]  leader's copy is used: 16 arrivals = 8 epilogue warps x 2 CTAs (remote mbarrier.arrive from the peer)
+//   res_full[b] / res_empty[b]  per CTA: residual staging buffer b filled by TMA / read by the 8 warps of the group that owns it
+//
+// Direct-store epilogue (split-fp16 outputs): no CTA-level barrier at all.  The per-channel scale / shift sit in shared memory
+// (loaded once per CTA), a dedicated warp (18) streams the residual tiles through the four staging buffers under the full/empty
+// barriers, and every epilogue warp runs tcgen05.ld -> affine -> residual -> ReLU -> split -> st.global on its own.  Measured
+// with ncu source counters on the 1x1 256 -> 1024 layer at 24x24 (profiles/r02c_pair_epilogue.md): the previous epilogue spent 27 %
+// of its stall samples on the scale / shift LDGs (L1-miss latency + LSU queue throttle behind the 32-sector row stores), 10 % in the
+// per-block bar.sync that recycled the residual buffer and 9 % in the MEMBAR.GPU + ERRBAR of a release.cluster remote arrive.
 #include "conv_tc_params.cuh"
+#include "pair_common.cuh"
 
 namespace lt {
 
@@ -36,62 +45,9 @@ struct PairExtra {
   int b_rows;   // weight rows per chunk = CoutP
   int res_bufs; // residual staging buffers (power of two): 16 KB blocks requested this many blocks ahead
   int direct_out;   // split-fp16 output rows are stored straight from registers
+  int off_aff, aff_n;   // per-channel scale [aff_n] and shift [aff_n] copied to shared memory at kernel start
   unsigned long long* prof;   // optional [16] cycle counters (lt_options.pair_prof): time each role spends waiting, summed over CTAs
 };
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives (once all previously issued MMAs have completed) on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// TMA loads whose completion is signalled on a barrier that may live in the peer (leader) CTA
-__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-// kind::f16 instruction descriptor for the pair: D = f32, A = B = fp16, K-major, M = 256, N = n
-__device__ __forceinline__ uint32_t make_idesc_f16_m256(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
 
 // 32 contiguous bytes (16 fp16 values of one voxel row) in one request
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
@@ -107,7 +63,8 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsi
 }
 
 constexpr int kPairEpiWarps = 8;       // per group
-constexpr int kPairThreads = 64 + 2 * kPairEpiWarps * 32;   // producer + MMA warp + two epilogue groups of 8 warps
+constexpr int kPairThreads = 64 + 2 * kPairEpiWarps * 32 + 32;   // producer + MMA warp + two epilogue groups of 8 warps + residual producer
+constexpr int kPairResWarp = 2 + 2 * kPairEpiWarps;
 __device__ __forceinline__ void epi_bar_sync_g(int grp) {
   if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
   else asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -127,7 +84,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc_full = empty + p.stages;   // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint64_t* res_full = acc_empty + 2;      // [kMaxResBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kMaxResBufs);
+  uint64_t* res_empty = res_full + kMaxResBufs;   // [kMaxResBufs] (direct-store epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + kMaxResBufs);
+  float* s_scale = reinterpret_cast<float*>(smem + x.off_aff);
+  float* s_shift = s_scale + x.aff_n;
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -138,9 +98,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kPairEpiWarps * (x.direct_out ? 2 : 1)); }
-    for (int i = 0; i < kMaxResBufs; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < kMaxResBufs; ++i) { mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], kPairEpiWarps); }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < x.aff_n; i += kPairThreads) { s_scale[i] = __ldg(p.scale + i); s_shift[i] = __ldg(p.shift + i); }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut.m[0]); }
   if (warp == 1) tmem_alloc2(tmem_slot, 512u);
   tc_fence_before();
@@ -158,6 +119,28 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     oh0 = (int)(t % p.th) * p.bh; t /= p.th;
     od0 = (int)(t % p.td) * p.bd; t /= p.td;
     nb0 = (int)t * p.bn;
+  };
+
+  // residual tiles: block c of this CTA's tile sequence (c runs across tiles) lives in staging buffer c % RB
+  const int nblk = p.Nt >> 5;
+  const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
+  const bool has_res = p.residual != LT_RES_NONE;
+  const long my_tiles = (x.total_tiles > pair_idx) ? (x.total_tiles - 1 - pair_idx) / n_pairs + 1 : 0;
+  const long total_blocks = my_tiles * nblk;
+  // The residual tiles stream through RB 16 KB buffers indexed by a block counter that runs across tiles: block c lives in
+  // buffer c % RB and is requested RB blocks ahead (a K-short 1x1 expand layer reads as many residual bytes as operand bytes:
+  // with two buffers its epilogue ran at the latency of one TMA round trip per block)
+  const int RB = x.res_bufs, rb_shift = (RB == 4) ? 2 : 1;
+  auto issue_res = [&](long c) {   // one thread: residual block c of this CTA's tile sequence
+    const long tile_c = pair_idx + (c / nblk) * n_pairs;
+    const int blk = (int)(c % nblk);
+    int a0, a1, a2, a3, an;
+    decode(tile_c, a0, a1, a2, a3, an);
+    const int buf = (int)(c & (RB - 1));
+    int ch = an + blk * 32, mi = 0;
+    if (p.n_maps > 1) { mi = ch / p.oc; ch -= mi * p.oc; }
+    mbar_expect_tx(&res_full[buf], 16384u);
+    tma_load_5d(res_stage + buf * 16384, &tmRes.m[mi], &res_full[buf], ch * esz, a0, a1, a2, a3);
   };
 
   if (warp == 0) {
@@ -224,6 +207,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (prof_on && lane == 0) { atomicAdd(&x.prof[2], w_acc); atomicAdd(&x.prof[3], w_full); atomicAdd(&x.prof[4], (unsigned long long)(clock64() - t_start)); }
     }
+  } else if (warp == kPairResWarp) {
+    // ================= residual producer (direct-store epilogue): block c -> buffer c % RB once its previous reader group is done ==========
+    if (x.direct_out && has_res) {
+      for (long c = 0; c < total_blocks; ++c) {
+        mbar_wait(&res_empty[c & (RB - 1)], (uint32_t)(((c >> rb_shift) & 1) ^ 1));
+        if (elect_one()) issue_res(c);
+        __syncwarp();
+      }
+    }
   } else {
     // ================= epilogue (both CTAs; each CTA drains its own 128 TMEM lanes) =================
     // Two groups of 8 warps (2..9, 10..17).  Direct-store mode: group g takes the 32-channel blocks i = g, g + 2, ... of a tile
@@ -236,30 +228,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = ((warp - 2) >> 2) & 1;
     const int row = quad * 32 + lane;
     const bool leader = threadIdx.x == 64 + grp * 256;
-    const int gstep = x.direct_out ? 2 : 1;
-    const int nblk = p.Nt >> 5;
-    const int esz = (p.out_format == LT_FMT_F32) ? 1 : 2;
-    const bool has_res = p.residual != LT_RES_NONE;
     const uint32_t acc_empty0 = map_to_cta(smem_u32(&acc_empty[0]), 0);
-    const long my_tiles = (x.total_tiles > pair_idx) ? (x.total_tiles - 1 - pair_idx) / n_pairs + 1 : 0;
-    const long total_blocks = my_tiles * nblk;
-    // The residual tiles stream through RB 16 KB buffers indexed by a block counter that runs across tiles: block c lives in
-    // buffer c % RB and is requested RB blocks ahead (a K-short 1x1 expand layer reads as many residual bytes as operand bytes:
-    // with two buffers its epilogue ran at the latency of one TMA round trip per block)
-    const int RB = x.res_bufs, rb_shift = (RB == 4) ? 2 : 1;
-    auto issue_res = [&](long c) {   // leader thread only: residual block c of this CTA's tile sequence
-      const long tile_c = pair_idx + (c / nblk) * n_pairs;
-      const int blk = (int)(c % nblk);
-      int a0, a1, a2, a3, an;
-      decode(tile_c, a0, a1, a2, a3, an);
-      const int buf = (int)(c & (RB - 1));
-      int ch = an + blk * 32, mi = 0;
-      if (p.n_maps > 1) { mi = ch / p.oc; ch -= mi * p.oc; }
-      mbar_expect_tx(&res_full[buf], 16384u);
-      tma_load_5d(res_stage + buf * 16384, &tmRes.m[mi], &res_full[buf], ch * esz, a0, a1, a2, a3);
-    };
-    if (leader && has_res)
-      for (long c = grp; c < RB && c < total_blocks; c += gstep) issue_res(c);
+    if (leader && has_res && !x.direct_out)
+      for (long c = 0; c < RB && c < total_blocks; ++c) issue_res(c);
     uint32_t it = 0;
     long c = 0;
     unsigned long long w_accf = 0, w_res = 0;
@@ -299,16 +270,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty0 + as * 8u);
           }
-          epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
+          epi_affine16_smem(v, s_scale, s_shift, n0 + i * 32 + half * 16);
           if (has_res) {
             mbar_wait_t(&res_full[rbuf], (uint32_t)((cb >> rb_shift) & 1), w_res, prof_on);
             epi_load16(smem_u32(res_stage + rbuf * 16384), row, half, LT_FMT_S32, r);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(&res_empty[rbuf]);   // this warp is done with res_stage[rbuf]
           }
           epi_activate16(v, r, p.residual, p.relu);
-          if (has_res) {
-            epi_bar_sync_g(grp);                // every thread of the group has read res_stage[rbuf]: it may be refilled
-            if (leader && cb + RB < total_blocks) issue_res(cb + RB);
-          }
           if (valid) {
             int ch = n0 + i * 32;
             long pix = opix;
@@ -343,7 +312,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(acc_empty0 + as * 8u);
         }
-        epi_affine16(v, p.scale, p.shift, n0 + i * 32 + half * 16);
+        epi_affine16_smem(v, s_scale, s_shift, n0 + i * 32 + half * 16);
         if (has_res) {
           mbar_wait(&res_full[rbuf], (uint32_t)((c >> rb_shift) & 1));
           epi_load16(smem_u32(res_stage + rbuf * 16384), row, half, p.out_format, r);
@@ -413,7 +382,7 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
   // shared memory: operand ring + 2 output staging tiles + (residual layers) 4 residual staging tiles, 16 KB each
   plan->res_bufs = d->residual != LT_RES_NONE ? kMaxResBufs : 0;
   plan->direct_out = (d->out_format == LT_FMT_S32 && opts().pair_direct_out) ? 1 : 0;
-  int stages = (227 * 1024 - 1024 - (plan->direct_out ? 0 : 32768) - plan->res_bufs * 16384 - 512) / stage_bytes;
+  int stages = (227 * 1024 - 1024 - (plan->direct_out ? 0 : 32768) - plan->res_bufs * 16384 - 8 * CoutP - 512) / stage_bytes;
   if (stages > 8) stages = 8;
   if (opts().pair_stages >= 2 && opts().pair_stages < stages) stages = opts().pair_stages;       // A/B override
   plan->stages = stages;
@@ -438,9 +407,11 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& t
   x.off_out = (ring + 1023) & ~1023;
   x.direct_out = plan.direct_out;
   x.off_res = x.off_out + (plan.direct_out ? 0 : 32768);
-  x.off_bar = x.off_res + plan.res_bufs * 16384;
+  x.off_aff = x.off_res + plan.res_bufs * 16384;      // scale [CoutP] | shift [CoutP]
+  x.aff_n = CoutP;
+  x.off_bar = x.off_aff + 8 * CoutP;
   x.res_bufs = plan.res_bufs ? plan.res_bufs : 2;
-  const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 4 + kMaxResBufs) * 8 + 16 + 1024;
+  const size_t smem = (size_t)x.off_bar + (2 * plan.stages + 4 + 2 * kMaxResBufs) * 8 + 16 + 1024;
   if (smem > 227 * 1024) return fail(LT_ERR_INVALID, "conv_pair: shared memory budget exceeded (%zu)", smem);
   static DeviceOnce configured;
   if (configured.first()) {

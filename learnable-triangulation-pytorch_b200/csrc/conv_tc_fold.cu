@@ -23,6 +23,7 @@
 // shift-adds with warp shuffles, applies scale/shift/residual/ReLU, compacts the valid rows into a 128B-swizzled
 // staging tile and stores it with TMA (which also clips partial tiles).
 #include "tc_common.cuh"
+#include "pair_common.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -38,6 +39,10 @@ struct FoldParams {
   int slab_bytes, a_slots;
   int b_resident, b_slots, b_bytes;
   int stage_rows;        // LINES * OWt
+  int fullw;             // 1: the M tile spans whole lines (WX == W, OWt == W): no x halo, the kw shift-add zero-fills at the line ends
+  int x_halo;            // x offset of the M tile's first row relative to its first output (pad, or 0 in full-width mode)
+  int pair;              // CTA-pair variant (see conv_fold_kernel<true>): b_bytes is the per-CTA share of a (kd, kh) weight tile
+  int off_xch;           // full-width, W > 32: edge rows exchanged between the epilogue warps of a line (floats, [half][quad][side][pad][pad][16])
   int out_format, relu, residual;
   const float* scale;
   const float* shift;
@@ -64,11 +69,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // differ from the slab / weight base by compile-time constants (no per-tap address arithmetic, parameter reloads, modulo).
 // Measured on B200 (LT_FOLD_PROF): the generic loop spent ~590 cycles per (kd, kh) step issuing 4 MMAs whose execution
 // takes 288 (3^3) / 336 (7^3) cycles and never waited on TMA or the epilogue: the kernel was bound by its own issue latency.
-template <int K>
+template <bool PAIR>
+__device__ __forceinline__ void fold_mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma2_f16(d, ad, bd, idesc, acc); else umma_f16(d, ad, bd, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void fold_commit(uint64_t* bar) {
+  if (PAIR) umma2_commit_mc(bar); else umma_commit(bar);
+}
+
+template <int K, bool PAIR>
 __device__ __forceinline__ void fold_issue_loop(const FoldParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t b_base, uint64_t* a_full,
                                                 uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty, uint64_t* acc_full,
                                                 uint64_t* acc_empty) {
-  const uint32_t idesc = make_idesc_f16(p.NF), idesc2 = make_idesc_f16(2 * p.NF);
+  const uint32_t idesc = PAIR ? make_idesc_f16_m256(p.NF) : make_idesc_f16(p.NF), idesc2 = PAIR ? make_idesc_f16_m256(2 * p.NF) : make_idesc_f16(2 * p.NF);
+  // pair: the A_lo x B_hi product reads the second region of a CTA's weight tile (this CTA's half of the B_hi rows), NF rows in
+  const uint64_t b2 = PAIR ? (uint64_t)((uint32_t)(p.NF * 64) >> 4) : 0ull;
+  const long tile0 = PAIR ? (long)(blockIdx.x >> 1) : (long)blockIdx.x, tstep = PAIR ? (long)(gridDim.x >> 1) : (long)gridDim.x;
+  const long ntile = PAIR ? (p.tiles + 1) / 2 : p.tiles;
   const uint32_t line_step = (uint32_t)(p.WX * 128) >> 4;     // descriptor address units (16 B) per slab line
   const uint32_t b_bytes = (uint32_t)p.b_bytes, b_step = b_bytes >> 4;
   const uint32_t slab_bytes = (uint32_t)p.slab_bytes, a_slots = (uint32_t)p.a_slots, b_slots = (uint32_t)p.b_slots;
@@ -76,14 +94,17 @@ __device__ __forceinline__ void fold_issue_loop(const FoldParams& p, uint32_t tm
   const bool resident = p.b_resident != 0;
   if (resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
   uint32_t slot = 0, a_ph = 0, bs = 0, b_ph = 0, it = 0;
-  for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+  const bool prof = p.prof != nullptr;
+  unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
+  const long long tstart = prof ? clock64() : 0;
+  for (long tile = tile0; tile < ntile; tile += tstep, ++it) {
     const uint32_t as = it & 1u;
-    mbar_wait(&acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+    mbar_wait_prof(&acc_empty[as], ((it >> 1) & 1u) ^ 1u, w_acc, prof);
     tc_fence_after();
     const uint32_t d1 = tmem_base + as * 2u * nf, d2 = d1 + nf;
 #pragma unroll 1
     for (int kd = 0; kd < K; ++kd) {
-      mbar_wait(&a_full[slot], a_ph);
+      mbar_wait_prof(&a_full[slot], a_ph, w_af, prof);
       tc_fence_after();
       const uint64_t ad0 = make_sw128_desc(a_base + slot * slab_bytes);
       const uint32_t first = kd ? 1u : 0u;
@@ -93,29 +114,29 @@ __device__ __forceinline__ void fold_issue_loop(const FoldParams& p, uint32_t tm
 #pragma unroll
           for (int kh = 0; kh < K; ++kh) {
             const uint64_t ad = ad0 + (uint64_t)((uint32_t)kh * line_step), bd = bd0 + (uint64_t)((uint32_t)kh * b_step);
-            umma_f16(d1, ad, bd, idesc2, kh == 0 ? first : 1u);   // A_hi(s0) x [B_hi;B_lo](s0) -> [D1|D2]
-            umma_f16(d2, ad + 4, bd, idesc, 1);                    // A_lo(s0) x B_hi(s0)        -> D2
-            umma_f16(d1, ad + 2, bd + 2, idesc2, 1);               // slice 1
-            umma_f16(d2, ad + 6, bd + 2, idesc, 1);
+            fold_mma<PAIR>(d1, ad, bd, idesc2, kh == 0 ? first : 1u);   // A_hi(s0) x [B_hi;B_lo](s0) -> [D1|D2]
+            fold_mma<PAIR>(d2, ad + 4, bd + b2, idesc, 1);               // A_lo(s0) x B_hi(s0)        -> D2
+            fold_mma<PAIR>(d1, ad + 2, bd + 2, idesc2, 1);               // slice 1
+            fold_mma<PAIR>(d2, ad + 6, bd + b2 + 2, idesc, 1);
           }
-          umma_commit(&a_empty[slot]);
-          if (kd == K - 1) umma_commit(&acc_full[as]);
+          fold_commit<PAIR>(&a_empty[slot]);
+          if (kd == K - 1) fold_commit<PAIR>(&acc_full[as]);
         }
         __syncwarp();
       } else {
 #pragma unroll
         for (int kh = 0; kh < K; ++kh) {
-          mbar_wait(&b_full[bs], b_ph);
+          mbar_wait_prof(&b_full[bs], b_ph, w_bf, prof);
           tc_fence_after();
           const uint64_t ad = ad0 + (uint64_t)((uint32_t)kh * line_step), bd = make_sw64_desc(b_base + bs * b_bytes);
           if (elect_one()) {
-            umma_f16(d1, ad, bd, idesc2, kh == 0 ? first : 1u);
-            umma_f16(d2, ad + 4, bd, idesc, 1);
-            umma_f16(d1, ad + 2, bd + 2, idesc2, 1);
-            umma_f16(d2, ad + 6, bd + 2, idesc, 1);
-            umma_commit(&b_empty[bs]);
-            if (kh == K - 1) umma_commit(&a_empty[slot]);
-            if (kh == K - 1 && kd == K - 1) umma_commit(&acc_full[as]);
+            fold_mma<PAIR>(d1, ad, bd, idesc2, kh == 0 ? first : 1u);
+            fold_mma<PAIR>(d2, ad + 4, bd + b2, idesc, 1);
+            fold_mma<PAIR>(d1, ad + 2, bd + 2, idesc2, 1);
+            fold_mma<PAIR>(d2, ad + 6, bd + b2 + 2, idesc, 1);
+            fold_commit<PAIR>(&b_empty[bs]);
+            if (kh == K - 1) fold_commit<PAIR>(&a_empty[slot]);
+            if (kh == K - 1 && kd == K - 1) fold_commit<PAIR>(&acc_full[as]);
           }
           __syncwarp();
           if (++bs == b_slots) { bs = 0; b_ph ^= 1u; }
@@ -124,8 +145,21 @@ __device__ __forceinline__ void fold_issue_loop(const FoldParams& p, uint32_t tm
       if (++slot == a_slots) { slot = 0; a_ph ^= 1u; }
     }
   }
+  if (prof && (threadIdx.x & 31) == 0) {
+    atomicAdd(&p.prof[3], w_acc); atomicAdd(&p.prof[4], w_af); atomicAdd(&p.prof[5], w_bf);
+    atomicAdd(&p.prof[6], (unsigned long long)(clock64() - tstart));
+  }
 }
 
+// PAIR = true: two CTAs of a cluster (one TPC) run the (kd, kh) steps of their two M tiles as ONE M = 256 tcgen05.mma.cta_group::2
+// sequence issued by the leader.  Why (ncu, profiles/r02c_fold_summary.md): with M = 128 a K slice reads A 4 KB + [B_hi;B_lo] 6 KB and
+// A_lo 4 KB + B_hi 3 KB of shared memory for 144 cycles of math -- 118 B/clk against the 128 B/clk the tensor core can fetch: the
+// operand-fetch path was 75 % busy and the math pipe 54 %.  In a pair each CTA fetches its own A tile but only HALF of every B
+// operand (a cta_group::2 MMA takes B rows [0, N/2) from CTA 0 and [N/2, N) from CTA 1): 87 B/clk.  Per-CTA weight tile of a
+// (kd, kh) step: rank 0 = [B_hi (NF rows) ; B_hi rows [0, NF/2)], rank 1 = [B_lo (NF rows) ; B_hi rows [NF/2, NF)] (64-byte rows).
+// Barriers: a_full / b_full / acc_empty live in the leader (the peer's TMA loads and epilogue warps signal them remotely),
+// a_empty / b_empty / acc_full are per CTA and receive the leader's multicast commits.
+template <bool PAIR>
 __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmOut,
@@ -148,27 +182,41 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int taps2 = p.K * p.K;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // this CTA's tiles: tile0, tile0 + tstep, ...  (pair k of P walks the tile pairs k, k + P, ...; rank r takes tile 2 * pair + r; an odd
+  // tile count leaves the last pair's rank 1 with tile == p.tiles, which decodes to n == N: loads zero-fill, stores are clipped)
+  const long tile0 = PAIR ? (long)(blockIdx.x >> 1) * 2 + rank : (long)blockIdx.x;
+  const long tstep = PAIR ? (long)(gridDim.x >> 1) * 2 : (long)gridDim.x;
+  const long tile_end = PAIR ? ((p.tiles + 1) / 2) * 2 : p.tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_slots; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 16 : kEpiThreads); }
     mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmOut); }
-  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  if (warp == 1) { if (PAIR) tmem_alloc2(tmem_slot, 512u); else tmem_alloc(tmem_slot, 512u); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // both CTAs' barriers initialised and TMEM allocated before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================= TMA producer (whole warp runs the loops; one elected lane issues) =================
+    // pair: "full" barriers are the leader's; its producer expects both CTAs' bytes, each CTA's loads signal it (cluster address)
+    const uint32_t a_full0 = PAIR ? map_to_cta(smem_u32(&a_full[0]), 0) : 0u, b_full0 = PAIR ? map_to_cta(smem_u32(&b_full[0]), 0) : 0u;
+    const uint32_t tx_mul = PAIR ? 2u : 1u;
+    const int b_rows = PAIR ? p.NF + p.NF / 2 : 2 * p.NF;      // rows of one (kd, kh) weight tile of this CTA
     if (p.b_resident) {
       if (elect_one()) {
-        mbar_expect_tx(&b_full[0], (uint32_t)(taps2 * p.b_bytes));
-        for (int t = 0; t < taps2; ++t) tma_load_2d(b_smem + (size_t)t * p.b_bytes, &tmB, &b_full[0], 0, t * 2 * p.NF);
+        if (rank == 0) mbar_expect_tx(&b_full[0], tx_mul * (uint32_t)(taps2 * p.b_bytes));
+        for (int t = 0; t < taps2; ++t) {
+          if (PAIR) tma2_load_2d(b_smem + (size_t)t * p.b_bytes, &tmB, b_full0, 0, (t * 2 + (int)rank) * b_rows);
+          else tma_load_2d(b_smem + (size_t)t * p.b_bytes, &tmB, &b_full[0], 0, t * b_rows);
+        }
       }
       __syncwarp();
     }
@@ -177,7 +225,7 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
     const bool prof = p.prof != nullptr;
     unsigned long long w_ae = 0, w_be = 0;
     const long long tstart = clock64();
-    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    for (long tile = tile0; tile < tile_end; tile += tstep) {
       long t = tile;
       const int xw = (int)(t % p.xwins); t /= p.xwins;
       const int yb = (int)(t % p.yblks); t /= p.yblks;
@@ -186,12 +234,14 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       for (int kd = 0; kd < p.K; ++kd) {
         mbar_wait_prof(&a_empty[slot], a_ph ^ 1u, w_ae, prof);
         if (elect_one()) {
-          if (p.dbg == 3 && pa >= (uint32_t)p.a_slots) {
+          if (!PAIR && p.dbg == 3 && pa >= (uint32_t)p.a_slots) {
             mbar_arrive(&a_full[slot]);          // debug: reuse stale slab contents, no TMA traffic
           } else {
-            mbar_expect_tx(&a_full[slot], (uint32_t)p.slab_bytes);
-            tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.pad, yb * p.LINES - p.pad,
-                        z + kd - p.pad, n);
+            if (rank == 0) mbar_expect_tx(&a_full[slot], tx_mul * (uint32_t)p.slab_bytes);
+            if (PAIR) tma2_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, a_full0 + slot * 8u, 0, xw * p.OWt - p.x_halo, yb * p.LINES - p.pad,
+                                   z + kd - p.pad, n);
+            else tma_load_5d(a_smem + (size_t)slot * p.slab_bytes, &tmA, &a_full[slot], 0, xw * p.OWt - p.x_halo, yb * p.LINES - p.pad,
+                             z + kd - p.pad, n);
           }
         }
         __syncwarp();
@@ -202,8 +252,9 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
             const uint32_t bs = bsl;
             mbar_wait_prof(&b_empty[bs], b_ph ^ 1u, w_be, prof);
             if (elect_one()) {
-              mbar_expect_tx(&b_full[bs], (uint32_t)p.b_bytes);
-              tma_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, &b_full[bs], 0, (kd * p.K + kh) * 2 * p.NF);
+              if (rank == 0) mbar_expect_tx(&b_full[bs], tx_mul * (uint32_t)p.b_bytes);
+              if (PAIR) tma2_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, b_full0 + bs * 8u, 0, ((kd * p.K + kh) * 2 + (int)rank) * b_rows);
+              else tma_load_2d(b_smem + (size_t)bs * p.b_bytes, &tmB, &b_full[bs], 0, (kd * p.K + kh) * b_rows);
             }
             __syncwarp();
             ++pb;
@@ -213,10 +264,12 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       }
     }
     if (prof && lane == 0) { atomicAdd(&p.prof[0], w_ae); atomicAdd(&p.prof[1], w_be); atomicAdd(&p.prof[2], (unsigned long long)(clock64() - tstart)); }
-  } else if (warp == 1 && p.fast_issue) {
-    // ================= MMA issuer, fast path: converged warp, kh taps unrolled, one election per slab =================
-    if (p.K == 3) fold_issue_loop<3>(p, tmem_base, smem_u32(a_smem), smem_u32(b_smem), a_full, a_empty, b_full, b_empty, acc_full, acc_empty);
-    else fold_issue_loop<7>(p, tmem_base, smem_u32(a_smem), smem_u32(b_smem), a_full, a_empty, b_full, b_empty, acc_full, acc_empty);
+  } else if (warp == 1 && (PAIR || p.fast_issue)) {
+    // ================= MMA issuer, fast path: converged warp, kh taps unrolled, one election per slab (pair: leader CTA only) ==========
+    if (rank == 0) {
+      if (p.K == 3) fold_issue_loop<3, PAIR>(p, tmem_base, smem_u32(a_smem), smem_u32(b_smem), a_full, a_empty, b_full, b_empty, acc_full, acc_empty);
+      else fold_issue_loop<7, PAIR>(p, tmem_base, smem_u32(a_smem), smem_u32(b_smem), a_full, a_empty, b_full, b_empty, acc_full, acc_empty);
+    }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp runs the loops; one elected lane issues) =================
     const uint32_t idesc = make_idesc_f16(p.NF), idesc2 = make_idesc_f16(2 * p.NF);
@@ -278,11 +331,14 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
     const bool leader = threadIdx.x == 64;
     const bool has_cols = half * 16 < p.NC;    // NC = 16: the upper half only writes the zero padding channels
     const uint32_t stage_bytes = (uint32_t)p.stage_rows * 128u;
+    float* xch = p.off_xch ? reinterpret_cast<float*>(smem + p.off_xch) : nullptr;
+    const bool right_nb = (((quad + 1) * 32) & (p.WX - 1)) != 0, left_nb = ((quad * 32) & (p.WX - 1)) != 0;   // neighbour warp in the same line
     uint32_t it = 0;
     const bool prof = p.prof != nullptr;
     unsigned long long w_accf = 0, w_res = 0;
     const long long tstart = clock64();
-    for (long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+    const uint32_t acc_empty0 = PAIR ? map_to_cta(smem_u32(&acc_empty[0]), 0) : 0u;
+    for (long tile = tile0; tile < tile_end; tile += tstep, ++it) {
       long t = tile;
       const int xw = (int)(t % p.xwins); t /= p.xwins;
       const int yb = (int)(t % p.yblks); t /= p.yblks;
@@ -306,24 +362,73 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
           tmem_ld16_nowait(tb + (uint32_t)(kw * p.NC), t1);
           tmem_ld16_nowait(tb + (uint32_t)(p.NF + kw * p.NC), t2);
           tmem_wait_ld();
+          if (!p.fullw) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float d = fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j]));
-            v[j] += __shfl_down_sync(0xffffffffu, d, kw);    // row (line, xi + kw) -> output (line, xi)
+            for (int j = 0; j < 16; ++j) {
+              const float d = fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j]));
+              v[j] += __shfl_down_sync(0xffffffffu, d, kw);    // row (line, xi + kw) -> output (line, xi)
+            }
+          } else {
+            // full-width tile: out(line, xi) += D(line, xi + s)[kw], s = kw - pad; rows outside [0, W) are the zero padding
+            const int sft = kw - p.pad, src = lane + sft;
+            const bool ok = (unsigned)(xi + sft) < (unsigned)p.WX && (unsigned)src < 32u;
+            float d[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              d[j] = fmaf(__uint_as_float(t2[j]), kLoInv, __uint_as_float(t1[j]));
+              const float t = __shfl_sync(0xffffffffu, d[j], src & 31);
+              v[j] += ok ? t : 0.0f;
+            }
+            if (xch) {
+              // lines wider than a warp: rows whose source sits in the neighbouring warp of the same line go through smem.
+              // low-edge row r' = lane publishes the blocks kw in (pad + r', 2 pad]; high-edge row r'' = 31 - lane the blocks [0, pad - r'')
+              int slot = -1;
+              if (lane < p.pad && kw > p.pad + lane) slot = (0 * p.pad + lane) * p.pad + (kw - p.pad - 1);
+              if (lane >= 32 - p.pad && kw < p.pad - (31 - lane)) slot = (1 * p.pad + (31 - lane)) * p.pad + kw;
+              if (slot >= 0) {
+                float* dst = xch + ((size_t)((half * 4 + quad) * 2 * p.pad * p.pad + slot) << 4);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+              }
+            }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[as]);              // accumulator stage drained: the MMA warp may start tile it+2
+      if (PAIR) {                               // accumulator stage drained (one arrival per warp, on the leader's barrier)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(acc_empty0 + as * 8u);
+      } else {
+        mbar_arrive(&acc_empty[as]);            // the MMA warp may start tile it+2
+      }
       if (p.dbg == 2) continue;
+      if (leader) bulk_wait_read<0>();          // previous tile's store has finished reading the staging buffer
+      epi_bar_sync();                           // + every warp's edge rows are published
+      if (xch && has_cols) {
+        const int pp = p.pad * p.pad;
+        if (right_nb && lane >= 32 - p.pad) {   // sources in the next warp's low edge
+          for (int sft = 32 - lane; sft <= p.pad; ++sft) {
+            const float* src = xch + ((size_t)((half * 4 + quad + 1) * 2 * pp + (lane + sft - 32) * p.pad + (sft - 1)) << 4);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) { const float4 q = *reinterpret_cast<const float4*>(src + j); v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w; }
+          }
+        }
+        if (left_nb && lane < p.pad) {          // sources in the previous warp's high edge
+          for (int sft = -p.pad; sft <= -(lane + 1); ++sft) {
+            const float* src = xch + ((size_t)((half * 4 + quad - 1) * 2 * pp + pp + (-1 - lane - sft) * p.pad + (sft + p.pad)) << 4);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) { const float4 q = *reinterpret_cast<const float4*>(src + j); v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w; }
+          }
+        }
+      }
       epi_affine16(v, p.scale, p.shift, half * 16);
       if (p.residual != LT_RES_NONE) {
         mbar_wait_prof(res_full, it & 1u, w_res, prof);
         if (keep) epi_load16(smem_u32(res_stage), srow, half, p.out_format, r);
       }
       epi_activate16(v, r, p.residual, p.relu);
-      if (leader) bulk_wait_read<0>();          // previous tile's store has finished reading the staging buffer
-      epi_bar_sync();
+      // the residual tile and the output tile share one staging buffer: every thread overwrites exactly the 16-channel half row it
+      // has just read, so no barrier is needed between the read and the write
       if (keep) epi_store16(smem_u32(out_stage), srow, half, p.out_format, v);
       fence_proxy_async();
       epi_bar_sync();
@@ -338,9 +443,10 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer may still read this CTA's weight half / signal its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512u);
+    if (PAIR) tmem_dealloc2(tmem_base, 512u); else tmem_dealloc(tmem_base, 512u);
   }
 }
 
@@ -364,6 +470,29 @@ __global__ void __launch_bounds__(256) pack_fold_weights_kernel(const float* __r
   }
 }
 
+// CTA-pair layout (conv_fold_kernel<true>): fp16 [kd][kh][rank][NF + NF/2 rows][32], 64 bytes per row:
+//   rank 0: B_hi rows (kw, co) [0, NF), then B_hi rows [0, NF/2);   rank 1: B_lo rows [0, NF), then B_hi rows [NF/2, NF)
+__global__ void __launch_bounds__(256) pack_fold_pair_weights_kernel(const float* __restrict__ w, sh_t* __restrict__ out, int K, int Cout, int NC) {
+  const int NF = K * NC, R = NF + NF / 2;
+  const long total = (long)K * K * 2 * R * 32;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % 32);
+    long r = i / 32;
+    const int row = (int)(r % R); r /= R;
+    const int rank = (int)(r % 2); r /= 2;
+    const int kh = (int)(r % K);
+    const int kd = (int)(r / K);
+    const bool second = row >= NF;                       // second region: this CTA's half of the B_hi rows
+    const int col = second ? (row - NF) + rank * (NF / 2) : row;
+    const bool want_lo = !second && rank == 1;
+    const int kw = col / NC, co = col % NC;
+    const float v = (co < Cout) ? w[((((long)kd * K + kh) * K + kw) * 32 + ci) * Cout + co] : 0.0f;
+    sh_t hi, lo;
+    split_s32(v, hi, lo);
+    out[i] = want_lo ? lo : hi;
+  }
+}
+
 int conv_fold_supported(const lt_conv_desc* d) {
   const bool cubic = d->KD == d->KH && d->KH == d->KW && (d->KW == 3 || d->KW == 7);
   const int p = d->KW / 2;
@@ -384,22 +513,29 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.K = d->KW; p.pad = d->KW / 2;
   p.NC = (d->Cout + 15) & ~15;
   p.NF = p.K * p.NC;
-  // x window: 16 rows keep 16-K+1 outputs per line, 32 rows keep 32-K+1; pick whichever computes fewer wasted rows
-  // (64-wide volumes: K=3 -> 16 (80 rows per line vs 96), K=7 -> 32 (96 vs 112))
-  p.WX = 16;
-  if (p.W >= 32 && ceil_div(p.W, 32 - p.K + 1) * 32 < ceil_div(p.W, 16 - p.K + 1) * 16) p.WX = 32;
-  p.wx_shift = p.WX == 32 ? 5 : 4;
+  // x window.  Full-width mode (W = 16 / 32 / 64): the M tile spans whole lines, every MMA row is an output position and the
+  // kw shift-add of the epilogue zero-fills at the line ends (the rows beyond them are the convolution's zero padding) -- no
+  // wasted rows.  Otherwise 16- or 32-row windows that keep 16-K+1 / 32-K+1 outputs per line (whichever wastes fewer rows).
+  p.fullw = (opts().fold_fullw && (p.W == 16 || p.W == 32 || p.W == 64)) ? 1 : 0;
+  if (p.fullw) {
+    p.WX = p.W;
+  } else {
+    p.WX = 16;
+    if (p.W >= 32 && ceil_div(p.W, 32 - p.K + 1) * 32 < ceil_div(p.W, 16 - p.K + 1) * 16) p.WX = 32;
+  }
+  p.wx_shift = p.WX == 64 ? 6 : (p.WX == 32 ? 5 : 4);
   p.LINES = 128 / p.WX;
-  p.OWt = p.WX - p.K + 1;
+  p.OWt = p.fullw ? p.WX : p.WX - p.K + 1;
+  p.x_halo = p.fullw ? 0 : p.pad;
   p.xwins = ceil_div(p.W, p.OWt);
   p.yblks = ceil_div(p.H, p.LINES);
   p.tiles = (long)p.N * p.D * p.yblks * p.xwins;
   const int slab_lines = p.LINES + p.K - 1;
   p.slab_bytes = p.WX * slab_lines * 128;
-  p.b_bytes = p.NF * 128;
+  // CTA pairs whenever there are at least two tiles (debug knock-outs stay on the one-CTA kernel)
+  p.pair = (opts().fold_pair && p.tiles >= 2 && sm_count() >= 2 && (opts().fold_debug & 15) == 0) ? 1 : 0;
+  p.b_bytes = p.pair ? p.NF * 96 : p.NF * 128;     // per-CTA share of a (kd, kh) weight tile: 1.5 NF or 2 NF rows of 64 bytes
   p.b_resident = (p.K * p.K * p.b_bytes <= 112 * 1024) ? 1 : 0;
-  p.b_slots = p.b_resident ? 1 : (p.WX == 32 ? 6 : 8);   // streamed weights: 14 KB tiles in flight hide the L2 latency of a (kd,kh) step
-  p.a_slots = p.b_resident ? (p.WX == 32 ? 3 : 5) : 3;    // slabs in flight
   p.stage_rows = p.LINES * p.OWt;
   p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
   p.scale = scale; p.shift = shift;
@@ -409,14 +545,30 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   if (want_prof && !prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long));
   p.prof = want_prof ? prof_buf : nullptr;
   const int fast_issue = opts().fold_fast_issue;
-  p.fast_issue = (fast_issue && p.dbg == 0 && p.prof == nullptr) ? 1 : 0;
+  p.fast_issue = (fast_issue && p.dbg == 0) ? 1 : 0;
   if (want_prof) cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
+  // shared memory: weights (resident: all K^2 (kd, kh) tiles; streamed: a ring of b_slots tiles that hides the L2 latency of a
+  // (kd, kh) step), the slab ring (as many slots as fit, at most 5), one staging tile, the edge-row exchange
+  const int xch_bytes = (p.fullw && p.WX > 32) ? 1024 * p.pad * p.pad : 0;
+  const int stage_bytes_out = up1024(p.stage_rows * 128);
+  const int budget = 227 * 1024 - 1024 - stage_bytes_out - xch_bytes - 512;
+  if (p.b_resident) {
+    p.b_slots = 1;
+  } else {
+    p.b_slots = p.WX == 16 ? 8 : 6;
+    while (p.b_slots > 3 && budget - up1024(p.b_slots * p.b_bytes) < 2 * up1024(p.slab_bytes)) --p.b_slots;
+  }
   const int b_region = p.b_resident ? p.K * p.K * p.b_bytes : p.b_slots * p.b_bytes;
+  p.a_slots = (budget - up1024(b_region)) / p.slab_bytes;
+  if (p.a_slots > 5) p.a_slots = 5;
+  if (!p.b_resident && p.a_slots > 3) p.a_slots = 3;
+  LT_REQUIRE(p.a_slots >= 2, "conv_fold: shared memory budget exceeded (slab %d B, weights %d B)", p.slab_bytes, b_region);
   p.off_b = 0;
   p.off_a = up1024(b_region);
   p.off_out = p.off_a + up1024(p.a_slots * p.slab_bytes);
-  p.off_res = p.off_out;   // residual tile and output tile share one staging buffer (read -> barrier -> overwrite)
-  p.off_bar = p.off_out + up1024(p.stage_rows * 128);
+  p.off_res = p.off_out;   // residual tile and output tile share one staging buffer (each thread overwrites the half row it has read)
+  p.off_xch = xch_bytes ? p.off_out + stage_bytes_out : 0;
+  p.off_bar = p.off_out + stage_bytes_out + xch_bytes;
   const size_t smem = (size_t)p.off_bar + (2 * p.a_slots + 2 * p.b_slots + 5) * 8 + 16 + 1024;
   LT_REQUIRE(smem <= 227 * 1024, "conv_fold: shared memory budget exceeded (%zu)", smem);
 
@@ -430,10 +582,14 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {32, (uint64_t)p.K * p.K * 2 * p.NF};
+    // the packed filter holds both layouts: [one-CTA: K^2 x 2 NF rows | pair: K^2 x 2 ranks x 1.5 NF rows], 64-byte rows, 64B swizzle
+    const size_t single_bytes = (size_t)p.K * p.K * 2 * p.NF * 64;
+    const uint8_t* wbase = reinterpret_cast<const uint8_t*>(weight) + (p.pair ? single_bytes : 0);
+    const uint32_t rows = (uint32_t)(p.pair ? p.NF + p.NF / 2 : 2 * p.NF);
+    const uint64_t dims[2] = {32, (uint64_t)p.K * p.K * (p.pair ? 2 : 1) * rows};
     const uint64_t str[1] = {64};
-    const uint32_t bx[2] = {32, (uint32_t)(2 * p.NF)};
-    int rc = make_map(&tmB, weight, 2, dims, str, bx, nullptr, 2);   // 64-byte rows, 64B swizzle
+    const uint32_t bx[2] = {32, rows};
+    int rc = make_map(&tmB, wbase, 2, dims, str, bx, nullptr, 2);
     if (rc) return rc;
   }
   {
@@ -452,11 +608,26 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   }
   static DeviceOnce configured;
   if (configured.first()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(conv_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  long grid = p.tiles < sm_count() ? p.tiles : sm_count();
-  conv_fold_kernel<<<(unsigned)grid, 320, smem, (cudaStream_t)stream>>>(tmA, tmB, tmOut, tmRes, p);
+  long grid;
+  if (p.pair) {
+    const long pairs = (p.tiles + 1) / 2, P = sm_count() / 2;
+    grid = 2 * (pairs < P ? pairs : P);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fold_kernel<true>, tmA, tmB, tmOut, tmRes, p);
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold_kernel<pair>: %s", cudaGetErrorString(e));
+  } else {
+    grid = p.tiles < sm_count() ? p.tiles : sm_count();
+    conv_fold_kernel<false><<<(unsigned)grid, 320, smem, (cudaStream_t)stream>>>(tmA, tmB, tmOut, tmRes, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LT_ERR_CUDA, "conv_fold_kernel: %s", cudaGetErrorString(e));
   if (want_prof) {   // debug only: synchronises
@@ -475,7 +646,8 @@ using namespace lt;
 
 extern "C" size_t lt_conv_fold_weight_bytes(int K, int Cout) {
   const int NC = (Cout + 15) & ~15;
-  return (size_t)K * K * K * NC * 64 * 2;
+  const size_t NF = (size_t)K * NC;
+  return (size_t)K * K * 2 * NF * 64 + (size_t)K * K * 3 * NF * 64;     // one-CTA layout + CTA-pair layout
 }
 
 extern "C" int lt_conv_fold_pack_weights(const float* w_tap_ci_co, void* packed, int K, int Cout, void* stream) {
@@ -486,5 +658,8 @@ extern "C" int lt_conv_fold_pack_weights(const float* w_tap_ci_co, void* packed,
   if (blocks > 65535) blocks = 65535;
   pack_fold_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_tap_ci_co, reinterpret_cast<sh_t*>(packed), K, Cout, NC);
   LT_CHECK_LAUNCH("pack_fold_weights_kernel");
+  sh_t* pair_base = reinterpret_cast<sh_t*>(reinterpret_cast<uint8_t*>(packed) + (size_t)K * K * 2 * K * NC * 64);
+  pack_fold_pair_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_tap_ci_co, pair_base, K, Cout, NC);
+  LT_CHECK_LAUNCH("pack_fold_pair_weights_kernel");
   return LT_OK;
 }

@@ -183,14 +183,28 @@ FOLD_CASES = [
     (32, 16, 7, (8, 8, 16), 1),       # 7^3, weights streamed
     (32, 16, 7, (7, 13, 25), 2),
     (32, 32, 3, (32, 32, 32), 2),     # many tiles per persistent CTA
-    (32, 16, 7, (5, 10, 64), 1),      # 7^3 on a 64-wide volume: 32-row x window (26 outputs per line), partial y block
+    (32, 16, 7, (5, 10, 64), 1),      # 7^3 on a 64-wide volume: full-width tiles (2 lines of 64), 3-row edge exchange
     (32, 16, 7, (4, 7, 71), 2),       # 32-row window with a partial last window (71 = 2*26 + 19)
+    (32, 32, 3, (3, 5, 64), 2),       # full-width tiles, 64-wide lines: the kw shift crosses warps (edge-row exchange), partial y block
+    (16, 32, 3, (4, 64, 64), 1),      # full-width 64^2 planes, 16 input channels stored 32 wide
+    (32, 16, 7, (9, 9, 32), 1),       # full-width, one line per warp
+    (32, 32, 3, (3, 5, 64), 1),       # odd tile count (9): the last pair's second CTA runs an out-of-range tile
 ]
 
 
 @pytest.mark.parametrize("case", FOLD_CASES)
 @pytest.mark.parametrize("with_res", [False, True])
-def test_conv_fold_vs_torch(case, with_res):
+@pytest.mark.parametrize("variant", ["pair", "one_cta", "windowed"])
+def test_conv_fold_vs_torch(case, with_res, variant):
+    # pair: cta_group::2 CTA pairs (default); one_cta: the single-CTA kernel; windowed: one CTA with 16/32-row x windows instead of full lines
+    capi.set_options(fold_pair=int(variant == "pair"), fold_fullw=int(variant != "windowed"))
+    try:
+        _fold_case(case, with_res)
+    finally:
+        capi.set_options(fold_pair=1, fold_fullw=1)
+
+
+def _fold_case(case, with_res):
     cin, cout, k, spatial, N = case
     torch.manual_seed(cin + cout + k + spatial[2])
     conv = torch.nn.Conv3d(cin, cout, k, 1, k // 2, bias=True).eval()
