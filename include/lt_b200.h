@@ -75,7 +75,10 @@ typedef struct lt_options {
   int pair_nt, pair_stages; /* conv_pair A/B overrides: N tile (0 = heuristic, 128, 256), operand ring depth cap (0 = as many as fit) */
   int pair_prof;           /* conv_pair: 1 = per-role wait counters to stderr after every launch (debug; synchronises) */
   int pair_direct_out;     /* conv_pair: split-fp16 outputs stored from registers (1, default) or staged + TMA store (0) */
-  int fold_pair;           /* conv_fold: CTA-pair variant (cta_group::2, each CTA fetches half of every weight operand) (1, default) */
+  int fold_pair;           /* conv_fold: CTA-pair variant (cta_group::2, each CTA fetches half of every weight operand): 0 = never, 1 = layers
+                              whose weights are streamed (7^3; default: measured 8 % faster there, neutral on the weight-resident 3^3), 2 = always */
+  int fold_direct;         /* conv_fold: full-width split-fp16 tiles stored from registers, residual read from global memory (default 0:
+                              measured 15-20 % slower than the staged TMA epilogue on the 3^3 layers -- 32-sector row stores / loads) */
   int fold_fullw;          /* conv_fold: full-width M tiles (W in {16, 32, 64}: every MMA row is an output position, the kw shift crosses
                               warps through shared memory) (1, default) or 16/32-position x windows with K-1 wasted rows each (0) */
 } lt_options;

@@ -28,6 +28,7 @@ static lt_options make_default_options() {
   o.pair_prof = 0;
   o.pair_direct_out = 1;
   o.fold_pair = 1;
+  o.fold_direct = 0;
   o.fold_fullw = 1;
   return o;
 }

@@ -49,12 +49,6 @@ struct PairExtra {
   unsigned long long* prof;   // optional [16] cycle counters (lt_options.pair_prof): time each role spends waiting, summed over CTAs
 };
 
-// 32 contiguous bytes (16 fp16 values of one voxel row) in one request
-__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
   if (!on) { mbar_wait(bar, parity); return; }
   const long long t0 = clock64();

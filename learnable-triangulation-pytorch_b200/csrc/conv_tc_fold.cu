@@ -44,6 +44,9 @@ struct FoldParams {
   int pair;              // CTA-pair variant (see conv_fold_kernel<true>): b_bytes is the per-CTA share of a (kd, kh) weight tile
   int off_xch;           // full-width, W > 32: edge rows exchanged between the epilogue warps of a line (floats, [half][quad][side][pad][pad][16])
   int out_format, relu, residual;
+  int direct;            // full-width, split-fp16 output: rows go from registers to global memory (no staging tile, no TMA store / residual load)
+  const void* res;
+  void* out;
   const float* scale;
   const float* shift;
   // smem offsets (bytes from the 1024-aligned base)
@@ -331,7 +334,8 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
     const bool leader = threadIdx.x == 64;
     const bool has_cols = half * 16 < p.NC;    // NC = 16: the upper half only writes the zero padding channels
     const uint32_t stage_bytes = (uint32_t)p.stage_rows * 128u;
-    float* xch = p.off_xch ? reinterpret_cast<float*>(smem + p.off_xch) : nullptr;
+    float* const xch_base = p.off_xch ? reinterpret_cast<float*>(smem + p.off_xch) : nullptr;
+    const int xch_floats = 256 * p.pad * p.pad;     // one buffer: [half][quad][side][pad][pad][16]
     const bool right_nb = (((quad + 1) * 32) & (p.WX - 1)) != 0, left_nb = ((quad * 32) & (p.WX - 1)) != 0;   // neighbour warp in the same line
     uint32_t it = 0;
     const bool prof = p.prof != nullptr;
@@ -345,7 +349,27 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
       const int z = (int)(t % p.D);
       const int n = (int)(t / p.D);
       const uint32_t as = it & 1u;
-      if (leader && p.residual != LT_RES_NONE) {
+      float* const xch = xch_base ? xch_base + ((p.direct && (it & 1u)) ? xch_floats : 0) : nullptr;
+      // direct mode: this thread's voxel row (16 channels = 32 B of high halves + 32 B of low halves) goes straight from registers
+      // to global memory and its residual comes straight from global memory, requested here, a whole accumulator wait ahead.
+      // (The staged path queues its TMA store behind every slab load the producer has already issued -- the SM's TMA queue is
+      // FIFO -- and the next tile cannot touch the staging buffer before that store has drained: ~3600 cycles per tile measured
+      // against 2592 cycles of MMA work for the 3^3 layers.)
+      uint32_t rh[8], rl[8];
+      uint8_t* gdst = nullptr;
+      bool gvalid = false;
+      if (p.direct) {
+        const int y = yb * p.LINES + line;
+        gvalid = y < p.H && n < p.N;
+        const long voxel = (((long)n * p.D + z) * p.H + y) * p.W + xi;
+        gdst = reinterpret_cast<uint8_t*>(p.out) + voxel * 128 + half * 32;
+        if (p.residual != LT_RES_NONE && gvalid) {
+          const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(p.res) + voxel * 128 + half * 32;
+          ldg256(gsrc, rh);
+          ldg256(gsrc + 64, rl);
+        }
+      }
+      if (leader && p.residual != LT_RES_NONE && !p.direct) {
         bulk_wait_read<0>();                    // staging buffer is shared: the previous tile's store must have drained it
         mbar_expect_tx(res_full, stage_bytes);
         tma_load_5d(res_stage, &tmRes, res_full, 0, xw * p.OWt, yb * p.LINES, z, n);
@@ -402,8 +426,8 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
         mbar_arrive(&acc_empty[as]);            // the MMA warp may start tile it+2
       }
       if (p.dbg == 2) continue;
-      if (leader) bulk_wait_read<0>();          // previous tile's store has finished reading the staging buffer
-      epi_bar_sync();                           // + every warp's edge rows are published
+      if (leader && !p.direct) bulk_wait_read<0>();   // previous tile's store has finished reading the staging buffer
+      if (!p.direct || xch) epi_bar_sync();     // staging buffer free / every warp's edge rows are published
       if (xch && has_cols) {
         const int pp = p.pad * p.pad;
         if (right_nb && lane >= 32 - p.pad) {   // sources in the next warp's low edge
@@ -422,6 +446,25 @@ __global__ void __launch_bounds__(320, 1) conv_fold_kernel(const __grid_constant
         }
       }
       epi_affine16(v, p.scale, p.shift, half * 16);
+      if (p.direct) {
+        if (p.residual != LT_RES_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rh[j])), b = __half22float2(*reinterpret_cast<const __half2*>(&rl[j]));
+            r[2 * j] = gvalid ? fmaf(b.x, kLoInv, a.x) : 0.0f;
+            r[2 * j + 1] = gvalid ? fmaf(b.y, kLoInv, a.y) : 0.0f;
+          }
+        }
+        epi_activate16(v, r, p.residual, p.relu);
+        if (gvalid) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_s32x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+          stg256(gdst, hi);
+          stg256(gdst + 64, lo);
+        }
+        continue;                               // (the edge-row exchange is double-buffered by tile parity: no second barrier)
+      }
       if (p.residual != LT_RES_NONE) {
         mbar_wait_prof(res_full, it & 1u, w_res, prof);
         if (keep) epi_load16(smem_u32(res_stage), srow, half, p.out_format, r);
@@ -532,13 +575,18 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   p.tiles = (long)p.N * p.D * p.yblks * p.xwins;
   const int slab_lines = p.LINES + p.K - 1;
   p.slab_bytes = p.WX * slab_lines * 128;
-  // CTA pairs whenever there are at least two tiles (debug knock-outs stay on the one-CTA kernel)
-  p.pair = (opts().fold_pair && p.tiles >= 2 && sm_count() >= 2 && (opts().fold_debug & 15) == 0) ? 1 : 0;
+  // CTA pairs (fold_pair = 2: always; 1: when the one-CTA kernel would have to stream its weights) if there are at least two tiles;
+  // debug knock-outs stay on the one-CTA kernel
+  const bool single_resident = p.K * p.K * p.NF * 128 <= 112 * 1024;
+  p.pair = ((opts().fold_pair == 2 || (opts().fold_pair == 1 && !single_resident)) && p.tiles >= 2 && sm_count() >= 2 &&
+            (opts().fold_debug & 15) == 0) ? 1 : 0;
   p.b_bytes = p.pair ? p.NF * 96 : p.NF * 128;     // per-CTA share of a (kd, kh) weight tile: 1.5 NF or 2 NF rows of 64 bytes
   p.b_resident = (p.K * p.K * p.b_bytes <= 112 * 1024) ? 1 : 0;
   p.stage_rows = p.LINES * p.OWt;
   p.out_format = d->out_format; p.relu = d->relu; p.residual = d->residual;
   p.scale = scale; p.shift = shift;
+  p.res = residual; p.out = out;
+  p.direct = (p.fullw && d->out_format == LT_FMT_S32 && opts().fold_direct) ? 1 : 0;
   p.dbg = opts().fold_debug & 15;
   static unsigned long long* prof_buf = nullptr;
   const bool want_prof = (opts().fold_debug & 16) != 0;
@@ -549,8 +597,8 @@ int conv_fold_fwd(const lt_conv_desc* d, const void* in, const void* weight, con
   if (want_prof) cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
   // shared memory: weights (resident: all K^2 (kd, kh) tiles; streamed: a ring of b_slots tiles that hides the L2 latency of a
   // (kd, kh) step), the slab ring (as many slots as fit, at most 5), one staging tile, the edge-row exchange
-  const int xch_bytes = (p.fullw && p.WX > 32) ? 1024 * p.pad * p.pad : 0;
-  const int stage_bytes_out = up1024(p.stage_rows * 128);
+  const int xch_bytes = (p.fullw && p.WX > 32) ? 1024 * p.pad * p.pad * (p.direct ? 2 : 1) : 0;
+  const int stage_bytes_out = p.direct ? 0 : up1024(p.stage_rows * 128);
   const int budget = 227 * 1024 - 1024 - stage_bytes_out - xch_bytes - 512;
   if (p.b_resident) {
     p.b_slots = 1;

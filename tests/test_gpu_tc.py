@@ -194,14 +194,16 @@ FOLD_CASES = [
 
 @pytest.mark.parametrize("case", FOLD_CASES)
 @pytest.mark.parametrize("with_res", [False, True])
-@pytest.mark.parametrize("variant", ["pair", "one_cta", "windowed"])
+@pytest.mark.parametrize("variant", ["pair", "one_cta", "staged", "windowed", "default"])
 def test_conv_fold_vs_torch(case, with_res, variant):
-    # pair: cta_group::2 CTA pairs (default); one_cta: the single-CTA kernel; windowed: one CTA with 16/32-row x windows instead of full lines
-    capi.set_options(fold_pair=int(variant == "pair"), fold_fullw=int(variant != "windowed"))
+    # pair: cta_group::2 CTA pairs, register -> global epilogue (default); one_cta: the single-CTA kernel; staged: pairs with the
+    # shared-memory staging tile + TMA store / residual load; windowed: one CTA with 16/32-row x windows instead of full lines
+    if variant != "default":
+        capi.set_options(fold_pair=2 * int(variant in ("pair", "staged")), fold_fullw=int(variant != "windowed"), fold_direct=int(variant != "staged"))
     try:
         _fold_case(case, with_res)
     finally:
-        capi.set_options(fold_pair=1, fold_fullw=1)
+        capi.set_options(fold_pair=1, fold_fullw=1, fold_direct=0)
 
 
 def _fold_case(case, with_res):
