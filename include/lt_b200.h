@@ -178,6 +178,11 @@ int lt_softargmax3d_fwd(const float* logits, long batch_stride, long voxel_strid
                         const float* coord, float* volumes_out, float* keypoints_out,
                         void* workspace, size_t workspace_bytes,
                         int B, int J, long nvox, float multiplier, int softmax, void* stream);
+/* Second half of lt_softargmax3d_fwd for compact channels-last logits (chan_stride 1, 20 <= voxel_stride <= 32) whose statistics were
+ * produced by lt_v2v_tail_stats_fwd: merge of the G partials per (sample, joint) -> keypoints_out, then volumes_out (may be NULL). */
+int lt_softargmax3d_finish_fwd(const float* logits, long batch_stride, long voxel_stride, const float* coord, float* volumes_out,
+                               float* keypoints_out, void* workspace, size_t workspace_bytes, int B, int J, long nvox, int G,
+                               float multiplier, int softmax, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * N-d convolution as implicit GEMM with fused epilogue.  Replaces nn.Conv2d/Conv3d (+ folded
@@ -253,6 +258,15 @@ int lt_conv_pair_eligible(const lt_conv_desc* desc);
 int lt_v2v_tail_fwd(const void* x, const void* w1, const void* w2, const void* w3, const float* scale1, const float* shift1,
                     const float* scale2, const float* shift2, const float* scale3, const float* bias3, float* logits, long rows, int FC,
                     void* stream);
+/* The same kernel with the STATISTICS PASS of the volumetric soft-argmax (op.py:84-96: integrate_tensor_3d_with_coordinates) fused into
+ * the epilogue that produces the logits (v2v.py:168-169 -> op.py:88-89): x [B * nvox][64], nvox % 128 == 0, FC <= 20, coord
+ * [B][nvox][3].  `workspace` (lt_softargmax3d_workspace_bytes(B, J, nvox)) receives the per-CTA online-softmax partials
+ * [B][*n_partials][J][5]; lt_softargmax3d_finish_fwd with G = *n_partials (a host value known at launch time, safe under stream
+ * capture) merges them into the key points and writes the normalised volumes.  softmax: 1 = softmax, 0 = ReLU (volume_softmax:false). */
+int lt_v2v_tail_stats_fwd(const void* x, const void* w1, const void* w2, const void* w3, const float* scale1, const float* shift1,
+                          const float* scale2, const float* shift2, const float* scale3, const float* bias3, float* logits, int B,
+                          long nvox, int FC, const float* coord, int J, float multiplier, int softmax, void* workspace,
+                          size_t workspace_bytes, int* n_partials, void* stream);
 
 /* kw-folded weight packing: float32 [K^3][32][Cout] (DEVICE) -> split-fp16 [kd][kh][kw*NC + co][64], NC = round_up(Cout, 16). */
 size_t lt_conv_fold_weight_bytes(int K, int Cout);

@@ -77,6 +77,10 @@ SIGNATURES = {
     "lt_conv_pair_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_conv_pair_eligible": (c_int, [ctypes.POINTER(ConvDesc)]),
     "lt_v2v_tail_fwd": (c_int, [c_void_p] * 11 + [c_long, c_int, c_void_p]),
+    "lt_v2v_tail_stats_fwd": (c_int, [c_void_p] * 11 + [c_int, c_long, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_size_t,
+                                      ctypes.POINTER(c_int), c_void_p]),
+    "lt_softargmax3d_finish_fwd": (c_int, [c_void_p, c_long, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_long, c_int,
+                                           c_float, c_int, c_void_p]),
     "lt_conv_fold_weight_bytes": (c_size_t, [c_int, c_int]),
     "lt_conv_fold_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lt_maxpool_fwd": (c_int, [c_void_p, c_void_p] + [c_int] * 18 + [c_void_p]),
@@ -289,6 +293,21 @@ def conv_pair_eligible(desc):
 def v2v_tail(x, w1, w2, w3, scale1, shift1, scale2, shift2, scale3, bias3, logits, rows, fc):
     _check(lib().lt_v2v_tail_fwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(scale1), _ptr(shift1), _ptr(scale2), _ptr(shift2), _ptr(scale3), _ptr(bias3),
                                  _ptr(logits), rows, fc, _stream()), "lt_v2v_tail_fwd")
+
+
+def v2v_tail_stats(x, w1, w2, w3, scale1, shift1, scale2, shift2, scale3, bias3, logits, B, nvox, fc, coord, J, multiplier, softmax, workspace):
+    """lt_v2v_tail_fwd + the statistics pass of the volumetric soft-argmax; returns the number of partials per sample (for softargmax3d_finish)."""
+    n = c_int(0)
+    _check(lib().lt_v2v_tail_stats_fwd(_ptr(x), _ptr(w1), _ptr(w2), _ptr(w3), _ptr(scale1), _ptr(shift1), _ptr(scale2), _ptr(shift2), _ptr(scale3),
+                                       _ptr(bias3), _ptr(logits), B, nvox, fc, _ptr(coord), J, float(multiplier), int(softmax), _ptr(workspace),
+                                       workspace.numel() * workspace.element_size(), ctypes.byref(n), _stream()), "lt_v2v_tail_stats_fwd")
+    return n.value
+
+
+def softargmax3d_finish(logits, batch_stride, voxel_stride, coord, volumes_out, keypoints_out, workspace, B, J, nvox, G, multiplier, softmax):
+    _check(lib().lt_softargmax3d_finish_fwd(_ptr(logits), batch_stride, voxel_stride, _ptr(coord), _ptr(volumes_out), _ptr(keypoints_out),
+                                            _ptr(workspace), workspace.numel() * workspace.element_size(), B, J, nvox, G, float(multiplier),
+                                            int(softmax), _stream()), "lt_softargmax3d_finish_fwd")
 
 
 def conv_fold_weight_bytes(k, cout):

@@ -13,62 +13,12 @@
 // Algorithmic bytes per sample (J=17, 64^3): 17.83 MB logits + 3.15 MB coords (+17.83 MB volume
 // write) = 20.97 MB keypoints-only / 38.80 MB with volumes.
 #include "tc_common.cuh"
+#include "softargmax_common.cuh"
 #include <stdlib.h>
 
 namespace lt {
 
 constexpr int kChunk = 2048;  // voxels per pass-1 CTA
-
-struct SoftState {
-  float m, d, sx, sy, sz;
-};
-
-__device__ __forceinline__ void st_init(SoftState& s, bool softmax) {
-  s.m = softmax ? -INFINITY : 0.0f;
-  s.d = s.sx = s.sy = s.sz = 0.0f;
-}
-// add one element with logit l and coordinate (x, y, z)
-__device__ __forceinline__ void st_push(SoftState& s, float l, float x, float y, float z, bool softmax) {
-  if (softmax) {
-    const float mn = fmaxf(s.m, l);
-    const float r = __expf(s.m - mn);   // rescale of the running sums (exp(-inf) = 0 on first element)
-    const float e = __expf(l - mn);
-    s.d = fmaf(s.d, r, e);
-    s.sx = fmaf(s.sx, r, e * x);
-    s.sy = fmaf(s.sy, r, e * y);
-    s.sz = fmaf(s.sz, r, e * z);
-    s.m = mn;
-  } else {
-    const float e = fmaxf(l, 0.0f);     // op.py:90-91: ReLU, no normalisation (d = mass, only used by mode 2, op.py:25-41)
-    s.d += e;
-    s.sx = fmaf(e, x, s.sx);
-    s.sy = fmaf(e, y, s.sy);
-    s.sz = fmaf(e, z, s.sz);
-  }
-}
-__device__ __forceinline__ void st_merge(SoftState& a, const SoftState& b, bool softmax) {
-  if (softmax) {
-    const float mn = fmaxf(a.m, b.m);
-    const float ra = (a.m == -INFINITY) ? 0.0f : __expf(a.m - mn);
-    const float rb = (b.m == -INFINITY) ? 0.0f : __expf(b.m - mn);
-    a.d = a.d * ra + b.d * rb;
-    a.sx = a.sx * ra + b.sx * rb;
-    a.sy = a.sy * ra + b.sy * rb;
-    a.sz = a.sz * ra + b.sz * rb;
-    a.m = mn;
-  } else {
-    a.d += b.d; a.sx += b.sx; a.sy += b.sy; a.sz += b.sz;
-  }
-}
-__device__ __forceinline__ SoftState st_shfl_xor(const SoftState& s, int o) {
-  SoftState r;
-  r.m = __shfl_xor_sync(0xffffffffu, s.m, o);
-  r.d = __shfl_xor_sync(0xffffffffu, s.d, o);
-  r.sx = __shfl_xor_sync(0xffffffffu, s.sx, o);
-  r.sy = __shfl_xor_sync(0xffffffffu, s.sy, o);
-  r.sz = __shfl_xor_sync(0xffffffffu, s.sz, o);
-  return r;
-}
 
 struct SoftParams {
   const float* logits;
@@ -239,8 +189,8 @@ constexpr int kStreamStageBytes = kStreamLogitBytes + kStreamCoordBytes;
 constexpr int kStreamScratchBytes = 20480;             // CTA merge scratch [256][20] floats (stats kernel)
 constexpr int kStreamSmemBytes = kStreamStages * kStreamStageBytes + kStreamScratchBytes + 128 + 128;
 constexpr int kMaxStreamCtas = 640;
+constexpr int kMaxPartials = 1024;      // partial slots per sample the workspace is sized for (fused tail: 3 CTAs per SM)
 constexpr long kStreamMinVoxels = 16384;
-constexpr float kLog2e = 1.4426950408889634f;
 
 struct StreamParams {
   const float* logits;    // [B][nvox][vs]
@@ -260,12 +210,6 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float ex2f(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
 // producer warp: stream the CTA's tiles in order; reverse = samples from last to first
 __device__ __forceinline__ void stream_producer(const StreamParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, bool with_coord,
                                                 bool reverse) {
@@ -288,30 +232,6 @@ __device__ __forceinline__ void stream_producer(const StreamParams& p, uint8_t* 
       if (with_coord) bulk_load_1d(dst + kStreamLogitBytes, p.coord + ((long)b * p.nvox + v0) * 3, cb, &full[s]);
     }
     __syncwarp();
-  }
-}
-
-// fold four (logit, coordinate) pairs into one online-softmax state: one rescale + four exponentials
-template <bool SM>
-__device__ __forceinline__ void st_push4(SoftState& s, const float (&l)[4], const float (&x)[4], const float (&y)[4], const float (&z)[4]) {
-  if (SM) {
-    const float mn = fmaxf(fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3])), s.m);
-    if (mn == -INFINITY) return;                 // nothing but padding so far
-    const float nb = -mn * kLog2e;
-    const float r = ex2f(fmaf(s.m, kLog2e, nb)); // exp(m_old - m_new); 0 for the first batch (m_old = -inf)
-    const float e0 = ex2f(fmaf(l[0], kLog2e, nb)), e1 = ex2f(fmaf(l[1], kLog2e, nb));
-    const float e2 = ex2f(fmaf(l[2], kLog2e, nb)), e3 = ex2f(fmaf(l[3], kLog2e, nb));
-    s.d = fmaf(s.d, r, (e0 + e1) + (e2 + e3));
-    s.sx = fmaf(s.sx, r, fmaf(e0, x[0], fmaf(e1, x[1], fmaf(e2, x[2], e3 * x[3]))));
-    s.sy = fmaf(s.sy, r, fmaf(e0, y[0], fmaf(e1, y[1], fmaf(e2, y[2], e3 * y[3]))));
-    s.sz = fmaf(s.sz, r, fmaf(e0, z[0], fmaf(e1, z[1], fmaf(e2, z[2], e3 * z[3]))));
-    s.m = mn;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float e = fmaxf(l[k], 0.0f);         // op.py:90-91: ReLU, no normalisation
-      s.sx = fmaf(e, x[k], s.sx); s.sy = fmaf(e, y[k], s.sy); s.sz = fmaf(e, z[k], s.sz);
-    }
   }
 }
 
@@ -492,6 +412,52 @@ __global__ void __launch_bounds__(kStreamThreads, 2) stream_normalize_kernel(con
   }
 }
 
+static bool stream_shape_ok(const float* logits, long batch_stride, long voxel_stride, const float* coord, const float* volumes_out, int J,
+                            long nvox) {
+  return J <= 32 && voxel_stride >= J && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 8 == 0 && batch_stride % 4 == 0 &&
+         nvox >= kStreamMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0 &&
+         (!volumes_out || ((uintptr_t)volumes_out & 31) == 0);
+}
+
+// tile geometry of the streaming kernels for one problem (everything but the partial / stats pointers and G)
+static int stream_setup(StreamParams& f, const float* logits, long batch_stride, int vs, const float* coord, float* volumes_out, float* keypoints_out,
+                        int B, int J, long nvox, float multiplier, int softmax) {
+  f.logits = logits; f.coord = coord; f.volumes = volumes_out; f.keypoints = keypoints_out;
+  f.bs = batch_stride; f.nvox = nvox; f.vs = vs; f.B = B; f.J = J;
+  f.Q = f.vs / 4;
+  f.RPI = (kStreamConsumers / f.Q) & ~1;      // rows per pass, even -> T = 4 * RPI is a multiple of 8 rows
+  f.T = 4 * f.RPI;
+  f.tiles = (int)((nvox + f.T - 1) / f.T);
+  f.total_tiles = (long)f.tiles * B;
+  f.mult = multiplier; f.softmax = softmax;
+  LT_REQUIRE(f.T * f.vs * 4 <= kStreamLogitBytes && f.T * 12 <= kStreamCoordBytes, "softargmax stream: tile does not fit (vs=%d)", f.vs);
+  LT_REQUIRE(f.total_tiles < (1L << 31), "softargmax stream: too many tiles");
+  static DeviceOnce configured;
+  if (configured.first()) {
+    cudaError_t e = cudaFuncSetAttribute(stream_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
+    if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  return LT_OK;
+}
+
+// merge of the f.G partials per (sample, joint) -> key points, (max, 1 / sum); then the normalisation pass (if volumes are requested)
+static int stream_finish(const StreamParams& f, cudaStream_t st) {
+  softargmax_stream_merge<<<ceil_div((long)f.B * f.J * 32, 128), 128, 0, st>>>(f);
+  LT_CHECK_LAUNCH("softargmax_stream_merge");
+  if (f.volumes) {
+    int G = 2 * sm_count();
+    if (G > kMaxStreamCtas) G = kMaxStreamCtas;
+    if ((long)G > f.total_tiles) G = (int)f.total_tiles;
+    if (f.softmax) stream_normalize_kernel<true><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
+    else stream_normalize_kernel<false><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
+    LT_CHECK_LAUNCH("stream_normalize_kernel");
+  }
+  return LT_OK;
+}
+
 static inline int n_chunks(long nvox) { return (int)((nvox + kChunk - 1) / kChunk); }
 
 }  // namespace lt
@@ -499,7 +465,7 @@ static inline int n_chunks(long nvox) { return (int)((nvox + kChunk - 1) / kChun
 extern "C" size_t lt_softargmax3d_workspace_bytes(int B, int J, long nvox) {
   const size_t classic = (size_t)B * J * ((size_t)lt::n_chunks(nvox) * 5 + 2) * sizeof(float);
   // streaming path: partial [B][G <= kMaxStreamCtas][J][5] + stats [B][J][2]
-  const size_t stream = (size_t)B * ((size_t)lt::kMaxStreamCtas * J * 5 + (size_t)J * 2) * sizeof(float) + 64;
+  const size_t stream = (size_t)B * ((size_t)lt::kMaxPartials * J * 5 + (size_t)J * 2) * sizeof(float) + 64;
   return classic > stream ? classic : stream;
 }
 
@@ -524,46 +490,21 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
   LT_REQUIRE(softmax >= 0 && softmax <= 2, "softargmax3d: mode must be 0 (ReLU), 1 (softmax) or 2 (ReLU, mass-normalised coordinates)");
   // ---- streaming path ----
   const int stream_mode = opts().softargmax_stream;
-  if (stream_mode && softmax != 2 && cl && voxel_stride % 4 == 0 && voxel_stride >= 20 && voxel_stride <= 32 && nvox % 8 == 0 && batch_stride % 4 == 0 &&
-      nvox >= kStreamMinVoxels && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)coord & 15) == 0 &&
-      (!volumes_out || ((uintptr_t)volumes_out & 31) == 0)) {
+  if (stream_mode && softmax != 2 && cl && stream_shape_ok(logits, batch_stride, voxel_stride, coord, volumes_out, J, nvox)) {
     StreamParams f;
-    f.logits = logits; f.coord = coord; f.volumes = volumes_out; f.keypoints = keypoints_out;
-    f.bs = batch_stride; f.nvox = nvox; f.vs = (int)voxel_stride; f.B = B; f.J = J;
-    f.Q = f.vs / 4;
-    f.RPI = (kStreamConsumers / f.Q) & ~1;      // rows per pass, even -> T = 4 * RPI is a multiple of 8 rows
-    f.T = 4 * f.RPI;
-    f.tiles = (int)((nvox + f.T - 1) / f.T);
-    f.total_tiles = (long)f.tiles * B;
-    f.mult = multiplier; f.softmax = softmax;
-    LT_REQUIRE(f.T * f.vs * 4 <= kStreamLogitBytes && f.T * 12 <= kStreamCoordBytes, "softargmax stream: tile does not fit (vs=%d)", f.vs);
-    LT_REQUIRE(f.total_tiles < (1L << 31), "softargmax stream: too many tiles");
-    static DeviceOnce configured;
-    if (configured.first()) {
-      cudaError_t e = cudaFuncSetAttribute(stream_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(stream_normalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes);
-      if (e != cudaSuccess) return fail(LT_ERR_CUDA, "softargmax stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
+    int rc = stream_setup(f, logits, batch_stride, (int)voxel_stride, coord, volumes_out, keypoints_out, B, J, nvox, multiplier, softmax);
+    if (rc) return rc;
     int max_ctas = 2 * sm_count();
     if (max_ctas > kMaxStreamCtas) max_ctas = kMaxStreamCtas;
     const int G = f.total_tiles < max_ctas ? (int)f.total_tiles : max_ctas;
     f.G = G;
     float* w = reinterpret_cast<float*>(workspace);
     f.partial = w;
-    f.stats = w + (((size_t)B * G * J * 5 + 3) & ~(size_t)3);   // 16-byte aligned (read as float2)
+    f.stats = w + stream_stats_offset(B, G, J);
     if (softmax) stream_stats_kernel<true><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
     else stream_stats_kernel<false><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
     LT_CHECK_LAUNCH("stream_stats_kernel");
-    softargmax_stream_merge<<<ceil_div((long)B * J * 32, 128), 128, 0, st>>>(f);
-    LT_CHECK_LAUNCH("softargmax_stream_merge");
-    if (volumes_out) {
-      if (softmax) stream_normalize_kernel<true><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
-      else stream_normalize_kernel<false><<<G, kStreamThreads, kStreamSmemBytes, st>>>(f);
-      LT_CHECK_LAUNCH("stream_normalize_kernel");
-    }
-    return LT_OK;
+    return stream_finish(f, st);
   }
   if (cl) softargmax_partial_cl<<<dim3(p.nch, B), 256, 0, st>>>(p);
   else softargmax_partial_generic<<<dim3(p.nch, J, B), 256, 0, st>>>(p);
@@ -584,4 +525,25 @@ extern "C" int lt_softargmax3d_fwd(const float* logits, long batch_stride, long 
     LT_CHECK_LAUNCH("softargmax_normalize");
   }
   return LT_OK;
+}
+
+// Second half of the streaming soft-argmax for logits whose statistics pass ran inside the kernel that produced them
+// (lt_v2v_tail_stats_fwd): workspace holds partial [B][G][J][5]; merges them -> key points, then writes the normalised volumes.
+extern "C" int lt_softargmax3d_finish_fwd(const float* logits, long batch_stride, long voxel_stride, const float* coord, float* volumes_out,
+                                          float* keypoints_out, void* workspace, size_t workspace_bytes, int B, int J, long nvox, int G,
+                                          float multiplier, int softmax, void* stream) {
+  using namespace lt;
+  LT_REQUIRE(logits && coord && keypoints_out && workspace, "softargmax3d_finish: null pointer");
+  LT_REQUIRE(B > 0 && J > 0 && nvox > 0 && G > 0 && G <= kMaxPartials, "softargmax3d_finish: bad sizes (G=%d)", G);
+  LT_REQUIRE(softmax == 0 || softmax == 1, "softargmax3d_finish: mode must be 0 (ReLU) or 1 (softmax)");
+  LT_REQUIRE(workspace_bytes >= lt_softargmax3d_workspace_bytes(B, J, nvox), "softargmax3d_finish: workspace too small");
+  LT_REQUIRE(stream_shape_ok(logits, batch_stride, voxel_stride, coord, volumes_out, J, nvox), "softargmax3d_finish: logits layout not covered by the streaming kernels");
+  StreamParams f;
+  int rc = stream_setup(f, logits, batch_stride, (int)voxel_stride, coord, volumes_out, keypoints_out, B, J, nvox, multiplier, softmax);
+  if (rc) return rc;
+  f.G = G;
+  float* w = reinterpret_cast<float*>(workspace);
+  f.partial = w;
+  f.stats = w + stream_stats_offset(B, G, J);
+  return stream_finish(f, (cudaStream_t)stream);
 }

@@ -29,10 +29,11 @@ def _round_up(v, m):
 
 class Act:
     """Channels-last activation: `data` is float32 [N,D,H,W,C] or bfloat16 [N,D,H,W,2C] (split-fp16)."""
-    __slots__ = ("data", "N", "D", "H", "W", "C", "fmt")
+    __slots__ = ("data", "N", "D", "H", "W", "C", "fmt", "stats")
 
     def __init__(self, N, D, H, W, C, fmt, device, zero=False):
         self.N, self.D, self.H, self.W, self.C, self.fmt = N, D, H, W, C, fmt
+        self.stats = None      # (workspace, n_partials): soft-argmax statistics produced together with these logits (fused V2V tail)
         alloc = torch.zeros if zero else torch.empty
         if fmt == FMT_F32:
             self.data = alloc((N, D, H, W, C), dtype=torch.float32, device=device)
@@ -94,6 +95,7 @@ class NativeEngine:
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
+        self.fuse_stats = os.environ.get("LT_TAIL_STATS", "1") == "1"      # soft-argmax statistics inside the fused tail kernel
         self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
 
@@ -485,8 +487,11 @@ class NativeEngine:
         self.launches += 1
         return vol
 
-    def v2v(self, x):
-        """volume Act (B, n, n, n, 32) -> logits Act float32 channels-last (v2v.py:164-169)."""
+    def v2v(self, x, softargmax_args=None):
+        """volume Act (B, n, n, n, 32) -> logits Act float32 channels-last (v2v.py:164-169).
+
+        softargmax_args = (coord, J, multiplier, softmax): when the fused tail kernel runs, the statistics pass of the volumetric
+        soft-argmax is folded into it (logits.stats); `softargmax` then only merges the partials and normalises."""
         P = self._packs
         x = self._conv(x, P["front0"], relu=True)
         for i in (1, 2, 3):
@@ -508,9 +513,19 @@ class NativeEngine:
             # v2v.py:154-160,168-169 in one kernel: the two hidden activations never leave the SM
             logits = Act(x.N, x.D, x.H, x.W, out_c, FMT_F32, x.data.device)
             rows = x.pixels
-            with self._timed("conv_tail", flops=2.0 * rows * (b1.kmacs + b2.kmacs + b3.kmacs), nbytes=rows * (128 + 4 * out_c),
-                             desc="N%d %dx%dx%d 32->32->32->%d k111 fused" % (x.N, x.D, x.H, x.W, b3.cout)):
-                capi.v2v_tail(x.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.scale, b3.shift, logits.data, rows, out_c)
+            nvox = x.D * x.H * x.W
+            fuse = (self.fuse_stats and softargmax_args is not None and nvox % 128 == 0 and nvox >= 16384 and out_c <= 20
+                    and softargmax_args[3] in (0, 1, False, True))
+            with self._timed("conv_tail", flops=2.0 * rows * (b1.kmacs + b2.kmacs + b3.kmacs), nbytes=rows * (128 + 4 * out_c + (12 if fuse else 0)),
+                             desc="N%d %dx%dx%d 32->32->32->%d k111 fused%s" % (x.N, x.D, x.H, x.W, b3.cout, " + soft-argmax statistics" if fuse else "")):
+                if fuse:
+                    coord, J, mult, softmax = softargmax_args
+                    ws = torch.empty(capi.softargmax3d_workspace_bytes(x.N, J, nvox) // 4 + 1, dtype=torch.float32, device=x.data.device)
+                    G = capi.v2v_tail_stats(x.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.scale, b3.shift,
+                                            logits.data, x.N, nvox, out_c, coord, J, mult, int(softmax), ws)
+                    logits.stats = (ws, G)
+                else:
+                    capi.v2v_tail(x.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.scale, b3.shift, logits.data, rows, out_c)
             self.launches += 1
             return logits
         x = self._conv(x, P["back1"], relu=True)
@@ -525,6 +540,14 @@ class NativeEngine:
         dev = logits.data.device
         volumes = torch.empty((B, J, n, n, n), dtype=torch.float32, device=dev)
         keypoints = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+        if logits.stats is not None:
+            # statistics came out of the fused V2V tail: merge + normalise only.  Algorithmic bytes as for the whole op (logits read once,
+            # volumes written once, coordinates read once -- by the tail kernel)
+            ws, G = logits.stats
+            with self._timed("softargmax", nbytes=B * (2 * J * nvox * 4 + nvox * 12)):
+                capi.softargmax3d_finish(logits.data, nvox * logits.C, logits.C, coord, volumes, keypoints, ws, B, J, nvox, G, multiplier, int(softmax))
+            self.launches += 2
+            return keypoints, volumes
         ws = torch.empty(capi.softargmax3d_workspace_bytes(B, J, nvox) // 4 + 1, dtype=torch.float32, device=dev)
         with self._timed("softargmax", nbytes=B * (2 * J * nvox * 4 + nvox * 12)):
             capi.softargmax3d(logits.data, nvox * logits.C, logits.C, 1, coord, volumes, keypoints, ws, B, J, nvox, multiplier, softmax)
@@ -551,7 +574,7 @@ class NativeEngine:
         del trunk
         agg = capi.AGG[m.volume_aggregation_method]
         vol = self.unproject(feats, B, V, proj, coord, agg, conf)
-        logits = self.v2v(vol)
+        logits = self.v2v(vol, (coord, m.num_joints, m.volume_multiplier, m.volume_softmax))
         keypoints, volumes = self.softargmax(logits, coord, m.num_joints, m.volume_multiplier, m.volume_softmax)
         # (B, V, 32, h, w) view of the channels-last features (values identical, strides permuted)
         features = feats.data.view(B, V, feats.H, feats.W, feats.C).permute(0, 1, 4, 2, 3)
@@ -648,8 +671,9 @@ class NativeEngine:
         else:
             capi.unproject_finalize(mine.contiguous(), vol.data, vol.fmt, Bl, feats.C, nvox, agg)
         self.launches += 1
-        logits = self.v2v(vol)
-        kp, volumes = self.softargmax(logits, coord_own.contiguous(), m.num_joints, m.volume_multiplier, m.volume_softmax)
+        coord_own = coord_own.contiguous()
+        logits = self.v2v(vol, (coord_own, m.num_joints, m.volume_multiplier, m.volume_softmax))
+        kp, volumes = self.softargmax(logits, coord_own, m.num_joints, m.volume_multiplier, m.volume_softmax)
         return kp, volumes
 
     def forward_view_sharded(self, images_local, proj_local, position, center, step, rot, plan, pg, collective="all_reduce",

@@ -25,6 +25,11 @@ class Recorder:
         for name in ("v2v_tail", "absmax", "conv_gather_weights", "fold_bn", "conv_pair_pack_weights", "conv_fold_pack_weights", "stem_s2d", "coord_volume", "unproject_aggregate", "softargmax3d", "maxpool", "nchw_to_nhwc", "f32_to_s32",
                      "s32_to_f32", "cl_to_cf", "conv_tc_pack_weights"):
             monkeypatch.setattr(capi, name, rec(name))
+        def tail_stats(*a, **k):
+            self.calls.append(("v2v_tail_stats", a))
+            return 444
+        monkeypatch.setattr(capi, "v2v_tail_stats", tail_stats)
+        monkeypatch.setattr(capi, "softargmax3d_finish", rec("softargmax3d_finish"))
         monkeypatch.setattr(capi, "lib", lambda: None)
         monkeypatch.setattr(capi, "conv_tc_weight_bytes", lambda t, ci, co: t * (ci // 32) * ((co + 15) // 16 * 16) * 64 * 2)
         monkeypatch.setattr(capi, "softargmax3d_workspace_bytes", lambda B, J, n: B * J * ((n + 2047) // 2048 * 5 + 2) * 4)
@@ -84,11 +89,13 @@ def test_engine_plan_is_consistent(monkeypatch, mode, layers):
     backbone = 1 + n_units * per_unit + n_ds + 12 + 1
     # V2V: front0 + 20 res blocks (2 convs each) + 4 skip convs (16->32, 32->64, 64->128 enc, none else) ...
     v2v = len(convs) - backbone
-    tail = sum(1 for c in rec.calls if c[0] == "v2v_tail")      # tc mode: back1 + back2 + output fused into one launch
+    tail = sum(1 for c in rec.calls if c[0] in ("v2v_tail", "v2v_tail_stats"))      # tc mode: back1 + back2 + output fused into one launch
+    # 32^3 volumes: the fused tail also carries the soft-argmax statistics pass, the soft-argmax itself is merge + normalise (2 launches)
+    assert sum(1 for c in rec.calls if c[0] == "softargmax3d_finish") == (1 if mode == "tc" else 0)
     assert tail == (1 if mode == "tc" else 0)
     up = 5 * (1 if mode == "tc" else 8)     # tc: each k2 s2 transposed conv is one grouped-output GEMM; simt: eight phase convs
     assert v2v == 1 + 20 * 2 + 3 + up + (0 if tail else 2 + 1), v2v
-    assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights", "conv_pair_pack_weights", "conv_gather_weights", "fold_bn", "absmax")) + 2   # softargmax = 3 launches
+    assert e.launches == len(rec.calls) - sum(1 for c in rec.calls if c[0] in ("conv_tc_pack_weights", "conv_fold_pack_weights", "conv_pair_pack_weights", "conv_gather_weights", "fold_bn", "absmax")) + (1 if tail else 2)   # softargmax = 3 launches (2 behind the fused tail)
     if mode == "tc":
         simt = [c for c in convs if c[1][0] == capi.CONV_SIMT]
         assert len(simt) == 0, "every conv runs on the tensor-core kernels"

@@ -413,3 +413,49 @@ def test_v2v_tail_fused_vs_torch(spatial, N):
     print("v2v tail %s N=%d rel err %.2e" % (spatial, N, err))
     assert err < TOL["tc"] * 2          # three chained layers
     assert float(got[:, 17:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("softmax", [True, False])
+@pytest.mark.parametrize("spatial,N", [((32, 32, 16), 3), ((64, 64, 16), 2), ((64, 64, 64), 1)])
+def test_v2v_tail_with_softargmax_statistics(spatial, N, softmax):
+    """lt_v2v_tail_stats_fwd + lt_softargmax3d_finish_fwd (statistics pass of op.py:84-96 fused into the kernel that produces the logits)
+    vs the unfused pair lt_v2v_tail_fwd + lt_softargmax3d_fwd on the same inputs: identical logits, key points / volumes to fp32
+    summation-order accuracy, equal arg-max.  Shapes: one tile per CTA with CTAs that own no tile of some samples (identity partials),
+    several tiles per CTA across a sample boundary (flush), and a full 64^3 volume."""
+    torch.manual_seed(5)
+    c1, c2, c3 = torch.nn.Conv3d(32, 32, 1).eval(), torch.nn.Conv3d(32, 32, 1).eval(), torch.nn.Conv3d(32, 17, 1).eval()
+    with torch.no_grad():
+        c3.weight.mul_(6.0)      # logit spread of a few units: peaked softmax
+    bn1, bn2 = _bn_for(c1, 5), _bn_for(c2, 6)
+    x = torch.randn(N, 32, *spatial)
+    e = _engine("tc")
+    b1 = e._pack_conv(c1.to(DEV), bn1.to(DEV), force_pair=True)
+    b2 = e._pack_conv(c2.to(DEV), bn2.to(DEV), force_pair=True)
+    b3 = e._pack_conv(c3.to(DEV), None, out_fmt=capi.FMT_F32, force_pair=True)
+    xa = act_from_nchw(x, capi.FMT_S32)
+    nvox, J, FC, mult = spatial[0] * spatial[1] * spatial[2], 17, 20, 1.7
+    coord = (torch.randn(N, nvox, 3) * 600).to(DEV)
+    args = (xa.data, b1.w_pair, b2.w_pair, b3.w_pair, b1.scale, b1.shift, b2.scale, b2.shift, b3.scale, b3.shift)
+    ws_bytes = capi.softargmax3d_workspace_bytes(N, J, nvox)
+    # unfused
+    lg0 = torch.empty((N * nvox, FC), dtype=torch.float32, device=DEV)
+    capi.v2v_tail(*args, lg0, N * nvox, FC)
+    v0 = torch.empty((N, J, nvox), dtype=torch.float32, device=DEV)
+    kp0 = torch.empty((N, J, 3), dtype=torch.float32, device=DEV)
+    ws0 = torch.empty(ws_bytes // 4 + 1, dtype=torch.float32, device=DEV)
+    capi.softargmax3d(lg0, nvox * FC, FC, 1, coord, v0, kp0, ws0, N, J, nvox, mult, softmax)
+    # fused (twice: the partials of every (sample, CTA) must be rewritten by each call)
+    for _ in range(2):
+        lg1 = torch.full((N * nvox, FC), 3.0, dtype=torch.float32, device=DEV)
+        ws1 = torch.full((ws_bytes // 4 + 1,), float("nan"), dtype=torch.float32, device=DEV)
+        G = capi.v2v_tail_stats(*args, lg1, N, nvox, FC, coord, J, mult, int(softmax), ws1)
+        v1 = torch.full((N, J, nvox), -1.0, dtype=torch.float32, device=DEV)
+        kp1 = torch.empty((N, J, 3), dtype=torch.float32, device=DEV)
+        capi.softargmax3d_finish(lg1, nvox * FC, FC, coord, v1, kp1, ws1, N, J, nvox, G, mult, int(softmax))
+        torch.cuda.synchronize()
+        assert G >= 1 and torch.equal(lg0, lg1), "the statistics variant must not change the logits"
+        err_kp = rel_err(kp1.cpu().numpy(), kp0.cpu().numpy())
+        err_v = rel_err(v1.cpu().numpy(), v0.cpu().numpy())
+        print("tail + statistics %s N=%d softmax=%s G=%d: keypoints %.2e volumes %.2e" % (spatial, N, softmax, G, err_kp, err_v))
+        assert err_kp < 3e-5 and err_v < 3e-5
+        assert torch.equal(v1.argmax(-1), v0.argmax(-1))

@@ -46,7 +46,7 @@ with torch.no_grad():
         for _ in range(a.repeat):
             vol = eng.unproject(feats, B, V, up(proj), coord, capi.AGG["softmax"])
             if a.stage == "v2v":
-                logits = eng.v2v(vol)
+                logits = eng.v2v(vol, (coord, 17, 1.0, True))      # fused tail: carries the soft-argmax statistics pass
                 eng.softargmax(logits, coord, 17, 1.0, True)
 torch.cuda.synchronize()
 print("done", eng.launches)
