@@ -191,7 +191,7 @@ def algebraic_rate(args, dev, vol_model, images_dev, batch, flush):
     alg = lt_b200.AlgebraicTriangulationNet(testing.make_alg_config(num_layers=args.layers), device=dev, backend="native", conv_mode=args.mode)
     alg.backbone.load_state_dict(vol_model.backbone.state_dict(), strict=False)     # shared trunk / deconvs / heat-map head
     alg = alg.to(dev).eval()
-    proj = testing.image_projections(batch).to(dev)
+    proj = torch.as_tensor(np.ascontiguousarray(testing.image_projections(batch), dtype=np.float32)).to(dev)
     B = images_dev.shape[0]
     steps = max(3, min(args.steps, 10))
     with torch.no_grad():

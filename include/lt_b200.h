@@ -75,6 +75,9 @@ typedef struct lt_options {
   int pair_nt, pair_stages; /* conv_pair A/B overrides: N tile (0 = heuristic, 128, 256), operand ring depth cap (0 = as many as fit) */
   int pair_prof;           /* conv_pair: 1 = per-role wait counters to stderr after every launch (debug; synchronises) */
   int pair_direct_out;     /* conv_pair: split-fp16 outputs stored from registers (1, default) or staged + TMA store (0) */
+  int pair_two_acc;        /* conv_pair: the hi*lo + lo*hi products accumulate in their own TMEM accumulator (1, default) or share the main
+                              one (0: 2.4 % faster, but 3x as many TRUNCATING tcgen05 accumulation steps on the main accumulator: the
+                              full-size config #2 parity then misses the 1e-3 contract, profiles/r02i_accumulation.md) */
   int fold_pair;           /* conv_fold: CTA-pair variant (cta_group::2, each CTA fetches half of every weight operand): 0 = never, 1 = layers
                               whose weights are streamed (7^3; default: measured 8 % faster there, neutral on the weight-resident 3^3), 2 = always */
   int fold_direct;         /* conv_fold: full-width split-fp16 tiles stored from registers, residual read from global memory (default 0:
@@ -232,7 +235,10 @@ int lt_conv_tc_pack_weights(const float* w_tap_ci_co, void* packed, int taps, in
  *   (td, th, tw, ci, co) is read from w[base + td*s_td + th*s_th + tw*s_tw + ci*s_ci + co*s_co] (nn.Conv: (Cout, Cin, k...);
  *   nn.ConvTranspose: (Cin, Cout, k...); stride phases of a transposed conv: a tap sub-lattice walked with negative strides).
  * lt_fold_bn_fwd: eval-mode BatchNorm (pose_resnet.py:30-31, v2v.py:12) + conv bias -> per-channel scale / shift [CP] (double
- *   arithmetic, rounded once); mean == NULL: no BatchNorm.
+ *   arithmetic, rounded once); mean == NULL: no BatchNorm.  accum_steps: tcgen05.mma steps that accumulate into the main fp32
+ *   accumulator of the kernel that will consume this scale (taps x Cin / 16; 0 for the exact-fp32 kernels).  The tensor core adds
+ *   with truncation, which shrinks a sum by an expected 0.28 x steps x 2^-24 (tools/accum_probe.py: 0.27-0.29 for K = 256..4608);
+ *   the scale is multiplied by 1 + that, which halves the rms accumulation error.
  * lt_absmax_fwd: float bit pattern of max|w| over n elements.  Passed (optionally, else NULL) to the two calls above it selects the
  *   power-of-two filter pre-scale S = 2^(9 - floor(log2 max|w|)) of the tensor-core path: the gathered filter is multiplied by S,
  *   the folded scale by 1 / S (exact), so that the unscaled low halves of the split-fp16 weights stay normal numbers. */
@@ -241,7 +247,7 @@ int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, long s_th, 
                                int Cin, int CinP, int Cout, int CoutP, const unsigned int* absmax_bits, float* out, int out_ld,
                                int out_col0, void* stream);   /* out row length (0 = CoutP) and first column: column blocks of a wider filter */
 int lt_fold_bn_fwd(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
-                   int C, int CP, const unsigned int* absmax_bits, float* scale, float* shift, void* stream);
+                   int C, int CP, const unsigned int* absmax_bits, int accum_steps, float* scale, float* shift, void* stream);
 
 /* CTA-pair weight packing: float32 [taps][Cin][Cout] (DEVICE) -> fp16 [taps][Cin/32][CoutP][32 hi | 32 lo] (128-byte rows),
  * CoutP = round_up(Cout, 128).  lt_conv_pair_eligible: 1 if LT_CONV_TC_PAIR covers this launch (shape / tiling heuristics),

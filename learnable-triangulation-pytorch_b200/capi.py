@@ -39,7 +39,7 @@ class ConvDesc(ctypes.Structure):
 class Options(ctypes.Structure):
     """Mirror of `struct lt_options` (include/lt_b200.h): kernel-selection switches, all defaulting to the measured-best path."""
     _fields_ = [(n, c_int) for n in ("tc_persist", "tc_splitk", "tc_bres", "tc_direct_epilogue", "fold_fast_issue", "fold_debug",
-                                     "softargmax_stream", "unproject_v2", "unproject_cpl", "unproject_lb", "unproject_brick", "pair_nt", "pair_stages", "pair_prof", "pair_direct_out", "fold_pair", "fold_direct", "fold_fullw")]
+                                     "softargmax_stream", "unproject_v2", "unproject_cpl", "unproject_lb", "unproject_brick", "pair_nt", "pair_stages", "pair_prof", "pair_direct_out", "pair_two_acc", "fold_pair", "fold_direct", "fold_fullw")]
 
 
 # The ONE place the environment is read (A/B tooling: tools/post_probe.py, tools/fold_probe.py): LT_OPT_<FIELD>=<int>
@@ -72,7 +72,7 @@ SIGNATURES = {
     "lt_conv_tc_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_absmax_fwd": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "lt_conv_gather_weights_fwd": (c_int, [c_void_p] + [c_long] * 6 + [c_int] * 7 + [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "lt_fold_bn_fwd": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lt_fold_bn_fwd": (c_int, [c_void_p] * 5 + [c_float, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "lt_conv_pair_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lt_conv_pair_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lt_conv_pair_eligible": (c_int, [ctypes.POINTER(ConvDesc)]),
@@ -273,9 +273,9 @@ def conv_gather_weights(w, base, strides, k, cin, cin_p, cout, cout_p, out, absm
                                             _ptr(absmax_bits), _ptr(out), out_ld, out_col0, _stream()), "lt_conv_gather_weights_fwd")
 
 
-def fold_bn(gamma, beta, mean, var, bias, eps, c, cp, scale, shift, absmax_bits=None):
+def fold_bn(gamma, beta, mean, var, bias, eps, c, cp, scale, shift, absmax_bits=None, accum_steps=0):
     _check(lib().lt_fold_bn_fwd(_ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), _ptr(bias), float(eps), c, cp, _ptr(absmax_bits),
-                                _ptr(scale), _ptr(shift), _stream()), "lt_fold_bn_fwd")
+                                int(accum_steps), _ptr(scale), _ptr(shift), _stream()), "lt_fold_bn_fwd")
 
 
 def conv_pair_weight_bytes(taps, cin, cout):

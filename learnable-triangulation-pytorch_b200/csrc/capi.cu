@@ -27,6 +27,7 @@ static lt_options make_default_options() {
   o.pair_nt = 0; o.pair_stages = 0;
   o.pair_prof = 0;
   o.pair_direct_out = 1;
+  o.pair_two_acc = 1;
   o.fold_pair = 1;
   o.fold_direct = 0;
   o.fold_fullw = 1;

@@ -46,6 +46,8 @@ struct PairExtra {
   int res_bufs; // residual staging buffers (power of two): 16 KB blocks requested this many blocks ahead
   int direct_out;   // split-fp16 output rows are stored straight from registers
   int off_aff, aff_n;   // per-channel scale [aff_n] and shift [aff_n] copied to shared memory at kernel start
+  int two_acc;          // 1: hi*hi -> D1, the two cross products -> D2 (Nt columns further); the epilogue adds them in fp32 RN
+  int acc_stages;       // accumulator stages in TMEM: 512 / (Nt * (1 + two_acc)), at most 2
   unsigned long long* prof;   // optional [16] cycle counters (lt_options.pair_prof): time each role spends waiting, summed over CTAs
 };
 
@@ -176,10 +178,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint64_t bd0 = make_sw128_desc(smem_u32(smem) + kATileBytes);
       const uint64_t sdelta = (uint64_t)(stage_bytes >> 4);
       for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
-        const uint32_t as = it & 1u;
-        mbar_wait_t(&acc_empty[as], ((it >> 1) & 1u) ^ 1u, w_acc, prof_on);
+        const uint32_t as = x.acc_stages == 2 ? (it & 1u) : 0u, aph = x.acc_stages == 2 ? ((it >> 1) & 1u) : (it & 1u);
+        mbar_wait_t(&acc_empty[as], aph ^ 1u, w_acc, prof_on);
         tc_fence_after();
-        const uint32_t d = tmem_base + as * (uint32_t)p.Nt;
+        const uint32_t d = tmem_base + as * (uint32_t)(p.Nt << x.two_acc);
+        const uint32_t d2 = x.two_acc ? d + (uint32_t)p.Nt : d;     // cross products (see the header comment on accumulation)
         for (int q = 0; q < nchunks; ++q) {
           mbar_wait_t(&full[rs], rph, w_full, prof_on);
           tc_fence_after();
@@ -188,10 +191,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // rows = [32 hi | 32 lo] fp16: slices hi0 +0, hi1 +2, lo0 +4, lo1 +6 (16-byte units)
             umma2_f16(d, ad, bd, idesc, q == 0 ? 0u : 1u);   // hi * hi
             umma2_f16(d, ad + 2, bd + 2, idesc, 1u);
-            umma2_f16(d, ad, bd + 4, idesc, 1u);             // hi * lo
-            umma2_f16(d, ad + 2, bd + 6, idesc, 1u);
-            umma2_f16(d, ad + 4, bd, idesc, 1u);             // lo * hi
-            umma2_f16(d, ad + 6, bd + 2, idesc, 1u);
+            umma2_f16(d2, ad, bd + 4, idesc, (q == 0 && x.two_acc) ? 0u : 1u);   // hi * lo
+            umma2_f16(d2, ad + 2, bd + 6, idesc, 1u);
+            umma2_f16(d2, ad + 4, bd, idesc, 1u);            // lo * hi
+            umma2_f16(d2, ad + 6, bd + 2, idesc, 1u);
             umma2_commit_mc(&empty[rs]);
             if (q == nchunks - 1) umma2_commit_mc(&acc_full[as]);
           }
@@ -232,10 +235,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (long tile = pair_idx; tile < x.total_tiles; tile += n_pairs, ++it) {
       int ow0, oh0, od0, nb0, n0;
       decode(tile, ow0, oh0, od0, nb0, n0);
-      const uint32_t as = it & 1u;
-      mbar_wait_t(&acc_full[as], (it >> 1) & 1u, w_accf, prof_on);
+      const uint32_t as = x.acc_stages == 2 ? (it & 1u) : 0u, aph = x.acc_stages == 2 ? ((it >> 1) & 1u) : (it & 1u);
+      mbar_wait_t(&acc_full[as], aph, w_accf, prof_on);
       tc_fence_after();
-      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.Nt;
+      const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)(p.Nt << x.two_acc);
       if (x.direct_out) {
         // ---- direct epilogue (split-fp16 outputs): this thread's voxel row goes from registers to global memory as 2 x 32
         // bytes per 32-channel block (high halves, low halves).  No staging tile, no TMA store: the TMA queue of the SM is
@@ -255,9 +258,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[16], r[16];
           {
             uint32_t t1[16];
-            tmem_ld16(tlane + (uint32_t)(i * 32 + half * 16), t1);
+            if (x.two_acc) {
+              uint32_t t2[16];
+              tmem_ld16_nowait(tlane + (uint32_t)(i * 32 + half * 16), t1);
+              tmem_ld16_nowait(tlane + (uint32_t)(p.Nt + i * 32 + half * 16), t2);
+              tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]) + __uint_as_float(t2[j]);
+            } else {
+              tmem_ld16(tlane + (uint32_t)(i * 32 + half * 16), t1);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
+            }
           }
           if (i + 2 >= nblk) {                   // this group's last block of the tile: its part of the accumulator is drained
             tc_fence_before();
@@ -297,9 +309,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[16], r[16];
         {
           uint32_t t1[16];
-          tmem_ld16(tlane + (uint32_t)(i * 32 + half * 16), t1);
+          if (x.two_acc) {
+            uint32_t t2[16];
+            tmem_ld16_nowait(tlane + (uint32_t)(i * 32 + half * 16), t1);
+            tmem_ld16_nowait(tlane + (uint32_t)(p.Nt + i * 32 + half * 16), t2);
+            tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]) + __uint_as_float(t2[j]);
+          } else {
+            tmem_ld16(tlane + (uint32_t)(i * 32 + half * 16), t1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t1[j]);
+          }
         }
         if (i == nblk - 1) {               // accumulator stage fully read by this warp: release it to the leader's MMA warp
           tc_fence_before();
@@ -368,6 +389,15 @@ bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* pl
   // the SMs (measured: 2x2 taps 2048 -> 256 at 12x12 = 36 pair tiles with 256 chunks each: 70 us here, 59 us there)
   const long best_tiles = m_pairs * (CoutP / best_nt);
   if (best_tiles * 4 < P || (best_tiles * 2 <= P && nchunks >= 64)) return false;
+  // Accumulation accuracy.  tcgen05 adds every MMA into the fp32 accumulator with TRUNCATION (tools/accum_probe.py: zero-mean operands,
+  // rms error 0.027 K x 2^-24 of the result scale, i.e. proportional to the number of MMA steps instead of its square root).  With one
+  // accumulator the three products of a 16-channel slice are three such steps on the big accumulator; keeping the two cross products
+  // (2^-11 of the main term) in their own accumulator leaves one.  Price: twice the TMEM columns -- with Nt = 256 only ONE accumulator
+  // stage fits, so the epilogue of a tile no longer overlaps the main loop of the next (+0.3-0.4 ms per step, mostly on the 1x1
+  // 256 -> 1024 layers).  Measured at config #2, B = 8 against the CPU oracle (profiles/r02i_accumulation.md): volumes 1.41e-3 with one
+  // accumulator (contract 1e-3 missed), 7.9e-4 with two.
+  plan->two_acc = opts().pair_two_acc ? 1 : 0;
+  plan->acc_stages = (best_nt << plan->two_acc) * 2 <= 512 ? 2 : 1;
   plan->Nt = best_nt;
   plan->n_tiles = CoutP / best_nt;
   plan->m_tiles = m_tiles;
@@ -400,6 +430,8 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& t
   const int ring = plan.stages * x.stage_bytes;
   x.off_out = (ring + 1023) & ~1023;
   x.direct_out = plan.direct_out;
+  x.two_acc = plan.two_acc;
+  x.acc_stages = plan.acc_stages;
   x.off_res = x.off_out + (plan.direct_out ? 0 : 32768);
   x.off_aff = x.off_res + plan.res_bufs * 16384;      // scale [CoutP] | shift [CoutP]
   x.aff_n = CoutP;

@@ -197,14 +197,25 @@ __global__ void __launch_bounds__(kTailThreads, 3) v2v_tail_kernel(const __grid_
         }
       }
     }
-    for (long t = blockIdx.x; t < p.tiles; t += gridDim.x, tp ^= 1u) {
-      if (STATS) {
-        const int b = (int)(t / p.tiles_per_sample);
-        if (b != cur_b) {
-          if (cur_b >= 0) flush(cur_b);
-          cur_b = b;
+    // statistics of the tile in lg_s / cd_s (rows [r_lo, r_hi) of this warp's 32): lane j folds joint j, four rows per step.
+    // They are computed ONE TILE LATE, in the two bubbles of the next tile's chain (after handing a hidden tile to the MMA warp the
+    // activation warp would otherwise just wait for the next accumulator), so the fused pass adds no latency to the GEMM chain.
+    auto stats_rows = [&](int r_lo, int r_hi) {
+      if (lane < p.J) {
+        for (int r0 = r_lo; r0 < r_hi; r0 += 4) {
+          float l[4], x[4], y[4], z[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            l[k] = lg_s[(r0 + k) * p.FC + lane] * p.mult;
+            const float4 c = cd_s[r0 + k];
+            x[k] = c.x; y[k] = c.y; z[k] = c.z;
+          }
+          st_push4<SM>(st, l, x, y, z);
         }
       }
+    };
+    bool pending = false;          // lg_s / cd_s hold a tile (of sample cur_b) whose statistics are not folded in yet
+    for (long t = blockIdx.x; t < p.tiles; t += gridDim.x, tp ^= 1u) {
 #pragma unroll
       for (int layer = 0; layer < 2; ++layer) {
         mbar_wait(&d_full[layer], tp);
@@ -230,6 +241,16 @@ __global__ void __launch_bounds__(kTailThreads, 3) v2v_tail_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_local(&h_full[layer]);
+        if (STATS && pending) stats_rows(layer * 16, layer * 16 + 16);
+      }
+      if (STATS) {
+        // the pending tile is folded in; a sample boundary between it and this tile closes the sample's partial (CTA-uniform)
+        const int b = (int)(t / p.tiles_per_sample);
+        __syncwarp();
+        if (b != cur_b) {
+          if (cur_b >= 0) flush(cur_b);
+          cur_b = b;
+        }
       }
       mbar_wait(&d_full[2], tp);
       tc_fence_after();
@@ -268,25 +289,15 @@ __global__ void __launch_bounds__(kTailThreads, 3) v2v_tail_kernel(const __grid_
           // rows = B x nvox with nvox % 128 == 0: every tile is full and lies inside one sample
           cd_s[lane] = make_float4(cxyz.x, cxyz.y, cxyz.z, 0.f);
           __syncwarp();
-          if (lane < p.J) {
-#pragma unroll 2
-            for (int r0 = 0; r0 < 32; r0 += 4) {
-              float l[4], x[4], y[4], z[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                l[k] = lg_s[(r0 + k) * p.FC + lane] * p.mult;
-                const float4 c = cd_s[r0 + k];
-                x[k] = c.x; y[k] = c.y; z[k] = c.z;
-              }
-              st_push4<SM>(st, l, x, y, z);
-            }
-          }
-          __syncwarp();     // the tile is consumed before the next tile's rows overwrite it
+          pending = true;
         }
       }
       tc_fence_before();   // accumulator reads of this tile are ordered before the next tile's h_full arrivals
     }
-    if (STATS && cur_b >= 0) flush(cur_b);
+    if (STATS) {
+      if (pending) { stats_rows(0, 32); __syncwarp(); }
+      if (cur_b >= 0) flush(cur_b);
+    }
   }
 
   tc_fence_before();

@@ -48,6 +48,8 @@ struct PairPlan {
   int stages;        // operand ring depth
   int res_bufs;      // residual staging tiles (0 without a residual)
   int direct_out;    // split-fp16 outputs: the epilogue stores rows straight from registers (no staging tile, no TMA store)
+  int two_acc;       // separate accumulator for the cross products (accuracy: see conv_pair.cu); acc_stages = TMEM stages that fit
+  int acc_stages;
   unsigned grid;     // CTAs (2 per pair)
 };
 bool pair_plan(const lt_conv_desc* d, const TcParams& p, int CoutP, PairPlan* plan);   // false: shape not covered by the pair kernel

@@ -224,8 +224,10 @@ __global__ void __launch_bounds__(256) gather_weights_kernel(const float* __rest
 
 // y = acc * scale + shift with scale = gamma / sqrt(var + eps), shift = beta - mean * scale (+ conv_bias * scale); double arithmetic,
 // rounded once.  Any of gamma / beta / bias may be null; mean == null means "no BatchNorm" (scale 1, shift = bias).
+// accum_gain = 1 + 0.28 * steps * 2^-24: compensates the expected shrinkage of a sum accumulated by `steps` truncating tcgen05.mma
+// additions (tools/accum_probe.py); 1 for the exact-fp32 kernels.
 __global__ void fold_bn_kernel(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias, double eps,
-                               int C, int CP, const unsigned* absmax_bits, float* scale, float* shift) {
+                               int C, int CP, const unsigned* absmax_bits, double accum_gain, float* scale, float* shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= CP) return;
   const double inv_s = 1.0 / (double)weight_pow2_scale(absmax_bits);   // the packed filter carries S: acc = S * sum x w
@@ -240,7 +242,7 @@ __global__ void fold_bn_kernel(const float* gamma, const float* beta, const floa
       sh = bias ? (double)bias[c] : 0.0;
     }
   }
-  scale[c] = (float)(sc * inv_s);
+  scale[c] = (float)(sc * inv_s * accum_gain);
   shift[c] = (float)sh;
 }
 
@@ -289,10 +291,11 @@ extern "C" int lt_conv_gather_weights_fwd(const float* w, long base, long s_td, 
 }
 
 extern "C" int lt_fold_bn_fwd(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps,
-                              int C, int CP, const unsigned int* absmax_bits, float* scale, float* shift, void* stream) {
+                              int C, int CP, const unsigned int* absmax_bits, int accum_steps, float* scale, float* shift, void* stream) {
   using namespace lt;
-  LT_REQUIRE(scale && shift && C > 0 && CP >= C && (!mean || var), "fold_bn: bad arguments");
-  fold_bn_kernel<<<ceil_div(CP, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, (double)eps, C, CP, absmax_bits, scale, shift);
+  LT_REQUIRE(scale && shift && C > 0 && CP >= C && (!mean || var) && accum_steps >= 0, "fold_bn: bad arguments");
+  const double accum_gain = 1.0 + 0.28 * (double)accum_steps * 5.9604644775390625e-08;   // 2^-24
+  fold_bn_kernel<<<ceil_div(CP, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, (double)eps, C, CP, absmax_bits, accum_gain, scale, shift);
   LT_CHECK_LAUNCH("fold_bn_kernel");
   return LT_OK;
 }

@@ -95,6 +95,7 @@ class NativeEngine:
         self.tc_stem = os.environ.get("LT_TC_STEM", "1") == "1"          # stem conv on the tensor-core kernel (space-to-depth)
         self.tc_strided = os.environ.get("LT_TC_STRIDED", "1") == "1"   # stride-2 convs on the tensor-core kernel
         self.compact_logits = os.environ.get("LT_LOGITS_COMPACT", "1") == "1"
+        self.accum_compensation = os.environ.get("LT_TC_ACCUM_COMP", "1") == "1"   # truncation-shrinkage factor in the folded scale
         self.fuse_stats = os.environ.get("LT_TAIL_STATS", "1") == "1"      # soft-argmax statistics inside the fused tail kernel
         self.timeline = None       # set to [] to record (label, flops, bytes, start_evt, end_evt) per launch
         capi.lib()                 # fail loudly if the extension is missing
@@ -166,13 +167,18 @@ class NativeEngine:
             pk.w, pk.cin, pk.cout_p, pk.impl, pk.in_fmt = wp, cin_p, cout_p, CONV_SIMT, FMT_F32
         pk.scale = torch.empty(cout_p, dtype=torch.float32, device=dev)
         pk.shift = torch.empty(cout_p, dtype=torch.float32, device=dev)
+        # tcgen05 accumulation steps on the main fp32 accumulator (one hi*hi MMA per 16 input channels and tap; the kw-folded kernel keeps
+        # the kw taps in separate accumulator columns): lt_fold_bn_fwd compensates the expected truncation shrinkage (include/lt_b200.h)
+        steps = 0
+        if use_tc and self.accum_compensation:
+            steps = (taps // k[2] if pk.w_fold is not None else taps) * (cin_p // 16)
         for g in range(G):     # the per-channel affine repeats for every column block
             sc, sh = pk.scale[g * cout:g * cout + blk_p], pk.shift[g * cout:g * cout + blk_p]
             if bn is not None:
                 capi.fold_bn(_f32(bn.weight), _f32(bn.bias), _f32(bn.running_mean), _f32(bn.running_var), _f32(bias), bn.eps, cout, blk_p,
-                             sc, sh, amax)
+                             sc, sh, amax, accum_steps=steps)
             else:
-                capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, blk_p, sc, sh, amax)
+                capi.fold_bn(None, None, None, None, _f32(bias), 0.0, cout, blk_p, sc, sh, amax, accum_steps=steps)
         return pk
 
     def _pack_conv(self, conv, bn, cin_pad=None, **kw):

@@ -167,6 +167,7 @@ def _engine(mode):
     e.tc_impl = {"simt": capi.CONV_SIMT, "tc": capi.CONV_TC, "tc1": capi.CONV_TC1}[mode]
     e._packs, e._graphs, e.launches, e.timeline, e.tc_strided, e.use_fold, e.tc_stem = {}, {}, 0, None, True, True, True
     e.use_pair, e.use_tail, e.weight_prescale, e.merge_deconv3d, e._epoch = True, True, True, True, 0
+    e.accum_compensation, e.fuse_stats, e.compact_logits = True, True, True
     return e
 
 

@@ -255,9 +255,19 @@ PAIR_CASES = [
 ]
 
 
+@pytest.mark.parametrize("acc", ["single", "two"])
 @pytest.mark.parametrize("case", PAIR_CASES)
-def test_conv_pair_vs_torch(case):
-    """CTA-pair kernel (cta_group::2, M = 256 per pair, single accumulator) against the fp32 torch op."""
+def test_conv_pair_vs_torch(case, acc):
+    """CTA-pair kernel (cta_group::2, M = 256 per pair) against the fp32 torch op, with one fp32 accumulator for the three products
+    and with the cross products in a second accumulator (one or two TMEM stages depending on the N tile)."""
+    capi.set_options(pair_two_acc=int(acc == "two"))
+    try:
+        _pair_case(case)
+    finally:
+        capi.set_options(pair_two_acc=1)
+
+
+def _pair_case(case):
     dims, cin, cout, k, stride, pad, spatial, N, res_mode = case
     torch.manual_seed(cin + cout + k + N)
     conv = (torch.nn.Conv2d if dims == 2 else torch.nn.Conv3d)(cin, cout, k, stride, pad, bias=(dims == 3)).eval()

@@ -13,7 +13,10 @@ KEYS = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
-    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe (hmma) active %"),
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % of elapsed"),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor operand fetch (smem) active % of elapsed"),
+    ("sm__cycles_elapsed.avg.per_second", "SM clock"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum", "L1 LSU wavefronts"),
     ("sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "TMEM pipe inst %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
@@ -30,7 +33,10 @@ def main():
         hdr, units = rows[0], rows[1]
         idx = {h: i for i, h in enumerate(hdr)}
         lines += ["## " + rep.split("/")[-1], ""]
-        lines += ["| metric | " + " | ".join(r[idx["Kernel Name"]].split("(")[0][:34] + " #%s" % r[idx["ID"]] for r in rows[2:]) + " |",
+        def gname(r):
+            g = r[idx["launch__grid_size"]] if "launch__grid_size" in idx else ""
+            return r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("lt::", "")[:30] + " #%s" % r[idx["ID"]]
+        lines += ["| metric | " + " | ".join(gname(r) for r in rows[2:]) + " |",
                   "|---|" + "---:|" * len(rows[2:])]
         for key, name in KEYS:
             if key not in idx:
