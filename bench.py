@@ -467,9 +467,13 @@ def main_native(args, rank, world, local_rank):
                                    "e2e": B * world * args.steps / es, "keypoints_vs_single_gpu_mm": err,
                                    "gpu_launches_per_step": r["launches"], "exchange": EXCHANGE_TEXT[name]}
                 # same inputs, two arithmetic orders (packed exp-sum partials reduced by NCCL vs one fused kernel): measured 0.02-0.07 mm at
-                # config #2; the contract against the reference is 1e-3 relative of a 2500 mm cuboid = 2.5 mm
-                assert err < 0.5, "view-sharded key points (%s) differ from the single-GPU forward by %.4f mm" % (name, err)
-            best = max(exchanges, key=lambda k: exchanges[k]["value"])
+                # config #2; the contract against the reference is 1e-3 relative of a 2500 mm cuboid = 2.5 mm.  An exchange whose key points
+                # disagree with the single-GPU forward of the same samples is reported but never selected as the line's value.
+                exchanges[name]["keypoints_ok"] = bool(err < 0.5)
+            if not any(e["keypoints_ok"] for e in exchanges.values()):
+                raise SystemExit("view-sharded key points differ from the single-GPU forward for every exchange: %s"
+                                 % {k: v["keypoints_vs_single_gpu_mm"] for k, v in exchanges.items()})
+            best = max((k for k in exchanges if exchanges[k]["keypoints_ok"]), key=lambda k: exchanges[k]["value"])
             r = results[best]
             dev_ms, e2e_s, e2e_sync_s, launches, d2h, h2d = r["dev_ms"], r["e2e_s"], r["e2e_s"], r["launches"], r["d2h"], arm.h2d
             parallelism = arm.describe(best)
@@ -482,7 +486,7 @@ def main_native(args, rank, world, local_rank):
                 k8 = max(2, args.steps // 2)
                 config4 = {"workload": "Volumetric(softmax) ResNet-%d, 8 views %dx%d, %d^3 grid, one view per GPU, group batch %d" % (args.layers, S, S, n, arm8.Bg),
                            "value": arm8.Bg * k8 / (dms / 1e3), "unit": "samples/s", "ms_per_step": dms / k8, "e2e": arm8.Bg * k8 / es,
-                           "exchange": best, "keypoints_vs_single_gpu_mm": err, "parallelism": arm8.describe(best)}
+                           "exchange": best, "keypoints_vs_single_gpu_mm": err, "keypoints_ok": bool(err < 0.5), "parallelism": arm8.describe(best)}
 
         # ---- per-kernel timing for the roofline: one eager (non-graph) step with a CUDA-event pair per launch ----
         eng.use_graph = False

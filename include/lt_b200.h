@@ -72,6 +72,7 @@ typedef struct lt_options {
   int unproject_cpl;       /* unprojection v2: channels per lane, 4 or 8 */
   int unproject_lb;        /* unprojection v2: min CTAs / SM override (0 = per-variant default) */
   int unproject_brick;     /* unprojection v2: side of the voxel bricks a CTA walks (0 = linear order, default: measured faster) */
+  int unproject_brick_order; /* voxel order inside a brick: 0 = z fastest, 1 = x fastest, 2 = 2 x 2 (x, y) tiles (voxels of a warp share taps) */
   int pair_nt, pair_stages; /* conv_pair A/B overrides: N tile (0 = heuristic, 128, 256), operand ring depth cap (0 = as many as fit) */
   int pair_prof;           /* conv_pair: 1 = per-role wait counters to stderr after every launch (debug; synchronises) */
   int pair_direct_out;     /* conv_pair: split-fp16 outputs stored from registers (1, default) or staged + TMA store (0) */

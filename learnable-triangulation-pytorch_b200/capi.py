@@ -39,7 +39,7 @@ class ConvDesc(ctypes.Structure):
 class Options(ctypes.Structure):
     """Mirror of `struct lt_options` (include/lt_b200.h): kernel-selection switches, all defaulting to the measured-best path."""
     _fields_ = [(n, c_int) for n in ("tc_persist", "tc_splitk", "tc_bres", "tc_direct_epilogue", "fold_fast_issue", "fold_debug",
-                                     "softargmax_stream", "unproject_v2", "unproject_cpl", "unproject_lb", "unproject_brick", "pair_nt", "pair_stages", "pair_prof", "pair_direct_out", "pair_two_acc", "fold_pair", "fold_direct", "fold_fullw")]
+                                     "softargmax_stream", "unproject_v2", "unproject_cpl", "unproject_lb", "unproject_brick", "unproject_brick_order", "pair_nt", "pair_stages", "pair_prof", "pair_direct_out", "pair_two_acc", "fold_pair", "fold_direct", "fold_fullw")]
 
 
 # The ONE place the environment is read (A/B tooling: tools/post_probe.py, tools/fold_probe.py): LT_OPT_<FIELD>=<int>

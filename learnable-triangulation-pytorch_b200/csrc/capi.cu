@@ -23,7 +23,7 @@ static lt_options make_default_options() {
   o.fold_fast_issue = 1; o.fold_debug = 0;
   o.softargmax_stream = 1;
   o.unproject_v2 = 1; o.unproject_cpl = 4; o.unproject_lb = 0;
-  o.unproject_brick = 0;
+  o.unproject_brick = 0; o.unproject_brick_order = 2;
   o.pair_nt = 0; o.pair_stages = 0;
   o.pair_prof = 0;
   o.pair_direct_out = 1;

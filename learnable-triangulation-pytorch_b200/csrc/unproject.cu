@@ -37,7 +37,23 @@ struct UnprojParams {
   // v2 kernel: cubic volumes (nvox = n^3, n % brick == 0) are walked brick by brick (brick^3 voxels at a time per CTA) so that
   // the 2x2 tap cells of a CTA's consecutive voxels overlap in every view and are served by L1 instead of the 64 B/clk L2 port
   int brick_n, brick;
+  int brick_order;   // voxel order inside a brick: 0 = z fastest, 1 = x fastest, 2 = 2 x 2 (x, y) tiles fastest (see brick_decode)
 };
+
+// Voxel w of a brick^3 block -> (dx, dy, dz).  Which voxels share a warp decides how many DISTINCT 128-byte feature rows one tap
+// instruction touches (the L1 serves one row per wavefront, whatever the number of lanes reading it): a camera moves the projection by
+// ~0.37 px per voxel along its viewing direction and ~1.1 px across it (cuboid 2.5 m / 64, heat-maps 96 x 96), and cameras look
+// horizontally, so vertical (z) neighbours never share a bilinear cell while neighbours along the viewing axis mostly do.
+//   0: z fastest (4 z-neighbours per warp: no sharing); 1: x fastest; 2: 2 x 2 tiles in (x, y) fastest: every horizontal camera
+//   direction gets one close pair per warp.
+__device__ __forceinline__ void brick_decode(int w, int bs, int order, int& dx, int& dy, int& dz) {
+  if (order == 1) { dx = w % bs; dy = (w / bs) % bs; dz = w / (bs * bs); }
+  else if (order == 2) {
+    const int q = w & 3, r = w >> 2, hb = bs >> 1;
+    dx = 2 * (r % hb) + (q & 1); dy = 2 * ((r / hb) % hb) + (q >> 1); dz = r / (hb * hb);
+  } else { dz = w % bs; dy = (w / bs) % bs; dx = w / (bs * bs); }
+}
+
 
 struct Taps {
   int o00, o01, o10, o11;  // pixel offsets (y*w + x), valid only when the matching weight flag is set
@@ -301,7 +317,8 @@ __global__ void __launch_bounds__(256) unproject_fast_kernel(const UnprojParams 
       const long brick = outer;
       const int w = inner * VPB + slot;                        // voxel inside the brick
       const int bz = (int)(brick % bpd), by = (int)((brick / bpd) % bpd), bx = (int)(brick / ((long)bpd * bpd));
-      const int dz = w % bs, dy = (w / bs) % bs, dx = w / (bs * bs);
+      int dx, dy, dz;
+      brick_decode(w, bs, p.brick_order, dx, dy, dz);
       vox = ((long)(bx * bs + dx) * p.brick_n + (by * bs + dy)) * p.brick_n + (bz * bs + dz);
       live = true;
     } else {
@@ -500,7 +517,8 @@ __global__ void __launch_bounds__(256, MINB) unproject_v2_kernel(const UnprojPar
       const long brick = outer;
       const int w = inner * VPB + slot;                        // voxel inside the brick
       const int bz = (int)(brick % bpd), by = (int)((brick / bpd) % bpd), bx = (int)(brick / ((long)bpd * bpd));
-      const int dz = w % bs, dy = (w / bs) % bs, dx = w / (bs * bs);
+      int dx, dy, dz;
+      brick_decode(w, bs, p.brick_order, dx, dy, dz);
       vox = ((long)(bx * bs + dx) * p.brick_n + (by * bs + dy)) * p.brick_n + (bz * bs + dz);
       live = true;
     } else {
@@ -658,7 +676,7 @@ static int launch_unproject(const float* features, const float* proj, const floa
   LT_REQUIRE(B <= 65535, "unproject: batch too large");
   UnprojParams p{features, proj, coord, conf, out, B, V, C, h, w, nvox, agg, out_format, 1, partial};
   p.samples_per_owner = 1; p.src_rank = src_rank;
-  p.brick_n = 0; p.brick = 8;
+  p.brick_n = 0; p.brick = 8; p.brick_order = 0;
   for (int i = 0; i < 8; ++i) p.peer[i] = (peers && i < n_peers) ? peers[i] : nullptr;
   if (partial == 2) {
     LT_REQUIRE(peers && n_peers >= 1 && n_peers <= 8 && B % n_peers == 0, "unproject_push: need 1..8 peers dividing the batch");
@@ -688,7 +706,7 @@ static int launch_unproject(const float* features, const float* proj, const floa
       long n = (long)llround(cbrt((double)nvox));
       const int bs = opts().unproject_brick;
       if (bs > 0 && n * n * n == nvox && n % bs == 0 && (bs * bs * bs) % (256 / (32 / cpl)) == 0) {
-        p.brick_n = (int)n; p.brick = bs;
+        p.brick_n = (int)n; p.brick = bs; p.brick_order = opts().unproject_brick_order;
         const long nbricks = (n / bs) * (n / bs) * (n / bs);
         grid.x = (unsigned)(nbricks < (long)sm_count() * 8 ? nbricks : (long)sm_count() * 8);
       }

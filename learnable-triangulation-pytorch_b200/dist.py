@@ -92,6 +92,11 @@ class PeerExchange:
 
     def __init__(self, plan, pg, batch, planes, nvox, channels, device):
         import torch.distributed._symmetric_memory as symm_mem
+        if plan.n_groups > 1:
+            # measured on 8 GPUs (2 groups x 4): the symmetric-memory exchanges give wrong key points as soon as two view groups
+            # rendezvous side by side, while one group of 2 / 4 / 8 ranks is exact (tools/dist_probe.py, profiles/r02_dist_probe_*.log)
+            raise NotImplementedError("the peer-memory exchange is validated for ONE view group spanning all ranks; "
+                                      "use collective='all_reduce' / 'reduce_scatter' / 'features' with several groups")
         self.plan, self.pg = plan, pg
         per = batch // plan.group_size
         self.shape = (plan.group_size, per, planes, nvox, channels)
@@ -110,23 +115,43 @@ class FeatureExchange:
     """
 
     def __init__(self, plan, pg, batch, n_views, h, w, channels, device):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.plan = plan
+        self.plan, self.pg = plan, pg
         self.per = batch // plan.group_size
         self.shape = (self.per, n_views, h, w, channels)
+        self.n_views = n_views
+        # One view group spanning all ranks: symmetric memory + our own store kernel.  Several groups side by side (world 8, 4 views):
+        # the symmetric-memory path returned wrong key points on the B200 box (2 groups x 4 ranks; one group of 2 / 4 ranks is exact,
+        # tools/dist_probe.py), so the groups then exchange the same maps with one NCCL all-gather each and assemble locally.
+        self.nccl = plan.n_groups > 1
+        if self.nccl:
+            self.buf = torch.empty(self.shape, dtype=torch.float32, device=device)
+            self.gathered = None
+            return
+        import torch.distributed._symmetric_memory as symm_mem
         self.buf = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.buf, pg.group_name if hasattr(pg, "group_name") else pg)
         self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        self.n_views = n_views
 
     def scatter(self, feats_local):
         """feats_local: (B, V_local, h, w, C) -> rows of the owners' buffers: one launch of our own copy kernel whose float4
-        stores go straight into peer memory over NVLink (lt_feature_scatter_fwd)."""
+        stores go straight into peer memory over NVLink (lt_feature_scatter_fwd); NCCL variant: all-gather + local assembly."""
+        if self.nccl:
+            import torch.distributed as dist
+            G = self.plan.group_size
+            B, Vl = feats_local.shape[:2]
+            if self.gathered is None or self.gathered.shape[1:] != feats_local.shape:
+                self.gathered = torch.empty((G,) + tuple(feats_local.shape), dtype=torch.float32, device=feats_local.device)
+            dist.all_gather([self.gathered[r] for r in range(G)], feats_local.contiguous(), group=self.pg)
+            lo = self.plan.view_rank * self.per
+            # global view v = j * G + r is local view j of group rank r:  buf[bl, j, r] = gathered[r, lo + bl, j]
+            self.buf.view(self.per, Vl, G, *self.shape[2:]).copy_(self.gathered[:, lo:lo + self.per].permute(1, 2, 0, 3, 4, 5))
+            return
         from . import capi
         capi.feature_scatter(feats_local, self.peer_ptrs, self.plan.view_rank, self.n_views)
 
     def barrier(self):
-        self.handle.barrier()
+        if not self.nccl:
+            self.handle.barrier()
 
 
 def gather_keypoints(kp_local, plan, pg):

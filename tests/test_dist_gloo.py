@@ -80,3 +80,34 @@ def test_plan_partitions_views_and_samples():
             members = [p for p in plans if p.group_index == gi]
             assert sorted(v for p in members for v in p.views) == list(range(views))
             assert sorted(s for p in members for s in p.owned_samples(2 * g)) == list(range(2 * g))
+
+
+def _feature_worker(rank, world, port, n_views, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = lt_dist.make_plan(world, rank, n_views)
+        pg = lt_dist.new_view_groups(plan)
+        assert plan.n_groups > 1, "this test covers the several-groups (NCCL / gloo all-gather) variant of the feature exchange"
+        per, h, w, C = 3, 4, 5, 8
+        B = per * plan.group_size
+        g = torch.Generator().manual_seed(7 + plan.group_index)
+        feats_all = torch.randn(B, n_views, h, w, C, generator=g)             # the group's true maps, all views
+        fx = lt_dist.FeatureExchange(plan, pg, B, n_views, h, w, C, torch.device("cpu"))
+        fx.barrier()
+        fx.scatter(feats_all[:, plan.views].contiguous())
+        fx.barrier()
+        own = plan.owned_samples(B)
+        ret[rank] = bool(torch.equal(fx.buf, feats_all[own[0]:own[-1] + 1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_views", [(4, 2), (4, 6)])
+def test_feature_exchange_with_several_view_groups(world, n_views):
+    """world 4, 2 views -> 2 groups x 2 ranks (one view each); 6 views -> 2 groups x 2 ranks with 3 views per rank: every owner must end
+    up with exactly its samples' maps of ALL views, in global view order (the layout lt_unproject_aggregate_fwd reads)."""
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_feature_worker, args=(world, _free_port(), n_views, ret), nprocs=world, join=True)
+    assert len(ret) == world and all(ret.values()), dict(ret)

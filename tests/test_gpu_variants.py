@@ -120,7 +120,11 @@ def test_algebraic_heatmap_softmax_false_native_vs_torch_backend():
         got = m(images.to(DEV), proj.to(DEV), batch)
     assert rel_err(got[2].cpu().numpy(), want[2].numpy()) < 1e-3            # ReLU heat-maps
     assert float((got[1].cpu() - want[1]).abs().max()) < 0.05               # 2-D key points, pixels
-    assert float((got[0].cpu() - want[0]).abs().max()) < 1.0                # triangulated key points, mm
+    # triangulated key points, mm.  Two views only: the DLT turns a 0.05 px difference of a 2-D key point into millimetres, so the
+    # 3-D bar against the torch backend is loose, and the DLT itself is checked tightly on the native 2-D key points.
+    assert float((got[0].cpu() - want[0]).abs().max()) < 5.0
+    same_2d = multiview.triangulate_batch_of_points(proj, got[1].cpu(), confidences_batch=got[3].cpu(), backend="torch")
+    assert float((got[0].cpu() - same_2d).abs().max()) < 0.5          # float32 SVD in the torch op, fp64 Jacobi in the kernel
 
 
 def test_input_side_not_multiple_of_32():

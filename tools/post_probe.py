@@ -12,6 +12,14 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     ("unproject", {"LT_OPT_UNPROJECT_V2": "0"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_LB": "5"}),
     ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "0"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "4"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "8", "LT_OPT_UNPROJECT_BRICK_ORDER": "0"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "8", "LT_OPT_UNPROJECT_BRICK_ORDER": "1"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "8", "LT_OPT_UNPROJECT_BRICK_ORDER": "2"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "4", "LT_OPT_UNPROJECT_BRICK_ORDER": "2"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "16", "LT_OPT_UNPROJECT_BRICK_ORDER": "2"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "4", "LT_OPT_UNPROJECT_BRICK": "16", "LT_OPT_UNPROJECT_BRICK_ORDER": "1"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3", "LT_OPT_UNPROJECT_BRICK": "8", "LT_OPT_UNPROJECT_BRICK_ORDER": "1"}),
+    ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3", "LT_OPT_UNPROJECT_BRICK": "8", "LT_OPT_UNPROJECT_BRICK_ORDER": "2"}),
     ("unproject", {"LT_OPT_UNPROJECT_CPL": "8"}), ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3"}),
     ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3", "LT_OPT_UNPROJECT_BRICK": "4"}),
     ("unproject", {"LT_OPT_UNPROJECT_CPL": "8", "LT_OPT_UNPROJECT_LB": "3", "LT_OPT_UNPROJECT_BRICK": "0"}),
