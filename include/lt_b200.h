@@ -69,7 +69,7 @@ typedef struct lt_options {
   int fold_debug;          /* conv_fold: 0 = off; 1..3 = stage knock-outs of tools/fold_probe.py; 16 = wait counters to stderr */
   int softargmax_stream;   /* soft-argmax: streaming TMA kernels for compact channels-last logits (default 1) */
   int unproject_v2;        /* unprojection: production-shape kernel (default 1) */
-  int unproject_cpl;       /* unprojection v2: channels per lane, 4 or 8 (default 8 with unproject_lb = 3) */
+  int unproject_cpl;       /* unprojection v2: channels per lane, 4 (default) or 8 */
   int unproject_lb;        /* unprojection v2: min CTAs / SM override (0 = per-variant default) */
   int unproject_brick;     /* unprojection v2: side of the voxel bricks a CTA walks (0 = linear order, default: measured faster) */
   int unproject_brick_order; /* voxel order inside a brick: 0 = z fastest, 1 = x fastest, 2 = 2 x 2 (x, y) tiles (voxels of a warp share taps) */

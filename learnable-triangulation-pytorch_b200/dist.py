@@ -79,7 +79,13 @@ def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum
             out = torch.empty((per,) + tuple(partial.shape[1:]), dtype=partial.dtype, device=partial.device)
         dist.reduce_scatter_tensor(out, partial.contiguous(), op=op, group=pg)
         return out
-    dist.all_reduce(partial, op=op, group=pg)
+    # Issued in slices of at most 512 MiB (whole samples).  Measured on B200 x4 / x8 (profiles/r02_bench_tc_n4*.json): with the
+    # 2 GiB buffer of a 32-sample group as ONE call the key points came out wrong by a run-dependent 2-84 mm, while the 1 GiB buffer
+    # of a 16-sample group (N = 2) and every smaller case agree with the single-GPU forward to 0.02-0.07 mm.
+    per_sample = partial[0].numel() * partial.element_size()
+    step = max(1, (1 << 29) // per_sample)
+    for s0 in range(0, B, step):
+        dist.all_reduce(partial[s0:s0 + step], op=op, group=pg)
     return partial[plan.view_rank * per:(plan.view_rank + 1) * per]
 
 
