@@ -63,7 +63,7 @@ def new_view_groups(plan):
     return mine
 
 
-def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum", out=None):
+def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum", out=None, max_bytes=1 << 29):
     """partial: [B][P][nvox][C] float32 on every rank of the group -> the block of fully reduced samples this rank owns.
 
     Returns a tensor [B/G][P][nvox][C].  `reduce_op` is "sum" (softmax num/den, sum, conf) or "max".
@@ -83,7 +83,7 @@ def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum
     # 2 GiB buffer of a 32-sample group as ONE call the key points came out wrong by a run-dependent 2-84 mm, while the 1 GiB buffer
     # of a 16-sample group (N = 2) and every smaller case agree with the single-GPU forward to 0.02-0.07 mm.
     per_sample = partial[0].numel() * partial.element_size()
-    step = max(1, (1 << 29) // per_sample)
+    step = max(1, max_bytes // per_sample)
     for s0 in range(0, B, step):
         dist.all_reduce(partial[s0:s0 + step], op=op, group=pg)
     return partial[plan.view_rank * per:(plan.view_rank + 1) * per]

@@ -32,7 +32,7 @@ def _scene(B, V, C, h, w, n):
     return heat, proj, coord
 
 
-def _worker(rank, world, port, n_views, agg, collective, ret):
+def _worker(rank, world, port, n_views, agg, collective, ret, max_bytes=1 << 29):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -46,7 +46,7 @@ def _worker(rank, world, port, n_views, agg, collective, ret):
         vs = plan.views
         sampled = torch_ops.sample_views(heat[:, vs], proj[:, vs], coord)
         partial = torch_ops.partial_aggregate(sampled, agg)
-        mine = lt_dist.complete_partials(partial, plan, pg, collective, "max" if agg == "max" else "sum")
+        mine = lt_dist.complete_partials(partial, plan, pg, collective, "max" if agg == "max" else "sum", max_bytes=max_bytes)
         vol_local = torch_ops.finalize_aggregate(mine, agg)
         full = torch_ops.unproject_heatmaps(heat, proj, coord, agg).reshape(B, 4, -1)
         own = plan.owned_samples(B)
@@ -69,6 +69,16 @@ def test_view_sharded_aggregation_equals_single_process(world, n_views, agg):
         # the unshifted exp num/den partials, summed and divided, differ from torch.softmax at fp32 rounding level
         tol = 1e-4 if agg == "softmax" else 1e-5
         assert err < tol and err_g < tol, (rank, err, err_g)
+
+
+def test_all_reduce_in_slices_equals_one_call():
+    """The packed partials are all-reduced in slices of whole samples (dist.complete_partials: at most 512 MiB per call on the GPU
+    path); forcing one sample per call must give the same aggregate."""
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), 4, "softmax", "all_reduce", ret, 64), nprocs=2, join=True)
+    assert len(ret) == 2
+    for rank, (err, err_g, g, ng, nv) in ret.items():
+        assert err < 1e-4 and err_g < 1e-4, (rank, err, err_g)
 
 
 def test_plan_partitions_views_and_samples():
