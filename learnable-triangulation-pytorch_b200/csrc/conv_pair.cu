@@ -7,24 +7,27 @@
 // halves, and each CTA's accumulator (its 128 rows x Nt fp32 columns) lives in its own TMEM.  At Nt = 256 a CTA ingests
 // 32 KB per 768 math cycles (42 B/clk) instead of 32 KB per 384.
 //
-// Precision: split-fp16 operands with UNSCALED low parts (common.cuh): the three products hi*hi, hi*lo, lo*hi of a 16-wide
-// K slice accumulate into ONE fp32 accumulator (Nt TMEM columns per stage; two stages so the epilogue of tile i overlaps
-// the main loop of tile i+1).  Weights: [tap][Cin/32][CoutP rows][32 hi | 32 lo] fp16 = 128-byte rows, 128B swizzle, so the
-// K slices of both operands are descriptor offsets (+0,+2 hi; +4,+6 lo, in 16-byte units) into MMA-ready rows.
+// Precision: split-fp16 operands with UNSCALED low parts (common.cuh), three products per 16-wide K slice.  hi*hi accumulates into
+// D1, hi*lo + lo*hi into D2 (Nt columns further), and the epilogue adds them in fp32 RN (lt_options.pair_two_acc = 1, default): tcgen05
+// truncates every accumulation step, so the big accumulator must see as few steps as possible (pair_plan()).  2 x Nt columns per
+// stage: two stages for Nt = 128, ONE for Nt = 256 (then the epilogue of tile i does not overlap the main loop of tile i+1).
+// pair_two_acc = 0: all three products into one accumulator of Nt columns, two stages.  Weights: [tap][Cin/32][CoutP rows][32 hi | 32 lo]
+// fp16 = 128-byte rows, 128B swizzle, so the K slices of both operands are descriptor offsets (+0,+2 hi; +4,+6 lo, in 16-byte units).
 //
 // Persistent: grid = 2 x min(#SM / 2, tiles); pair k walks tiles k, k + P, ...  (tile = (pair of M tiles, N tile), N fastest
 // so that concurrently running pairs share the activation tile in L2).
 //
-// Warp roles per CTA (320 threads): warp 0 TMA producer (both CTAs), warp 1 TMEM allocator + MMA issuer (leader CTA only),
-// warps 2..9 epilogue (both CTAs, each draining its own TMEM lanes): tcgen05.ld -> scale/shift (+ residual tile that arrived
-// by TMA) -> ReLU -> split-fp16 repack into a swizzled smem tile -> TMA store (also implements the stride-phase mapping).
+// Warp roles per CTA (608 threads): warp 0 TMA producer (both CTAs), warp 1 TMEM allocator + MMA issuer (leader CTA only),
+// warps 2..17 two epilogue groups of 8 warps (both CTAs, each draining its own TMEM lanes), warp 18 residual producer.
+// Staged epilogue (float32 outputs; group 0 only): tcgen05.ld -> scale/shift (+ residual tile that arrived by TMA) -> ReLU ->
+// repack into a swizzled smem tile -> TMA store (also implements the stride-phase mapping).
 //
 // Barriers (same smem offsets in both CTAs):
 //   full[s]       leader's copy is used: 1 arrival (leader producer's expect_tx of both CTAs' bytes) + complete_tx of all four
 //                 TMA loads (the non-leader's loads signal the leader's barrier through the .cta_group::2 form)
 //   empty[s]      per CTA; tcgen05.commit multicast from the leader frees the slot in both CTAs
 //   acc_full[a]   per CTA; commit multicast when a tile's last MMA has completed
-//   acc_empty[a]  leader's copy is used: 16 arrivals = 8 epilogue warps x 2 CTAs (remote mbarrier.arrive from the peer)
+//   acc_empty[a]  leader's copy is used: 16 (staged) / 32 (direct) arrivals = epilogue warps x 2 CTAs (remote mbarrier.arrive from the peer)
 //   res_full[b] / res_empty[b]  per CTA: residual staging buffer b filled by TMA / read by the 8 warps of the group that owns it
 //
 // Direct-store epilogue (split-fp16 outputs): no CTA-level barrier at all.  The per-channel scale / shift sit in shared memory

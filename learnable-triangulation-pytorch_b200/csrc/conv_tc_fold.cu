@@ -7,10 +7,10 @@
 // Here the kw taps are folded into the MMA's N dimension:
 //     D[(line, xi)][kw*NC + co] = sum_{kd,kh,ci} in[z+kd-p][y+line+kh-p][x0-p+xi][ci] * W[kd][kh][kw][ci][co]
 //     out[(line, xo)][co]       = sum_kw D[(line, xo+kw)][kw*NC + co]          (shift-add in the epilogue)
-// so one un-shifted 16-position line tile feeds N = K*NC = 96 / 112 columns (MMA is math-bound, not A-read-bound),
-// a z-slab of (8+K-1) lines is loaded ONCE per kd and reused for all kh via the descriptor start address, and
-// the 3^3 weights (108 KB) stay resident in shared memory for the whole persistent CTA.  Each M tile yields
-// 16-K+1 output positions per line (14 for K=3, 10 for K=7).
+// so one un-shifted line tile feeds N = K*NC = 96 / 112 columns (MMA is math-bound, not A-read-bound),
+// a z-slab of (LINES+K-1) lines is loaded ONCE per kd and reused for all kh via the descriptor start address, and
+// the 3^3 weights (108 KB) stay resident in shared memory for the whole persistent CTA.  Full-width mode (W = 16 / 32 / 64:
+// the M tile spans whole lines) keeps every row; otherwise a 16- / 32-row x window yields 16-K+1 / 32-K+1 outputs per line.
 //
 // Products: activations are split-fp16 rows [32 hi | 32 lo]; the weights of a (kd,kh) step are stored as a
 // 2*NF-row, 64-byte-swizzled tile  [hi rows (kw,co) ; lo rows (kw,co)] x 32 channels, so that per 16-wide K slice
@@ -19,7 +19,7 @@
 // i.e. two MMAs instead of three (a single-CTA SS-mode UMMA costs ~(128 + N)/2 cycles of operand fetch).
 //
 // Persistent CTAs (one per SM), warp roles as in conv_tc.cu; TMEM holds two accumulator stages of 2*NF columns
-// (hi*hi and the 2^11-scaled cross terms) so the epilogue of tile i overlaps the MMAs of tile i+1; the epilogue
+// (hi*hi and the cross terms) so the epilogue of tile i overlaps the MMAs of tile i+1; the epilogue
 // shift-adds with warp shuffles, applies scale/shift/residual/ReLU, compacts the valid rows into a 128B-swizzled
 // staging tile and stores it with TMA (which also clips partial tiles).
 #include "tc_common.cuh"
