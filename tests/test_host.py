@@ -104,3 +104,42 @@ def test_native_backend_refuses_cpu_tensors_and_training():
         op.unproject_heatmaps(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 1, 3, 4), torch.zeros(1, 2, 2, 2, 3))
     with pytest.raises(ValueError):
         op.unproject_heatmaps(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 1, 3, 4), torch.zeros(1, 2, 2, 2, 3), "median")
+
+
+def test_header_is_plain_c_and_the_library_is_callable_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/lt_b200.h must compile as C99 (no C++-isms, no torch types) and a plain C program must be
+    able to dlopen the library and call it (no GPU work here: version, default options, error string of a rejected call)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_lt.c"
+    src.write_text(r'''
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include "lt_b200.h"
+int main(int argc, char** argv) {
+  void* h = dlopen(argv[1], RTLD_NOW);
+  if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
+  int (*version)(void) = (int (*)(void))dlsym(h, "lt_version");
+  void (*defaults)(lt_options*) = (void (*)(lt_options*))dlsym(h, "lt_default_options");
+  const char* (*last_error)(void) = (const char* (*)(void))dlsym(h, "lt_last_error_string");
+  int (*coord)(const float*, const float*, const float*, const float*, float*, int, int, int, void*) =
+      (int (*)(const float*, const float*, const float*, const float*, float*, int, int, int, void*))dlsym(h, "lt_coord_volume_fwd");
+  if (!version || !defaults || !last_error || !coord) return 3;
+  lt_options o;
+  memset(&o, 0xff, sizeof o);
+  defaults(&o);
+  int rc = coord(0, 0, 0, 0, 0, 1, 64, 0, 0);          /* null pointers: must be rejected with a message, not crash */
+  printf("%d %d %d %d %s\n", version(), o.tc_splitk, o.pair_two_acc, rc, last_error());
+  return 0;
+}
+''')
+    exe = tmp_path / "use_lt"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), "-ldl"], check=True)
+    capi.lib()
+    out = subprocess.run([str(exe), capi.LIB_PATH], capture_output=True, text=True, check=True).stdout.split(None, 4)
+    assert int(out[0]) >= 100 and int(out[1]) == 1 and int(out[2]) == 1
+    assert int(out[3]) < 0 and "null pointer" in out[4]
