@@ -75,6 +75,10 @@ def complete_partials(partial, plan, pg, collective="all_reduce", reduce_op="sum
     B = partial.shape[0]
     per = B // plan.group_size
     if collective == "reduce_scatter":
+        if partial.numel() * partial.element_size() >= (1 << 31):
+            # see below: a single 2 GiB collective on this buffer gave wrong sums on B200 x4; the all-reduce is sliced, the
+            # reduce-scatter (one output block per rank) is not
+            raise NotImplementedError("reduce_scatter of a packed buffer >= 2 GiB is not validated; use collective='all_reduce' or 'features'")
         if out is None:
             out = torch.empty((per,) + tuple(partial.shape[1:]), dtype=partial.dtype, device=partial.device)
         dist.reduce_scatter_tensor(out, partial.contiguous(), op=op, group=pg)
