@@ -501,7 +501,8 @@ def main_native(args, rank, world, local_rank):
         else:
             # ---- view-sharded: G ranks share a group batch of B*G samples and split its views; W/G groups are replicas ----
             arm = ShardedArm(args, model, world, rank, dev, V)
-            names = ["all_reduce", "features"] if args.collective == "both" else [args.collective]
+            # `features` first: if the contract all-reduce misbehaves at some size it cannot disturb the other measurement
+            names = ["features", "all_reduce"] if args.collective == "both" else [args.collective]
             results = {}
             sampler = ClockSampler(local_rank)
             sampler.start()
